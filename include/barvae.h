@@ -1,0 +1,205 @@
+/*
+ * barvae.h -- C ABI of libbarvae.so: the B200 (sm_100a) kernels behind the bar-VAE train / decode hot path.
+ *
+ * The reference (KMU-AELAB-MusicProject/MusicGeneration_VAE-torch) has no native layer: every op on the path is a
+ * stock torch.nn layer.  The seam this library sits under is therefore the set of ATen ops
+ * the reference's nn.Modules dispatch; each entry point below names the reference lines whose work it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); the library never frees or
+ *     retains one beyond the call; all scratch is passed in explicitly.
+ *   - every call is asynchronous on the given stream (a cudaStream_t passed as void*).
+ *   - return value: 0 = ok, otherwise a BVAE_ERR_* code; bvae_last_error() gives the message (thread local).
+ *   - activations: NHWC, bf16, addressed as ptr[((n*H + h)*W + w)*pitch + c]; `pitch` (elements per pixel)
+ *     may exceed C so that a branch can write straight into its slice of a concatenated tensor
+ *     (torch.cat at graph/encoder.py:30, graph/decoder.py:100,145,208 is never materialised).
+ *   - parameters and their gradients: fp32, in the reference's own state_dict layouts.
+ */
+#ifndef BARVAE_H_
+#define BARVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BVAE_OK 0
+#define BVAE_ERR_SHAPE 1
+#define BVAE_ERR_ALIGN 2
+#define BVAE_ERR_ARCH 3
+#define BVAE_ERR_CUDA 4
+#define BVAE_ERR_UNSUPPORTED 5
+
+#define BVAE_MAX_TAPS 16
+
+/* implementation selector for the contraction kernels */
+#define BVAE_IMPL_AUTO 0  /* tcgen05 when the shape allows, else SIMT */
+#define BVAE_IMPL_SIMT 1  /* CUDA-core reference kernel (debug / odd shapes such as C_in = 1) */
+#define BVAE_IMPL_TC 2    /* tcgen05 + TMEM + TMA; error if the shape is not eligible */
+
+int bvae_version(void);
+const char* bvae_last_error(void);
+/* number of kernels launched by this library since load / since the last reset (bench.py's gpu_launches) */
+uint64_t bvae_launch_count(void);
+void bvae_launch_count_reset(void);
+/* 1 if the current device is sm_100 (B200); kernels refuse to run elsewhere */
+int bvae_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution  (forward of Conv2d / ConvTranspose2d / Linear and their data gradients).
+ *
+ *   out[n, qy*osy+ooy, qx*osx+oox, co] = epi( sum_{t < ntaps} sum_{c < C}
+ *                                              x[n, qy*sy + dy[t], qx*sx + dx[t], c] * w[co, t*C + c] )
+ *   for qy < QH, qx < QW; out-of-range input pixels contribute zero (padding).
+ *   epi(v) = act(v + bias[co]) (+ addend) (* act'(mask))  ->  bf16 or fp32 store.
+ *
+ * One call covers one "phase": a strided transposed convolution is 4 calls (sub-pixel decomposition), a
+ * k == stride transposed convolution is one call per tap.  Replaces aten::convolution as dispatched by
+ * nn.Conv2d (graph/encodingBlock.py:12-15,43-46,74-77,107-108; graph/decoder.py:79,122,172,175),
+ * nn.ConvTranspose2d (graph/decoder.py:12-15,43-46,73-77,116-120), nn.Linear (graph/encoder.py:22,
+ * graph/phrase_encoder.py:23, graph/decoder.py:166-167) and their convolution_backward data-gradient halves.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct bvae_conv_desc {
+  const void* x;     /* bf16 NHWC [N, H, W, C], pitch x_pitch */
+  const void* w;     /* bf16 [Cout, w_pitch] rows; this phase uses columns [0, ntaps*C) (K-major, tap-major) */
+  void* y;           /* bf16 (or fp32 if out_f32) NHWC [N, OH, OW, Cout], pitch y_pitch */
+  const float* bias; /* [Cout] or NULL */
+  const void* addend; /* same geometry/dtype as y (pitch add_pitch) or NULL: out += addend */
+  const void* mask;  /* bf16, same geometry as y (pitch mask_pitch) or NULL: out *= (mask > 0 ? 1 : mask_slope) */
+  int32_t N, H, W, C, x_pitch;
+  int32_t Cout, w_pitch;
+  int32_t ntaps;
+  int32_t dy[BVAE_MAX_TAPS], dx[BVAE_MAX_TAPS];
+  int32_t sy, sx;    /* input stride */
+  int32_t QH, QW;    /* output grid of this phase */
+  int32_t OH, OW, y_pitch;
+  int32_t osy, osx, ooy, oox; /* output stride / offset of this phase */
+  int32_t add_pitch, mask_pitch;
+  int32_t act;       /* 0 none, 1 leaky-relu with `slope` (0 = ReLU) applied after bias */
+  int32_t out_f32;
+  float slope, mask_slope;
+} bvae_conv_desc;
+
+int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight gradient of the same contractions:
+ *   dw[(ra*Cs + rs)*T + tap_idx[t]] (+)= sum_{n, ay, ax} a[n, ay, ax, ra] * s[n, ay*sy + dy[t], ax*sx + dx[t], rs]
+ * a = "anchor" tensor (dY for Conv2d/Linear, X for ConvTranspose2d), s = "shifted" tensor (the other one).
+ * dw is fp32 in the reference parameter layout (Conv2d [Cout][Cin][kh*kw], ConvTranspose2d [Cin][Cout][kh*kw]);
+ * the result is ACCUMULATED (atomically) -- zero it first for a plain gradient.
+ * Replaces the weight-gradient half of aten::convolution_backward / addmm backward for the layers listed above.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct bvae_wgrad_desc {
+  const void* a;  /* bf16 NHWC [N, AH, AW, Ca], pitch a_pitch */
+  const void* s;  /* bf16 NHWC [N, SH, SW, Cs], pitch s_pitch */
+  float* dw;
+  int32_t N, AH, AW, Ca, a_pitch;
+  int32_t SH, SW, Cs, s_pitch;
+  int32_t sy, sx;
+  int32_t ntaps, T;
+  int32_t dy[BVAE_MAX_TAPS], dx[BVAE_MAX_TAPS], tap_idx[BVAE_MAX_TAPS];
+} bvae_wgrad_desc;
+
+int bvae_wgrad_gemm(const bvae_wgrad_desc* d, int impl, void* stream);
+
+/* fp32 parameter (reference layout) -> bf16 GEMM operand:
+ *   dst[r*dst_pitch + tp*Cc + c] = bf16(src[r*sr + c*sc + perm[tp]])   r < R, tp < T, c < Cc   */
+int bvae_pack_weight(const float* src, void* dst, int R, int T, int Cc, int64_t sr, int64_t sc,
+                     const int32_t* perm /* host array [T] */, int dst_pitch, void* stream);
+
+/* column sums: out[c] += sum over rows of x[row*pitch + c]  (bias gradients; x bf16 or fp32) */
+int bvae_colsum(const void* x, int x_f32, int64_t rows, int C, int pitch, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * "Norm block": InstanceNorm2d(affine) [+ CBAM] [+ residual] + (Leaky)ReLU on a raw convolution output.
+ *
+ *   u   = (y - mean_nc) * rstd_nc * gamma_c + beta_c                       (graph/encodingBlock.py:30,61,92,120)
+ *   cb  = u * gc[n,c] * gs[n,h,w]                                          (graph/cbam.py:22-29,43-52,64-68)
+ *         gc = sigmoid(W2 relu(W1 avgpool(u)) + W2 relu(W1 maxpool(u)))
+ *         gs = sigmoid(conv3x3_{2->1}([mean_c(u*gc), max_c(u*gc)]))
+ *   out = act( res_mode 0: u | 1: u + cb | 2: res + cb | 3: cb )
+ * Replaces aten::instance_norm, adaptive_avg/max_pool2d, the 1x1 MLP convs, mean/max over C, cat, the 3x3
+ * attention conv, sigmoid, mul, add and (leaky_)relu at every site listed in SURVEY.md section 8 rows a3-a14.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct bvae_nb_desc {
+  int32_t N, H, W, C;
+  int32_t y_pitch, out_pitch, res_pitch, dout_pitch, dy_pitch, dres_pitch;
+  int32_t has_cbam, Cr, res_mode; /* res_mode: 0 u | 1 u + cbam(u) | 2 res + cbam(u) | 3 cbam(u) */
+  int32_t y_f32;        /* raw conv output dtype: 1 = fp32 (default: survives |mean| >> std), 0 = bf16 */
+  float slope, eps;
+  const void* y;        /* raw conv output [N,H,W,C] (forward only; not needed by backward) */
+  void* uhat;           /* bf16 [N,H,W,C] dense: normalised activations, saved for backward */
+  void* out;            /* bf16 block output */
+  void* stats;          /* forward scratch, 24*N*C bytes */
+  const void* res;      /* bf16 external residual (res_mode 2) */
+  const float* gamma;   /* [C] */
+  const float* beta;    /* [C] */
+  const float* w1;      /* [Cr][C]  channel_attention.conv1.weight */
+  const float* w2;      /* [C][Cr]  channel_attention.conv2.weight */
+  const float* wsp;     /* [2][3][3] spatial_attention.conv.weight */
+  /* saved per block (caller-allocated) */
+  float* nc;            /* [N][C][8]: mean, rstd, a, b, gc, ext_u (max-pooled u), ext_uhat, spare */
+  int32_t* nc_idx;      /* [N][C]: pixel index of the max-pooled element */
+  float* sa;            /* [N][H*W][2]: mean_c, max_c of u*gc */
+  int32_t* cidx;        /* [N][H*W]: argmax channel */
+  float* gs;            /* [N][H*W] */
+  /* backward */
+  const void* dout;     /* bf16 grad wrt out */
+  void* dy;             /* bf16 grad wrt y (also used as scratch for du) */
+  void* dres;           /* bf16 grad wrt res (res_mode 2) or NULL */
+  float* dgamma;        /* [C], accumulated */
+  float* dbeta;         /* [C], accumulated */
+  float* dw1;           /* accumulated */
+  float* dw2;           /* accumulated */
+  float* dwsp;          /* accumulated */
+  float* bwd_nc;        /* scratch [N][C][4]: dgc, S1, S2, dmx  (zeroed by the call) */
+  float* bwd_px;        /* scratch [N][H*W][4]: dq, dsa_mean, dsa_max, spare */
+} bvae_nb_desc;
+
+int bvae_nb_forward(const bvae_nb_desc* d, void* stream);
+int bvae_nb_backward(const bvae_nb_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fit2 (1x1 conv 64->1) + sigmoid + BCE(mean, log clamp -100) [+ pitch-prior label smoothing] + the
+ * non-differentiable missed-note count  (graph/decoder.py:175,220; graph/loss/bar_loss.py:23-33).
+ *   x [rows, C] bf16 (rows = N*96*60), w [C] fp32, target [rows] fp32 {0,1}
+ *   recon [rows] fp32 = sigmoid(x.w);  loss_out[0] += BCE sum / rows;  loss_out[1] += missed-note count
+ * smoothing: 0 = pre-training (plain labels), 1 = 0.82*t + 0.1/60 + 0.08*prior[pitch], pitch = row % 60.
+ * Backward: dx[row, c] = g[row] * w[c],  dw[c] += sum_row g[row]*x[row,c],
+ *   g = gscale * (p - t') / max(p(1-p), 1e-12) * p(1-p)    (BCELoss backward then sigmoid backward, as autograd)
+ * ------------------------------------------------------------------------------------------------------------ */
+int bvae_fit_sigmoid_fwd(const void* x, int x_pitch, const float* w, int64_t rows, int C, float* logits,
+                         float* recon, void* stream);
+int bvae_bce_fwd(const float* recon, const float* target, int64_t rows, int smoothing, float* loss_out,
+                 void* stream);
+/* autograd's BCELoss backward alone: drecon[i] = gscale * (p - t') / max(p(1-p), 1e-12)   (gscale = dL / rows) */
+int bvae_bce_bwd(const float* recon, const float* target, int64_t rows, int smoothing, float gscale, float* drecon,
+                 void* stream);
+int bvae_fit_sigmoid_bce_bwd(const void* x, int x_pitch, const float* w, const float* recon, const float* target,
+                             const float* drecon /* NULL: use BCE grad with gscale */, float gscale, int smoothing,
+                             int64_t rows, int C, void* dx, int dx_pitch, float* dw, void* stream);
+
+/* reparameterise + KL  (old/graphs/models/bar_v1/encoder.py:60-63, old/graphs/losses/loss.py:16)
+ *   z = mu + eps*exp(0.5*logvar);  kl_out[0] += -0.5*sum(1 + logvar - mu^2 - exp(logvar))
+ *   backward: dmu = dz + gkl*mu ; dlogvar = dz*eps*0.5*exp(0.5*logvar) + gkl*0.5*(exp(logvar) - 1) */
+int bvae_reparam_kl_fwd(const float* mu, const float* logvar, const float* eps, float* z, float* kl_out,
+                        int64_t n, void* stream);
+int bvae_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, const float* dz, float gkl,
+                        float* dmu, float* dlogvar, int64_t n, void* stream);
+
+/* torch.optim.Adam (agent/barGen.py:61-62,327,333) on ONE flat fp32 bucket holding every generator parameter
+ * (p, g, m, v each contiguous, 16-byte aligned): p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps), g is
+ * pre-multiplied by grad_scale (1/world_size when the bucket holds an NCCL sum).  16 B read + 12 B written/param. */
+int bvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+                   int step, float grad_scale, void* stream);
+
+/* fp32 -> bf16 cast of a contiguous buffer (piano-roll inputs: [N,1,H,W] with C == 1 is already NHWC) */
+int bvae_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BARVAE_H_ */

@@ -1,0 +1,27 @@
+"""Same attribute names as the reference's config.py:1-20, plus the knobs the B200 path adds."""
+
+
+class Config(object):
+    epoch = 5000
+    batch_size = 8
+    learning_rate = 0.002
+
+    sigma = 1.0
+
+    cuda = True
+    gpu_cnt = 4            # reference: nn.DataParallel device count; here informational (one process per GPU)
+
+    async_loading = True
+    pin_memory = True
+
+    root_path = '.'
+    data_path = 'data/dataset'
+    checkpoint_dir = 'model'
+    checkpoint_file = 'checkpoint.pth.tar'
+    summary_dir = 'board'
+
+    pretraining_step_size = 220
+
+    # --- additions ---
+    bucket_mb = 64         # NCCL gradient bucket size
+    vae_head = False

@@ -1,0 +1,768 @@
+// normblock.cu -- InstanceNorm2d(affine) [+ CBAM] [+ residual] + (Leaky)ReLU, forward and backward.
+// All kernels are HBM-bound sweeps over NHWC tensors: a pixel's C channels are covered by G = min(32, C/8)
+// lanes doing 16-byte loads (ITERS = C/(8G) rounds), per-pixel reductions are warp shuffles inside the lane
+// group, per-(n,c) reductions go registers -> shuffle -> shared atomics -> one global atomic per CTA.
+#include "common.cuh"
+
+namespace bvae {
+
+typedef unsigned long long u64;
+
+// nc layout (floats per (n,c))
+enum { NC_MEAN = 0, NC_RSTD = 1, NC_A = 2, NC_B = 3, NC_GC = 4, NC_EXTU = 5, NC_EXTUHAT = 6, NC_SPARE = 7, NC_W = 8 };
+// bwd_nc layout
+enum { BN_DGC = 0, BN_S1 = 1, BN_S2 = 2, BN_DMX = 3, BN_W = 4 };
+// bwd_px layout
+enum { BP_DQ = 0, BP_DMEAN = 1, BP_DMAX = 2, BP_W = 4 };
+
+template <bool F32>
+__device__ __forceinline__ void load8(const void* base, int64_t off, float* f) {
+  if (F32) ldg8f((const float*)base + off, f);
+  else unpack8(ldg8((const bf16*)base + off), f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward 1: per-(n,c) shifted sums and extrema (with first-index tie break) of the raw conv output
+// grid (ceil(C/256), psplit, N), block 256
+// ---------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void __launch_bounds__(256) nb_stats_kernel(const void* __restrict__ y, int pitch, int HW, int C,
+                                                       int psplit, float2* __restrict__ ss, u64* __restrict__ kmax,
+                                                       u64* __restrict__ kmin) {
+  __shared__ float s_sum[256], s_sq[256];
+  __shared__ u64 s_kmax[256], s_kmin[256];
+  const int Cc = min(C, 256);
+  const int G = Cc / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int cl = sub * 8;                       // channel offset inside this chunk
+  const int c0 = blockIdx.x * 256 + cl;
+  const int n = blockIdx.z;
+  const int pps = ceil_div(HW, psplit);
+  const int p_begin = blockIdx.y * pps, p_end = min(HW, p_begin + pps);
+  const int64_t base = (int64_t)n * HW * pitch;
+  s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; s_kmax[threadIdx.x] = 0; s_kmin[threadIdx.x] = 0;
+  __syncthreads();
+
+  float shift[8], sum[8], sq[8];
+  u64 kx[8], kn[8];
+  load8<F32>(y, base + c0, shift);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; kx[i] = 0; kn[i] = 0; }
+  for (int p = p_begin + warp * gpw + grp; p < p_end; p += 8 * gpw) {
+    float v[8];
+    load8<F32>(y, base + (int64_t)p * pitch + c0, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dlt = v[i] - shift[i];
+      sum[i] += dlt;
+      sq[i] += dlt * dlt;
+      const u64 a = make_key(v[i], (uint32_t)p), b = make_key(-v[i], (uint32_t)p);
+      kx[i] = a > kx[i] ? a : kx[i];
+      kn[i] = b > kn[i] ? b : kn[i];
+    }
+  }
+  for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], o);
+      sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+      const u64 a = __shfl_xor_sync(0xffffffffu, kx[i], o), b = __shfl_xor_sync(0xffffffffu, kn[i], o);
+      kx[i] = a > kx[i] ? a : kx[i];
+      kn[i] = b > kn[i] ? b : kn[i];
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_sum[cl + i], sum[i]);
+      atomicAdd(&s_sq[cl + i], sq[i]);
+      atomicMax(&s_kmax[cl + i], kx[i]);
+      atomicMax(&s_kmin[cl + i], kn[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < Cc) {
+    const int64_t o = (int64_t)n * C + blockIdx.x * 256 + threadIdx.x;
+    if (psplit == 1) {
+      ss[o] = make_float2(s_sum[threadIdx.x], s_sq[threadIdx.x]);
+      kmax[o] = s_kmax[threadIdx.x];
+      kmin[o] = s_kmin[threadIdx.x];
+    } else {
+      atomicAdd(&ss[o].x, s_sum[threadIdx.x]);
+      atomicAdd(&ss[o].y, s_sq[threadIdx.x]);
+      atomicMax(&kmax[o], s_kmax[threadIdx.x]);
+      atomicMax(&kmin[o], s_kmin[threadIdx.x]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward 2: per-sample coefficients (mean, rstd, a, b), max-pooled value, channel-attention MLP -> gc
+// grid N, block 256, dynamic smem (2*C + 64) floats
+// ---------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y, int pitch, int HW, int C,
+                                                      const float2* __restrict__ ss, const u64* __restrict__ kmax,
+                                                      const u64* __restrict__ kmin, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float eps, int has_cbam,
+                                                      int Cr, const float* __restrict__ w1,
+                                                      const float* __restrict__ w2, float* __restrict__ nc,
+                                                      int32_t* __restrict__ nc_idx) {
+  extern __shared__ float sm[];
+  float* s_avg = sm;          // [C]
+  float* s_mx = sm + C;       // [C]
+  float* s_h = sm + 2 * C;    // [Cr]
+  const int n = blockIdx.x;
+  const int64_t base = (int64_t)n * HW * pitch;
+  const float inv = 1.f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int64_t o = (int64_t)n * C + c;
+    const float shift = F32 ? ((const float*)y)[base + c] : bf2f(((const bf16*)y)[base + c]);
+    const float2 s = ss[o];
+    const float md = s.x * inv;
+    const float mean = shift + md;
+    const float var = fmaxf(s.y * inv - md * md, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma[c], b0 = beta[c];
+    const float a = g * rstd, b = b0 - mean * a;
+    float yext; uint32_t idx;
+    if (a >= 0.f) { const u64 k = kmax[o]; yext = key_val(k); idx = key_idx(k); }
+    else { const u64 k = kmin[o]; yext = -key_val(k); idx = key_idx(k); }
+    const float ext_uhat = (yext - mean) * rstd;
+    const float ext_u = g * ext_uhat + b0;
+    float* q = nc + o * NC_W;
+    q[NC_MEAN] = mean; q[NC_RSTD] = rstd; q[NC_A] = a; q[NC_B] = b;
+    q[NC_EXTU] = ext_u; q[NC_EXTUHAT] = ext_uhat; q[NC_GC] = 1.f; q[NC_SPARE] = 0.f;
+    nc_idx[o] = (int32_t)idx;
+    s_avg[c] = b0;      // mean over H*W of an instance-normalised map is exactly beta
+    s_mx[c] = ext_u;
+  }
+  if (!has_cbam) return;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = warp; j < Cr; j += 8) {
+    float pa = 0.f, pm = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float w = w1[(int64_t)j * C + c];
+      pa += w * s_avg[c];
+      pm += w * s_mx[c];
+    }
+    pa = warp_sum(pa);
+    pm = warp_sum(pm);
+    if (lane == 0) s_h[j] = fmaxf(pa, 0.f) + fmaxf(pm, 0.f);   // W2 is linear: W2 ha + W2 hm = W2 (ha + hm)
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = 0.f;
+    for (int j = 0; j < Cr; ++j) v += w2[(int64_t)c * Cr + j] * s_h[j];
+    nc[((int64_t)n * C + c) * NC_W + NC_GC] = 1.f / (1.f + expf(-v));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward 3: sweep raw y: write uhat (bf16); with CBAM: per-pixel mean_c / max_c / argmax_c of u*gc;
+// without CBAM: write out = act(u) directly.      grid (pchunks, N), block 256, dyn smem 5*C floats
+// ---------------------------------------------------------------------------------------------------
+template <bool F32, int ITERS>
+__global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y, int y_pitch, int HW, int C,
+                                                      const float* __restrict__ nc, int has_cbam, float slope,
+                                                      bf16* __restrict__ uhat, bf16* __restrict__ out,
+                                                      int out_pitch, float* __restrict__ sa,
+                                                      int32_t* __restrict__ cidx, int ppc) {
+  extern __shared__ float sm[];
+  float* s_mean = sm; float* s_rstd = sm + C; float* s_a = sm + 2 * C; float* s_b = sm + 3 * C; float* s_gc = sm + 4 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* q = nc + ((int64_t)n * C + c) * NC_W;
+    s_mean[c] = q[NC_MEAN]; s_rstd[c] = q[NC_RSTD]; s_a[c] = q[NC_A]; s_b[c] = q[NC_B]; s_gc[c] = q[NC_GC];
+  }
+  __syncthreads();
+  const int G = min(32, C / 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
+  const int64_t ybase = (int64_t)n * HW * y_pitch, ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
+    const int p = pb + grp;
+    const bool valid = p < p_end;
+    float sum = 0.f, mx = -INFINITY;
+    int mxc = 0;
+    if (valid) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = (it * G + sub) * 8;
+        float v[8], uh[8];
+        load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uh[i] = (v[i] - s_mean[c + i]) * s_rstd[c + i];
+        stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
+        if (has_cbam) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float u1 = (s_a[c + i] * v[i] + s_b[c + i]) * s_gc[c + i];
+            sum += u1;
+            if (u1 > mx) { mx = u1; mxc = c + i; }
+          }
+        } else {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = act_fwd(s_a[c + i] * v[i] + s_b[c + i], slope);
+          stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
+        }
+      }
+    }
+    if (has_cbam) {
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+        if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+      }
+      if (valid && sub == 0) {
+        const int64_t o = (int64_t)n * HW + p;
+        sa[o * 2] = sum / (float)C;
+        sa[o * 2 + 1] = mx;
+        cidx[o] = mxc;
+      }
+    }
+  }
+}
+
+// 3x3 attention conv on the [mean, max] map (zero padding), one pixel
+__device__ __forceinline__ float sa_conv(const float* __restrict__ sa_n, const float* __restrict__ wsp, int H, int W,
+                                         int py, int px) {
+  float q = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float2 v = *reinterpret_cast<const float2*>(sa_n + ((int64_t)yy * W + xx) * 2);
+      q += wsp[ky * 3 + kx] * v.x + wsp[9 + ky * 3 + kx] * v.y;
+    }
+  }
+  return q;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward 4 (CBAM only): gs = sigmoid(conv3x3(sa)); out = act(r + u*gc*gs)
+// grid (pchunks, N), block 256, dyn smem 3*C floats
+// ---------------------------------------------------------------------------------------------------
+template <int ITERS>
+__global__ void __launch_bounds__(256) nb_apply_kernel(const bf16* __restrict__ uhat, int H, int W, int C,
+                                                       const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float* __restrict__ wsp,
+                                                       const float* __restrict__ sa, int res_mode,
+                                                       const bf16* __restrict__ res, int res_pitch, float slope,
+                                                       bf16* __restrict__ out, int out_pitch, float* __restrict__ gs,
+                                                       int ppc) {
+  extern __shared__ float sm[];
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C;
+  __shared__ float s_w[18];
+  const int n = blockIdx.y, HW = H * W;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_g[c] = gamma[c]; s_b[c] = beta[c];
+    s_gc[c] = nc[((int64_t)n * C + c) * NC_W + NC_GC];
+  }
+  if (threadIdx.x < 18) s_w[threadIdx.x] = wsp[threadIdx.x];
+  __syncthreads();
+  const int G = min(32, C / 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
+  const float* sa_n = sa + (int64_t)n * HW * 2;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
+    const int p = pb + grp;
+    const bool valid = p < p_end;
+    float g = 0.f;
+    if (valid && sub == 0) {
+      g = 1.f / (1.f + expf(-sa_conv(sa_n, s_w, H, W, p / W, p % W)));
+      gs[(int64_t)n * HW + p] = g;
+    }
+    g = __shfl_sync(0xffffffffu, g, grp * G);
+    if (!valid) continue;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * G + sub) * 8;
+      float uh[8], r[8], o[8];
+      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
+      if (res_mode == 2) unpack8(ldg8(res + rbase + (int64_t)p * res_pitch + c), r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u = s_g[c + i] * uh[i] + s_b[c + i];
+        const float cb = u * s_gc[c + i] * g;
+        const float rr = res_mode == 1 ? u : (res_mode == 2 ? r[i] : 0.f);
+        o[i] = act_fwd(rr + cb, slope);
+      }
+      stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward helpers
+// ---------------------------------------------------------------------------------------------------
+// reduce per-lane per-channel accumulators over the pixel groups of the warp, then the CTA, then one global
+// atomic per channel.  acc[it][i] belongs to channel (it*G + sub)*8 + i.
+template <int ITERS>
+__device__ __forceinline__ void flush_nc(float (&acc)[ITERS][8], int G, int sub, int grp, int C, float* s_buf,
+                                         float* __restrict__ dst /* element stride BN_W */, int field) {
+  for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[it][i] += __shfl_xor_sync(0xffffffffu, acc[it][i], o);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_buf[c] = 0.f;
+  __syncthreads();
+  if (grp == 0)
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_buf[(it * G + sub) * 8 + i], acc[it][i]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dst + (int64_t)c * BN_W + field, s_buf[c]);
+}
+
+// backward 1 (CBAM only): dgs[p] = sum_c ds*u*gc -> dq ; dgc[n,c] += sum_p ds*u*gs
+template <int ITERS>
+__global__ void __launch_bounds__(256) nb_bwd1_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                      const bf16* __restrict__ out, int out_pitch,
+                                                      const bf16* __restrict__ uhat, int HW, int C,
+                                                      const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ gs,
+                                                      float slope, float* __restrict__ bwd_nc,
+                                                      float* __restrict__ bwd_px, int ppc) {
+  extern __shared__ float sm[];
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_buf = sm + 3 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_g[c] = gamma[c]; s_b[c] = beta[c];
+    s_gc[c] = nc[((int64_t)n * C + c) * NC_W + NC_GC];
+  }
+  __syncthreads();
+  const int G = min(32, C / 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
+  float acc[ITERS][8];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[it][i] = 0.f;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
+    const int p = pb + grp;
+    const bool valid = p < p_end;
+    float dgs = 0.f, g = 0.f;
+    if (valid) {
+      g = gs[(int64_t)n * HW + p];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = (it * G + sub) * 8;
+        float uh[8], o[8], d[8];
+        unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
+        unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
+        unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
+          const float t = ds * (s_g[c + i] * uh[i] + s_b[c + i]);
+          dgs += t * s_gc[c + i];
+          acc[it][i] += t * g;
+        }
+      }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+    if (valid && sub == 0) bwd_px[((int64_t)n * HW + p) * BP_W + BP_DQ] = dgs * g * (1.f - g);
+  }
+  flush_nc<ITERS>(acc, G, sub, grp, C, s_buf, bwd_nc + (int64_t)n * C * BN_W, BN_DGC);
+}
+
+// backward 1b (CBAM only): dsa = conv3x3^T(dq), dwsp += sum dq * sa(shifted).  one thread per pixel
+__global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const float* __restrict__ wsp,
+                                                        const float* __restrict__ sa, float* __restrict__ bwd_px,
+                                                        float* __restrict__ dwsp) {
+  __shared__ float s_w[18];
+  __shared__ float s_red[18];
+  if (threadIdx.x < 18) { s_w[threadIdx.x] = wsp[threadIdx.x]; s_red[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int n = blockIdx.y, HW = H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* sa_n = sa + (int64_t)n * HW * 2;
+  float* px_n = bwd_px + (int64_t)n * HW * BP_W;
+  float part[18];
+#pragma unroll
+  for (int i = 0; i < 18; ++i) part[i] = 0.f;
+  if (p < HW) {
+    const int py = p / W, px = p % W;
+    const float dq = px_n[(int64_t)p * BP_W + BP_DQ];
+    float dmean = 0.f, dmax = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        // q[p'] uses sa[p' + (ky-1, kx-1)]:  dsa[p] += w[ky][kx] * dq[p - (ky-1, kx-1)]
+        const int yy = py - (ky - 1), xx = px - (kx - 1);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float dqq = px_n[((int64_t)yy * W + xx) * BP_W + BP_DQ];
+          dmean += s_w[ky * 3 + kx] * dqq;
+          dmax += s_w[9 + ky * 3 + kx] * dqq;
+        }
+        // dw[ky][kx] += dq[p] * sa[p + (ky-1, kx-1)]
+        const int y2 = py + ky - 1, x2 = px + kx - 1;
+        if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+          const float2 v = *reinterpret_cast<const float2*>(sa_n + ((int64_t)y2 * W + x2) * 2);
+          part[ky * 3 + kx] = dq * v.x;
+          part[9 + ky * 3 + kx] = dq * v.y;
+        }
+      }
+    px_n[(int64_t)p * BP_W + BP_DMEAN] = dmean;
+    px_n[(int64_t)p * BP_W + BP_DMAX] = dmax;
+  }
+#pragma unroll
+  for (int i = 0; i < 18; ++i) {
+    const float v = warp_sum(part[i]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_red[i], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 18) atomicAdd(dwsp + threadIdx.x, s_red[threadIdx.x]);
+}
+
+// backward 2: du (-> dy buffer, bf16), dres, and per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += ...
+template <int ITERS>
+__global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                      const bf16* __restrict__ out, int out_pitch,
+                                                      const bf16* __restrict__ uhat, int HW, int C,
+                                                      const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ gs,
+                                                      const int32_t* __restrict__ cidx,
+                                                      const float* __restrict__ bwd_px, int has_cbam, int res_mode,
+                                                      float slope, bf16* __restrict__ dy, int dy_pitch,
+                                                      bf16* __restrict__ dres, int dres_pitch,
+                                                      float* __restrict__ bwd_nc, int ppc) {
+  extern __shared__ float sm[];
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_buf = sm + 3 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_g[c] = gamma[c]; s_b[c] = beta[c];
+    s_gc[c] = nc[((int64_t)n * C + c) * NC_W + NC_GC];
+  }
+  __syncthreads();
+  const int G = min(32, C / 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
+  const int64_t ybase = (int64_t)n * HW * dy_pitch, rbase = (int64_t)n * HW * dres_pitch;
+  const float invC = 1.f / (float)C;
+  float a1[ITERS][8], a2[ITERS][8], a3[ITERS][8];
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1[it][i] = 0.f; a2[it][i] = 0.f; a3[it][i] = 0.f; }
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
+    const int p = pb + grp;
+    if (p >= p_end) continue;
+    float g = 0.f, dmean = 0.f, dmax = 0.f;
+    int ci = -1;
+    if (has_cbam) {
+      const int64_t o = (int64_t)n * HW + p;
+      g = gs[o];
+      dmean = bwd_px[o * BP_W + BP_DMEAN] * invC;
+      dmax = bwd_px[o * BP_W + BP_DMAX];
+      ci = cidx[o];
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * G + sub) * 8;
+      float uh[8], o[8], d[8], du[8], dsv[8];
+      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
+      unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
+      unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
+        dsv[i] = ds;
+        float v = (res_mode == 0 || res_mode == 1) ? ds : 0.f;
+        if (has_cbam) {
+          const float gc = s_gc[c + i];
+          const float dsp = dmean + ((c + i) == ci ? dmax : 0.f);   // grad wrt u1 = u*gc from the spatial branch
+          v += ds * gc * g + dsp * gc;
+          a3[it][i] += dsp * (s_g[c + i] * uh[i] + s_b[c + i]);
+        }
+        du[i] = v;
+        a1[it][i] += v;
+        a2[it][i] += v * uh[i];
+      }
+      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(du));
+      if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * dres_pitch + c, pack8(dsv));
+    }
+  }
+  float* dst = bwd_nc + (int64_t)n * C * BN_W;
+  flush_nc<ITERS>(a1, G, sub, grp, C, s_buf, dst, BN_S1);
+  flush_nc<ITERS>(a2, G, sub, grp, C, s_buf, dst, BN_S2);
+  if (has_cbam) flush_nc<ITERS>(a3, G, sub, grp, C, s_buf, dst, BN_DGC);
+}
+
+// backward 3: per-sample: channel-MLP backward, dgamma/dbeta, and the IN-backward means m1, m2.
+// Overwrites bwd_nc[n][c] = {d_mx (grad wrt the max-pooled u), m1, m2, -}.   grid N, block 256
+__global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has_cbam, int Cr,
+                                                          const float* __restrict__ nc,
+                                                          const float* __restrict__ beta,
+                                                          const float* __restrict__ w1, const float* __restrict__ w2,
+                                                          float* __restrict__ bwd_nc, float* __restrict__ dgamma,
+                                                          float* __restrict__ dbeta, float* __restrict__ dw1,
+                                                          float* __restrict__ dw2) {
+  extern __shared__ float sm[];
+  float* s_avg = sm;            // [C]
+  float* s_mx = sm + C;         // [C]
+  float* s_dv = sm + 2 * C;     // [C]
+  float* s_ha = sm + 3 * C;     // [Cr] pre-activation hidden (avg branch)
+  float* s_hm = s_ha + 64;      // [Cr]
+  float* s_dh = s_hm + 64;      // [Cr]
+  const int n = blockIdx.x;
+  const float inv = 1.f / (float)HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* bn = bwd_nc + (int64_t)n * C * BN_W;
+  const float* q0 = nc + (int64_t)n * C * NC_W;
+  if (has_cbam) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float gc = q0[c * NC_W + NC_GC];
+      s_avg[c] = beta[c];
+      s_mx[c] = q0[c * NC_W + NC_EXTU];
+      s_dv[c] = bn[c * BN_W + BN_DGC] * gc * (1.f - gc);
+    }
+    __syncthreads();
+    for (int j = warp; j < Cr; j += 8) {
+      float pa = 0.f, pm = 0.f, dh = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float w = w1[(int64_t)j * C + c];
+        pa += w * s_avg[c];
+        pm += w * s_mx[c];
+        dh += w2[(int64_t)c * Cr + j] * s_dv[c];
+      }
+      pa = warp_sum(pa); pm = warp_sum(pm); dh = warp_sum(dh);
+      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; s_dh[j] = dh; }
+    }
+    __syncthreads();
+    // dW2[c][j] += dv_c * (relu(ha_j) + relu(hm_j));  dW1[j][c] += dh_j*[ha_j>0]*avg_c + dh_j*[hm_j>0]*mx_c
+    for (int e = threadIdx.x; e < C * Cr; e += blockDim.x) {
+      const int c = e / Cr, j = e % Cr;
+      const float h = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[j], 0.f);
+      const float v = s_dv[c] * h;
+      if (v != 0.f) atomicAdd(dw2 + (int64_t)c * Cr + j, v);
+    }
+    for (int e = threadIdx.x; e < C * Cr; e += blockDim.x) {
+      const int j = e / C, c = e % C;
+      const float v = s_dh[j] * ((s_ha[j] > 0.f ? s_avg[c] : 0.f) + (s_hm[j] > 0.f ? s_mx[c] : 0.f));
+      if (v != 0.f) atomicAdd(dw1 + (int64_t)j * C + c, v);
+    }
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float d_avg = 0.f, d_mx = 0.f;
+    if (has_cbam) {
+      for (int j = 0; j < Cr; ++j) {
+        const float w = w1[(int64_t)j * C + c];
+        if (s_ha[j] > 0.f) d_avg += w * s_dh[j];
+        if (s_hm[j] > 0.f) d_mx += w * s_dh[j];
+      }
+    }
+    const float ext_uhat = q0[c * NC_W + NC_EXTUHAT];
+    const float S1 = bn[c * BN_W + BN_S1] + d_mx;
+    const float S2 = bn[c * BN_W + BN_S2] + d_mx * ext_uhat;
+    atomicAdd(dbeta + c, S1 + d_avg);
+    atomicAdd(dgamma + c, S2);
+    bn[c * BN_W + BN_DMX] = d_mx;
+    bn[c * BN_W + BN_S1] = S1 * inv;   // m1
+    bn[c * BN_W + BN_S2] = S2 * inv;   // m2
+  }
+}
+
+// backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2), in place over du
+template <int ITERS>
+__global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ uhat, int HW, int C,
+                                                      const float* __restrict__ nc,
+                                                      const int32_t* __restrict__ nc_idx,
+                                                      const float* __restrict__ bwd_nc, int has_cbam,
+                                                      bf16* __restrict__ dy, int dy_pitch, int ppc) {
+  extern __shared__ float sm[];
+  float* s_a = sm; float* s_m1 = sm + C; float* s_m2 = sm + 2 * C; float* s_dmx = sm + 3 * C;
+  int* s_idx = (int*)(sm + 4 * C);
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int64_t o = (int64_t)n * C + c;
+    s_a[c] = nc[o * NC_W + NC_A];
+    s_m1[c] = bwd_nc[o * BN_W + BN_S1];
+    s_m2[c] = bwd_nc[o * BN_W + BN_S2];
+    s_dmx[c] = bwd_nc[o * BN_W + BN_DMX];
+    s_idx[c] = has_cbam ? nc_idx[o] : -1;
+  }
+  __syncthreads();
+  const int G = min(32, C / 8);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
+  const int64_t ubase = (int64_t)n * HW * C, ybase = (int64_t)n * HW * dy_pitch;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
+    const int p = pb + grp;
+    if (p >= p_end) continue;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int c = (it * G + sub) * 8;
+      float uh[8], du[8], o[8];
+      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
+      unpack8(ldg8(dy + ybase + (int64_t)p * dy_pitch + c), du);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float extra = (p == s_idx[c + i]) ? s_dmx[c + i] : 0.f;
+        o[i] = s_a[c + i] * (du[i] + extra - s_m1[c + i] - uh[i] * s_m2[c + i]);
+      }
+      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(o));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int pick_ppc(int HW, int N, int G) {
+  // pixels per CTA: a multiple of the CTA's pixel-group count, sized so the grid has ~4 waves of 148 SMs
+  const int pg = 8 * (32 / G);
+  int chunks = ceil_div(148 * 4, N);
+  if (chunks < 1) chunks = 1;
+  int ppc = ceil_div(HW, chunks);
+  ppc = ceil_div(ppc, pg) * pg;
+  return ppc;
+}
+
+static int validate(const bvae_nb_desc* d, const char* who) {
+  BVAE_REQUIRE(d->C >= 32 && d->C <= 1024 && (d->C & (d->C - 1)) == 0, BVAE_ERR_SHAPE,
+               "%s: C=%d must be a power of two in [32,1024]", who, d->C);
+  BVAE_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, BVAE_ERR_SHAPE, "%s: empty tensor", who);
+  BVAE_REQUIRE(d->y_pitch % 8 == 0 && d->out_pitch % 8 == 0, BVAE_ERR_ALIGN, "%s: pitches must be multiples of 8", who);
+  BVAE_REQUIRE(!d->has_cbam || (d->Cr == d->C / 16 && d->Cr <= 64), BVAE_ERR_SHAPE, "%s: Cr must be C/16", who);
+  BVAE_REQUIRE(d->has_cbam || d->res_mode == 0, BVAE_ERR_SHAPE, "%s: residual modes need CBAM", who);
+  return BVAE_OK;
+}
+
+#define DISPATCH_ITERS(iters, ...)              \
+  switch (iters) {                              \
+    case 1: { constexpr int IT = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int IT = 2; __VA_ARGS__; } break; \
+    default: { constexpr int IT = 4; __VA_ARGS__; } break; \
+  }
+
+}  // namespace bvae
+
+using namespace bvae;
+
+extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = validate(d, "nb_forward");
+  if (rc) return rc;
+  const int N = d->N, HW = d->H * d->W, C = d->C;
+  const int64_t NC = (int64_t)N * C;
+  // scratch layout inside d->stats: [NC] float2 | [NC] u64 max keys | [NC] u64 min keys
+  float2* ss = (float2*)d->stats;
+  u64* kmax = (u64*)(ss + NC);
+  u64* kmin = kmax + NC;
+  const int cchunks = ceil_div(C, 256);
+  int psplit = 1;
+  if ((int64_t)N * cchunks < 148 * 2) {
+    psplit = ceil_div(148 * 2, N * cchunks);
+    const int maxsplit = ceil_div(HW, 64);
+    if (psplit > maxsplit) psplit = maxsplit;
+    if (psplit < 1) psplit = 1;
+  }
+  if (psplit > 1) {
+    if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
+  }
+  dim3 g1(cchunks, psplit, N);
+  if (d->y_f32) nb_stats_kernel<true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+  else nb_stats_kernel<false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+  if ((rc = check_launch("nb_stats"))) return rc;
+
+  const size_t sm2 = (2 * C + 64) * sizeof(float);
+  if (d->y_f32)
+    nb_coef_kernel<true><<<N, 256, sm2, st>>>(d->y, d->y_pitch, HW, C, ss, kmax, kmin, d->gamma, d->beta, d->eps,
+                                              d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx);
+  else
+    nb_coef_kernel<false><<<N, 256, sm2, st>>>(d->y, d->y_pitch, HW, C, ss, kmax, kmin, d->gamma, d->beta, d->eps,
+                                               d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx);
+  if ((rc = check_launch("nb_coef"))) return rc;
+
+  const int G = C / 8 < 32 ? C / 8 : 32;
+  const int iters = C / (8 * G);
+  const int ppc = pick_ppc(HW, N, G);
+  dim3 g3(ceil_div(HW, ppc), N);
+  const size_t sm3 = 5 * C * sizeof(float);
+  DISPATCH_ITERS(iters, {
+    if (d->y_f32)
+      nb_pool_kernel<true, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
+                                                      (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);
+    else
+      nb_pool_kernel<false, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
+                                                       (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);
+  });
+  if ((rc = check_launch("nb_pool"))) return rc;
+  if (!d->has_cbam) return BVAE_OK;
+
+  const size_t sm4 = 3 * C * sizeof(float);
+  DISPATCH_ITERS(iters, {
+    nb_apply_kernel<IT><<<g3, 256, sm4, st>>>((const bf16*)d->uhat, d->H, d->W, C, d->nc, d->gamma, d->beta, d->wsp,
+                                               d->sa, d->res_mode, (const bf16*)d->res, d->res_pitch, d->slope,
+                                               (bf16*)d->out, d->out_pitch, d->gs, ppc);
+  });
+  return check_launch("nb_apply");
+}
+
+extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  int rc = validate(d, "nb_backward");
+  if (rc) return rc;
+  BVAE_REQUIRE(d->dout_pitch % 8 == 0 && d->dy_pitch % 8 == 0, BVAE_ERR_ALIGN, "nb_backward: pitches % 8 != 0");
+  const int N = d->N, HW = d->H * d->W, C = d->C;
+  const int G = C / 8 < 32 ? C / 8 : 32;
+  const int iters = C / (8 * G);
+  const int ppc = pick_ppc(HW, N, G);
+  dim3 gp(ceil_div(HW, ppc), N);
+  if (cudaMemsetAsync(d->bwd_nc, 0, (size_t)N * C * BN_W * sizeof(float), st) != cudaSuccess) {
+    set_error("nb_backward: memset failed");
+    return BVAE_ERR_CUDA;
+  }
+  const size_t smb = 4 * C * sizeof(float);
+  if (d->has_cbam) {
+    DISPATCH_ITERS(iters, {
+      nb_bwd1_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
+                                                (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->slope,
+                                                d->bwd_nc, d->bwd_px, ppc);
+    });
+    if ((rc = check_launch("nb_bwd1"))) return rc;
+    dim3 gs(ceil_div(HW, 256), N);
+    nb_bwd_sp_kernel<<<gs, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->bwd_px, d->dwsp);
+    if ((rc = check_launch("nb_bwd_sp"))) return rc;
+  }
+  DISPATCH_ITERS(iters, {
+    nb_bwd2_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
+                                              (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->cidx,
+                                              d->bwd_px, d->has_cbam, d->res_mode, d->slope, (bf16*)d->dy, d->dy_pitch,
+                                              (bf16*)d->dres, d->dres_pitch, d->bwd_nc, ppc);
+  });
+  if ((rc = check_launch("nb_bwd2"))) return rc;
+  const size_t smc = (3 * C + 192) * sizeof(float);
+  nb_bwd_coef_kernel<<<N, 256, smc, st>>>(HW, C, d->has_cbam, d->Cr, d->nc, d->beta, d->w1, d->w2, d->bwd_nc, d->dgamma,
+                                          d->dbeta, d->dw1, d->dw2);
+  if ((rc = check_launch("nb_bwd_coef"))) return rc;
+  const size_t sm5 = 5 * C * sizeof(float);
+  DISPATCH_ITERS(iters, {
+    nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->uhat, HW, C, d->nc, d->nc_idx, d->bwd_nc, d->has_cbam,
+                                              (bf16*)d->dy, d->dy_pitch, ppc);
+  });
+  return check_launch("nb_bwd3");
+}

@@ -1,0 +1,432 @@
+"""Host-side plumbing between the nn.Module mirror of the reference and the C ABI of libbarvae.so.
+
+* ``Act``        -- an NHWC bf16/fp32 activation view (tensor, geometry, channel pitch/offset).
+* ``GemmLayer``  -- one Conv2d / ConvTranspose2d / Linear weight: plans the implicit-GEMM phases (sub-pixel
+                    decomposition of strided transposed convolutions), keeps the packed bf16 operands in sync with
+                    the fp32 master parameter, and issues forward / data-gradient / weight-gradient calls.
+* ``NormBlock``  -- InstanceNorm(+CBAM)(+residual)+activation through bvae_nb_forward / bvae_nb_backward.
+* ``FlatParams`` -- re-homes a module's parameters and gradients into flat fp32 buckets (one Adam launch, one
+                    NCCL all-reduce per bucket).
+
+PyTorch here is device memory + streams only; all arithmetic on the hot path happens inside libbarvae.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, NbDesc, WgradDesc
+
+BF16 = torch.bfloat16
+_PARAM_EPOCH = [0]          # bumped whenever libbarvae itself rewrites parameters (fused Adam)
+_IMPL = [_lib.IMPL_AUTO]    # contraction implementation selector (tests flip it to compare SIMT vs tcgen05)
+_RAW_F32 = [True]           # dtype of raw conv outputs feeding an InstanceNorm (see DESIGN.md "Parity tolerances")
+
+
+def set_impl(impl: int):
+    _IMPL[0] = impl
+
+
+def get_impl() -> int:
+    return _IMPL[0]
+
+
+def set_raw_f32(flag: bool):
+    _RAW_F32[0] = bool(flag)
+
+
+def raw_dtype():
+    return torch.float32 if _RAW_F32[0] else BF16
+
+
+def bump_param_epoch():
+    _PARAM_EPOCH[0] += 1
+
+
+class Act:
+    """NHWC activation view: element (n,h,w,c) lives at t.data_ptr() + (((n*H+h)*W+w)*pitch + off + c)*esize."""
+    __slots__ = ("t", "N", "H", "W", "C", "pitch", "off")
+
+    def __init__(self, t: torch.Tensor, N: int, H: int, W: int, C: int, pitch: Optional[int] = None, off: int = 0):
+        self.t, self.N, self.H, self.W, self.C = t, N, H, W, C
+        self.pitch = C if pitch is None else pitch
+        self.off = off
+
+    @staticmethod
+    def empty(N, H, W, C, dtype=BF16, device="cuda") -> "Act":
+        return Act(torch.empty((N, H, W, C), dtype=dtype, device=device), N, H, W, C)
+
+    def slice(self, off: int, C: int) -> "Act":
+        return Act(self.t, self.N, self.H, self.W, C, self.pitch, self.off + off)
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + self.off * self.t.element_size()
+
+    @property
+    def f32(self) -> bool:
+        return self.t.dtype == torch.float32
+
+    def dense(self) -> torch.Tensor:
+        """[N,H,W,C] tensor view (strided if this is a slice of a concatenated buffer)."""
+        v = self.t.view(self.N, self.H, self.W, self.pitch)
+        return v[..., self.off:self.off + self.C]
+
+
+def grad_ptr(p: Optional[torch.Tensor]) -> int:
+    """Device pointer of p.grad, creating a zero gradient if needed.  Frozen parameters (requires_grad=False,
+    agent/barGen.py:143-149) get a throw-away sink so kernels can still accumulate somewhere."""
+    if p is None:
+        return 0
+    if not p.requires_grad:
+        sink = getattr(p, "_bvae_sink", None)
+        if sink is None or sink.shape != p.shape or sink.device != p.device:
+            sink = torch.zeros_like(p)
+            p._bvae_sink = sink
+        return sink.data_ptr()
+    if p.grad is None:
+        flat = getattr(p, "_bvae_flat", None)
+        if flat is not None:
+            p.grad = flat.grad_view(p).zero_()
+        else:
+            p.grad = torch.zeros_like(p)
+    return p.grad.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# implicit-GEMM layers
+# ---------------------------------------------------------------------------------------------------------
+class _Phase:
+    __slots__ = ("taps", "dy", "dx", "sy", "sx", "osy", "osx", "ooy", "oox", "k_off")
+
+    def __init__(self, taps, dy, dx, sy, sx, osy, osx, ooy, oox, k_off):
+        self.taps, self.dy, self.dx = taps, dy, dx
+        self.sy, self.sx, self.osy, self.osx, self.ooy, self.oox = sy, sx, osy, osx, ooy, oox
+        self.k_off = k_off          # first packed tap of this phase inside the packed weight rows
+
+
+def _transposed_phases(kh, kw, sy, sx, py, px):
+    """Sub-pixel decomposition of out[o] = sum_{i,k : i*s - p + k = o} in[i] w[k]: for output parity r the valid
+    taps have (r + p - k) % s == 0 and read in[q + (r + p - k)//s] for o = q*s + r."""
+    phases, perm = [], []
+    for ry in range(sy):
+        for rx in range(sx):
+            taps, dys, dxs = [], [], []
+            for ky in range(kh):
+                if (ry + py - ky) % sy:
+                    continue
+                for kx in range(kw):
+                    if (rx + px - kx) % sx:
+                        continue
+                    taps.append(ky * kw + kx)
+                    dys.append((ry + py - ky) // sy)
+                    dxs.append((rx + px - kx) // sx)
+            phases.append(_Phase(taps, dys, dxs, 1, 1, sy, sx, ry, rx, len(perm)))
+            perm += taps
+    return phases, perm
+
+
+def _direct_phase(kh, kw, sy, sx, py, px):
+    taps = list(range(kh * kw))
+    dys = [t // kw - py for t in taps]
+    dxs = [t % kw - px for t in taps]
+    return [_Phase(taps, dys, dxs, sy, sx, 1, 1, 0, 0, 0)], taps
+
+
+class GemmLayer:
+    """One contraction weight of the model.
+
+    kind "conv"   : nn.Conv2d weight [Cout, Cin, kh, kw]   (graph/encodingBlock.py, graph/decoder.py:79,122,172)
+    kind "convT"  : nn.ConvTranspose2d weight [Cin, Cout, kh, kw] (graph/decoder.py:12-15,43-46,73-77,116-120)
+    kind "linear" : nn.Linear weight [out, in] == 1x1 conv on a 1x1 map (graph/encoder.py:22, decoder.py:166-167)
+    """
+
+    def __init__(self, kind: str, weight: torch.nn.Parameter, bias: Optional[torch.nn.Parameter] = None,
+                 kernel=(1, 1), stride=(1, 1), padding=(0, 0), output_padding=(0, 0)):
+        self.kind, self.weight, self.bias = kind, weight, bias
+        self.kh, self.kw = kernel
+        self.sy, self.sx = stride
+        self.py, self.px = padding
+        self.opy, self.opx = output_padding
+        if kind == "convT":
+            self.Cin, self.Cout = weight.shape[0], weight.shape[1]
+        else:
+            self.Cout, self.Cin = weight.shape[0], weight.shape[1]
+        self.T = self.kh * self.kw
+        T, Cin, Cout = self.T, self.Cin, self.Cout
+        if kind == "convT":
+            self.f_phases, self.f_perm = _transposed_phases(self.kh, self.kw, self.sy, self.sx, self.py, self.px)
+            self.d_phases, self.d_perm = _direct_phase(self.kh, self.kw, self.sy, self.sx, self.py, self.px)
+            # W[ci][co][t]: forward operand rows = co, K = (tap, ci); dgrad operand rows = ci, K = (tap, co)
+            self.f_src = (T, Cout * T)
+            self.d_src = (Cout * T, T)
+        else:
+            self.f_phases, self.f_perm = _direct_phase(self.kh, self.kw, self.sy, self.sx, self.py, self.px)
+            self.d_phases, self.d_perm = _transposed_phases(self.kh, self.kw, self.sy, self.sx, self.py, self.px)
+            # W[co][ci][t]
+            self.f_src = (Cin * T, T)
+            self.d_src = (T, Cin * T)
+        self._wf = self._wd = None
+        self._wf_key = self._wd_key = None
+        self._cache: Dict[tuple, object] = {}
+
+    # ---- geometry -------------------------------------------------------------------------------------
+    def out_hw(self, H: int, W: int) -> Tuple[int, int]:
+        if self.kind == "convT":
+            return ((H - 1) * self.sy - 2 * self.py + self.kh + self.opy,
+                    (W - 1) * self.sx - 2 * self.px + self.kw + self.opx)
+        return ((H + 2 * self.py - self.kh) // self.sy + 1, (W + 2 * self.px - self.kw) // self.sx + 1)
+
+    # ---- packed operands ------------------------------------------------------------------------------
+    def _key(self):
+        w = self.weight
+        return (w.data_ptr(), w._version, _PARAM_EPOCH[0])
+
+    def _pack(self, rows: int, cc: int, src, perm) -> torch.Tensor:
+        T = len(perm)
+        dst = torch.empty((rows, T * cc), dtype=BF16, device=self.weight.device)
+        arr = (C.c_int32 * T)(*perm)
+        w = self.weight.detach()
+        assert w.is_contiguous() and w.dtype == torch.float32
+        _lib.check(_lib.lib().bvae_pack_weight(w.data_ptr(), dst.data_ptr(), rows, T, cc, src[0], src[1], arr,
+                                               T * cc, _lib.stream_ptr()), "pack_weight")
+        return dst
+
+    def w_fwd(self) -> torch.Tensor:
+        k = self._key()
+        if self._wf_key != k:
+            self._wf = self._pack(self.Cout, self.Cin, self.f_src, self.f_perm)
+            self._wf_key = k
+        return self._wf
+
+    def w_dgrad(self) -> torch.Tensor:
+        k = self._key()
+        if self._wd_key != k:
+            self._wd = self._pack(self.Cin, self.Cout, self.d_src, self.d_perm)
+            self._wd_key = k
+        return self._wd
+
+    # ---- launches -------------------------------------------------------------------------------------
+    def _run_phases(self, phases, wpk: torch.Tensor, x: Act, y: Act, cout: int, grid_of, bias, act, slope,
+                    addend: Optional[Act], mask: Optional[Act], mask_slope: float, tag: str):
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        key = (tag, x.N, x.H, x.W, x.pitch, y.H, y.W, y.pitch, y.f32, act, slope, addend is not None and addend.pitch,
+               mask is not None and mask.pitch, mask_slope, bias is not None)
+        descs = self._cache.get(key)
+        if descs is None:
+            descs = []
+            for ph in phases:
+                if not ph.taps:
+                    raise RuntimeError("phase without taps (kernel smaller than stride) is not supported")
+                QH, QW = grid_of(ph)
+                if QH <= 0 or QW <= 0:
+                    continue
+                d = ConvDesc()
+                d.N, d.H, d.W, d.C, d.x_pitch = x.N, x.H, x.W, x.C, x.pitch
+                d.Cout, d.w_pitch, d.ntaps = cout, wpk.shape[1], len(ph.taps)
+                for i in range(len(ph.taps)):
+                    d.dy[i], d.dx[i] = ph.dy[i], ph.dx[i]
+                d.sy, d.sx, d.QH, d.QW = ph.sy, ph.sx, QH, QW
+                d.OH, d.OW, d.y_pitch = y.H, y.W, y.pitch
+                d.osy, d.osx, d.ooy, d.oox = ph.osy, ph.osx, ph.ooy, ph.oox
+                d.add_pitch = addend.pitch if addend is not None else 0
+                d.mask_pitch = mask.pitch if mask is not None else 0
+                d.act, d.out_f32, d.slope, d.mask_slope = int(act), int(y.f32), float(slope), float(mask_slope)
+                descs.append((d, ph.k_off * x.C * 2))
+            self._cache[key] = descs
+        xp, yp, wp = x.ptr, y.ptr, wpk.data_ptr()
+        bp = bias.data_ptr() if bias is not None else None
+        ap = addend.ptr if addend is not None else None
+        mp = mask.ptr if mask is not None else None
+        for d, woff in descs:
+            d.x, d.w, d.y, d.bias, d.addend, d.mask = xp, wp + woff, yp, bp, ap, mp
+            _lib.check(lib.bvae_conv_gemm(C.byref(d), _IMPL[0], st), "conv_gemm[%s]" % tag)
+
+    def forward(self, x: Act, y: Act, act: bool = False, slope: float = 0.0, use_bias: bool = True):
+        """y = epi(conv(x)); y geometry must be out_hw(x) with C == Cout."""
+        assert x.C == self.Cin and y.C == self.Cout, (x.C, self.Cin, y.C, self.Cout)
+        if self.kind == "convT":
+            grid_of = lambda ph: (-(-(y.H - ph.ooy) // ph.osy), -(-(y.W - ph.oox) // ph.osx))
+        else:
+            grid_of = lambda ph: (y.H, y.W)
+        bias = self.bias.detach() if (self.bias is not None and use_bias) else None
+        self._run_phases(self.f_phases, self.w_fwd(), x, y, self.Cout, grid_of, bias, act, slope, None, None, 0.0, "f")
+
+    def dgrad(self, dy: Act, dx: Act, addend: Optional[Act] = None, mask: Optional[Act] = None,
+              mask_slope: float = 0.0):
+        """dx = conv_backward_data(dy) (+ addend) (* act'(mask))."""
+        assert dy.C == self.Cout and dx.C == self.Cin
+        if self.kind == "convT":
+            grid_of = lambda ph: (dx.H, dx.W)
+        else:
+            grid_of = lambda ph: (-(-(dx.H - ph.ooy) // ph.osy), -(-(dx.W - ph.oox) // ph.osx))
+        self._run_phases(self.d_phases, self.w_dgrad(), dy, dx, self.Cin, grid_of, None, False, 0.0, addend, mask,
+                         mask_slope, "d")
+
+    def wgrad(self, x: Act, dy: Act):
+        """weight.grad += conv_backward_weight(x, dy); bias.grad += column sums of dy."""
+        lib = _lib.lib()
+        st = _lib.stream_ptr()
+        if self.weight.requires_grad:
+            a, s = (x, dy) if self.kind == "convT" else (dy, x)
+            key = ("w", a.N, a.H, a.W, a.pitch, s.H, s.W, s.pitch)
+            d = self._cache.get(key)
+            if d is None:
+                d = WgradDesc()
+                d.N, d.AH, d.AW, d.Ca, d.a_pitch = a.N, a.H, a.W, a.C, a.pitch
+                d.SH, d.SW, d.Cs, d.s_pitch = s.H, s.W, s.C, s.pitch
+                d.sy, d.sx, d.ntaps, d.T = self.sy, self.sx, self.T, self.T
+                for t in range(self.T):
+                    d.dy[t], d.dx[t], d.tap_idx[t] = t // self.kw - self.py, t % self.kw - self.px, t
+                self._cache[key] = d
+            d.a, d.s, d.dw = a.ptr, s.ptr, grad_ptr(self.weight)
+            _lib.check(lib.bvae_wgrad_gemm(C.byref(d), _IMPL[0], st), "wgrad_gemm")
+
+    def bias_grad(self, dy: Act):
+        if self.bias is not None and self.bias.requires_grad:
+            _lib.check(_lib.lib().bvae_colsum(dy.ptr, int(dy.f32), dy.N * dy.H * dy.W, dy.C, dy.pitch,
+                                              grad_ptr(self.bias), _lib.stream_ptr()), "colsum")
+
+    def zero_bias_grad(self):
+        """Bias in front of an InstanceNorm: its gradient is analytically zero (the reference only yields rounding
+        noise there); make sure a zero .grad exists so optimisers see the same parameter set."""
+        if self.bias is not None and self.bias.requires_grad:
+            grad_ptr(self.bias)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# InstanceNorm (+CBAM) (+residual) + activation
+# ---------------------------------------------------------------------------------------------------------
+class NormBlock:
+    def __init__(self, C: int, gamma, beta, cbam=None, res_mode: int = 0, slope: float = 0.0):
+        """cbam = (w1 [C/16,C,1,1], w2 [C,C/16,1,1], wsp [1,2,3,3]) parameters or None."""
+        self.C, self.gamma, self.beta, self.cbam, self.res_mode, self.slope = C, gamma, beta, cbam, res_mode, slope
+
+    def _desc(self, y_pitch, y_f32, out: Act, N, H, W) -> NbDesc:
+        d = NbDesc()
+        d.N, d.H, d.W, d.C = N, H, W, self.C
+        d.y_pitch, d.out_pitch = y_pitch, out.pitch
+        d.has_cbam = int(self.cbam is not None)
+        d.Cr = self.C // 16
+        d.res_mode, d.y_f32, d.slope, d.eps = self.res_mode, int(y_f32), self.slope, 1e-5
+        d.gamma, d.beta = self.gamma.data_ptr(), self.beta.data_ptr()
+        if self.cbam is not None:
+            d.w1, d.w2, d.wsp = (p.data_ptr() for p in self.cbam)
+        return d
+
+    def forward(self, y: Act, out: Act, res: Optional[Act] = None) -> dict:
+        N, H, W, Cc = y.N, y.H, y.W, self.C
+        dev = y.t.device
+        ctx = {"N": N, "H": H, "W": W, "out": out,
+               "uhat": torch.empty((N, H, W, Cc), dtype=BF16, device=dev),
+               "nc": torch.empty((N, Cc, 8), dtype=torch.float32, device=dev),
+               "nc_idx": torch.empty((N, Cc), dtype=torch.int32, device=dev)}
+        stats = torch.empty((N * Cc * 6,), dtype=torch.float32, device=dev)
+        d = self._desc(y.pitch, y.f32, out, N, H, W)
+        d.y, d.uhat, d.out, d.stats = y.ptr, ctx["uhat"].data_ptr(), out.ptr, stats.data_ptr()
+        d.nc, d.nc_idx = ctx["nc"].data_ptr(), ctx["nc_idx"].data_ptr()
+        if self.cbam is not None:
+            ctx["sa"] = torch.empty((N, H * W, 2), dtype=torch.float32, device=dev)
+            ctx["cidx"] = torch.empty((N, H * W), dtype=torch.int32, device=dev)
+            ctx["gs"] = torch.empty((N, H * W), dtype=torch.float32, device=dev)
+            d.sa, d.cidx, d.gs = ctx["sa"].data_ptr(), ctx["cidx"].data_ptr(), ctx["gs"].data_ptr()
+        if self.res_mode == 2:
+            assert res is not None
+            d.res, d.res_pitch = res.ptr, res.pitch
+        _lib.check(_lib.lib().bvae_nb_forward(C.byref(d), _lib.stream_ptr()), "nb_forward")
+        return ctx
+
+    def backward(self, ctx: dict, dout: Act, dy: Act, dres: Optional[Act] = None):
+        N, H, W, Cc = ctx["N"], ctx["H"], ctx["W"], self.C
+        dev = dout.t.device
+        out: Act = ctx["out"]
+        d = self._desc(0, True, out, N, H, W)
+        d.uhat, d.out, d.nc, d.nc_idx = ctx["uhat"].data_ptr(), out.ptr, ctx["nc"].data_ptr(), ctx["nc_idx"].data_ptr()
+        bwd_nc = torch.empty((N, Cc, 4), dtype=torch.float32, device=dev)
+        d.bwd_nc = bwd_nc.data_ptr()
+        d.dout, d.dout_pitch, d.dy, d.dy_pitch = dout.ptr, dout.pitch, dy.ptr, dy.pitch
+        d.dgamma, d.dbeta = grad_ptr(self.gamma), grad_ptr(self.beta)
+        if self.cbam is not None:
+            bwd_px = torch.empty((N, H * W, 4), dtype=torch.float32, device=dev)
+            d.bwd_px = bwd_px.data_ptr()
+            d.sa, d.cidx, d.gs = ctx["sa"].data_ptr(), ctx["cidx"].data_ptr(), ctx["gs"].data_ptr()
+            d.dw1, d.dw2, d.dwsp = (grad_ptr(p) for p in self.cbam)
+        if self.res_mode == 2 and dres is not None:
+            d.dres, d.dres_pitch = dres.ptr, dres.pitch
+        _lib.check(_lib.lib().bvae_nb_backward(C.byref(d), _lib.stream_ptr()), "nb_backward")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# flat parameter / gradient buckets
+# ---------------------------------------------------------------------------------------------------------
+class FlatParams:
+    """All parameters of a module in ONE fp32 buffer (and their gradients in another), each parameter a view.
+
+    Replaces the per-parameter Adam loop (agent/barGen.py:61-62,327,333: 221 tensors) by one launch, and the
+    per-parameter Horovod hooks (agent/barGen_horovod.py:91-99) by bucketed all-reduces of contiguous slices."""
+    ALIGN = 64
+
+    def __init__(self, module: torch.nn.Module):
+        params, seen = [], set()
+        for p in module.parameters():
+            if id(p) not in seen:
+                seen.add(id(p))
+                params.append(p)
+        self.params = params
+        dev = params[0].device
+        self.offsets, off = [], 0
+        for p in params:
+            self.offsets.append(off)
+            off += -(-p.numel() // self.ALIGN) * self.ALIGN
+        self.numel = off
+        self.data = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.exp_avg = self.exp_avg_sq = None
+        with torch.no_grad():
+            for p, o in zip(params, self.offsets):
+                v = self.data[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                p._bvae_flat = self
+                p._bvae_off = o
+                p.grad = None
+        bump_param_epoch()
+
+    def grad_view(self, p) -> torch.Tensor:
+        o = p._bvae_off
+        return self.grad[o:o + p.numel()].view(p.shape)
+
+    def attach_grads(self, zero: bool = True):
+        """Point every .grad at its slice of the flat gradient bucket (one memset instead of 221)."""
+        if zero:
+            self.grad.zero_()
+        for p in self.params:
+            if p.requires_grad:
+                p.grad = self.grad_view(p)
+
+    def intact(self) -> bool:
+        p, o = self.params[0], self.offsets[0]
+        return p.data_ptr() == self.data.data_ptr() + o * 4
+
+
+def flatten(module: torch.nn.Module) -> FlatParams:
+    flat = getattr(module, "_bvae_flat_params", None)
+    if flat is None or not flat.intact() or flat.data.device != next(module.parameters()).device:
+        flat = FlatParams(module)
+        module._bvae_flat_params = flat
+    return flat
+
+
+def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
+    """torch.optim.Adam semantics (agent/barGen.py:61-62) on the flat bucket, one kernel."""
+    if flat.exp_avg is None:
+        flat.exp_avg = torch.zeros_like(flat.data)
+        flat.exp_avg_sq = torch.zeros_like(flat.data)
+    _lib.check(_lib.lib().bvae_adam_step(flat.data.data_ptr(), flat.grad.data_ptr(), flat.exp_avg.data_ptr(),
+                                         flat.exp_avg_sq.data_ptr(), flat.numel, lr, betas[0], betas[1], eps, step,
+                                         grad_scale, _lib.stream_ptr()), "adam")
+    bump_param_epoch()

@@ -1,0 +1,125 @@
+"""Generator composition with the reference's forward signature (graph/model.py:12-41).
+
+``Model.forward(note, pre_note, phrase, position, is_train=True)`` returns ``(gen_note, z, pre_z, phrase_feature)``
+in training mode and the generated bar when ``is_train=False`` (sampling: the ``note`` slot carries the latent,
+maker_bar.py:38).  The reference's Refiner cannot execute (graph/refiner.py:12 vs :19), so --
+exactly like the reference's own runnable composition graph/model_with_gan.py:20-38 -- it is not applied here.
+
+``vae_head=True`` adds the reparameterise + KL head of the archived generation
+(old/graphs/models/bar_v1/encoder.py:55-63): forward then returns ``(recon, mu, logvar)``.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from ..engine import flatten
+from .decoder import Decoder
+from .encoder import Encoder
+from .phrase_encoder import PhraseModel
+from .weights_initializer import weights_init
+
+
+class _ReparamFn(torch.autograd.Function):
+    """z = mu + eps * exp(0.5 * logvar), one fused kernel each way (KL gradient is added by VAELoss)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar, eps):
+        mu, logvar, eps = mu.contiguous(), logvar.contiguous(), eps.contiguous()
+        z = torch.empty_like(mu)
+        kl = torch.zeros(1, device=mu.device)
+        _lib.check(_lib.lib().bvae_reparam_kl_fwd(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), z.data_ptr(),
+                                                  kl.data_ptr(), mu.numel(), _lib.stream_ptr()), "reparam_kl_fwd")
+        ctx.save_for_backward(mu, logvar, eps)
+        ctx.mark_non_differentiable(kl)
+        return z, kl
+
+    @staticmethod
+    def backward(ctx, dz, _dkl):
+        mu, logvar, eps = ctx.saved_tensors
+        dz = dz.contiguous()
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+        _lib.check(_lib.lib().bvae_reparam_kl_bwd(mu.data_ptr(), logvar.data_ptr(), eps.data_ptr(), dz.data_ptr(), 0.0,
+                                                  dmu.data_ptr(), dlv.data_ptr(), mu.numel(), _lib.stream_ptr()),
+                   "reparam_kl_bwd")
+        return dmu, dlv, None
+
+
+class _KLFn(torch.autograd.Function):
+    """-0.5 * sum(1 + logvar - mu^2 - exp(logvar))  (old/graphs/losses/loss.py:16)."""
+
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        mu, logvar = mu.contiguous(), logvar.contiguous()
+        z = torch.empty_like(mu)
+        kl = torch.zeros(1, device=mu.device)
+        zero = torch.zeros_like(mu)
+        _lib.check(_lib.lib().bvae_reparam_kl_fwd(mu.data_ptr(), logvar.data_ptr(), zero.data_ptr(), z.data_ptr(),
+                                                  kl.data_ptr(), mu.numel(), _lib.stream_ptr()), "reparam_kl_fwd")
+        ctx.save_for_backward(mu, logvar)
+        return kl[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, logvar = ctx.saved_tensors
+        dmu, dlv = torch.empty_like(mu), torch.empty_like(mu)
+        _lib.check(_lib.lib().bvae_reparam_kl_bwd(mu.data_ptr(), logvar.data_ptr(), mu.data_ptr(), None, 1.0,
+                                                  dmu.data_ptr(), dlv.data_ptr(), mu.numel(), _lib.stream_ptr()),
+                   "reparam_kl_bwd")
+        return dmu * g, dlv * g
+
+
+def reparameterize(mu, logvar, eps=None):
+    """old/graphs/models/bar_v1/encoder.py:60-63; eps defaults to torch.randn_like (CUDA Philox)."""
+    if eps is None:
+        eps = torch.randn_like(mu)
+    return _ReparamFn.apply(mu, logvar, eps)[0]
+
+
+def kl_divergence(mu, logvar):
+    return _KLFn.apply(mu, logvar)
+
+
+class Model(nn.Module):
+    def __init__(self, vae_head: bool = False):
+        super().__init__()
+        self.encoder = Encoder([64, 128, 256, 512, 1024])
+        self.decoder = Decoder([1024, 512, 256, 128, 64])
+        self.phrase_encoder = PhraseModel([64, 128, 256, 512, 1024])
+        self.vae_head = vae_head
+        if vae_head:
+            # log-variance head next to the mean head (= encoder.linear), as `var` sits next to `mean` in
+            # old/graphs/models/bar_v1/encoder.py:55-56.  Not part of the HEAD state_dict.
+            self.logvar_head = nn.Linear(1152, 1152)
+            nn.init.zeros_(self.logvar_head.weight)
+            nn.init.constant_(self.logvar_head.bias, -4.0)
+        self.apply(weights_init) if not vae_head else [m.apply(weights_init) for m in
+                                                        (self.encoder, self.decoder, self.phrase_encoder)]
+
+    def flatten_parameters(self):
+        """Re-home all parameters into one flat fp32 bucket (engine.FlatParams) -- used by the fused Adam step
+        and the NCCL gradient all-reduce.  state_dict()/load_state_dict() keep working (parameters become views)."""
+        return flatten(self)
+
+    def forward(self, note, pre_note, phrase, position, is_train=True, dropout_masks=None, eps=None):
+        if is_train:
+            B = note.shape[0]
+            phrase_feature = self.phrase_encoder(phrase)
+            # encoder(note) and encoder(pre_note) share weights and have no batch-coupled op (InstanceNorm is
+            # per sample): one pass over 2B bars (model.py:26-27)
+            zz = self.encoder(torch.cat((note, pre_note), 0))
+            z, pre_z = zz[:B], zz[B:]
+            if self.vae_head:
+                mu, pre_mu = z, pre_z
+                lv_all = self.logvar_head(zz)
+                logvar, pre_logvar = lv_all[:B], lv_all[B:]
+                e1, e2 = (None, None) if eps is None else eps
+                z = reparameterize(mu, logvar, e1)
+                pre_z = reparameterize(pre_mu, pre_logvar, e2)
+                recon = self.decoder(z, pre_z, phrase_feature, position, dropout_masks)
+                self.last_pre = (pre_mu, pre_logvar)
+                return recon, mu, logvar
+            gen_note = self.decoder(z, pre_z, phrase_feature, position, dropout_masks)
+            return gen_note, z, pre_z, phrase_feature
+        phrase_feature = self.phrase_encoder(phrase)
+        pre_z = self.encoder(pre_note)
+        return self.decoder(note, pre_z, phrase_feature, position, dropout_masks)

@@ -1,0 +1,265 @@
+"""GPU (B200) kernel-level parity, all through the C ABI of libbarvae.so (ctypes).
+
+Floating-point kernels: the comparison is against plain PyTorch fp32 ops on the same device, on inputs that are
+already bf16-representable, so the only differences are accumulation order and the bf16 rounding of stored outputs.
+Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from gpu_util import nchw, nhwc, pkg, rel_fro, report
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+def _bf(t):
+    return t.to(BF16).float()
+
+
+LAYERS = [
+    # kind, cin, cout, kernel, stride, padding, output_padding, H, W          (reference site)
+    ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 12, 10),                # encodingBlock.py:74-77
+    ("conv", 64, 128, (3, 3), (2, 2), (1, 1), (0, 0), 24, 15),               # encodingBlock.py:107 (odd width)
+    ("conv", 32, 32, (1, 4), (1, 2), (0, 1), (0, 0), 12, 60),                # encodingBlock.py:14
+    ("conv", 32, 32, (4, 1), (2, 1), (1, 0), (0, 0), 96, 30),                # encodingBlock.py:45
+    ("conv", 1, 32, (4, 1), (2, 1), (1, 0), (0, 0), 96, 60),                 # encodingBlock.py:12 (C_in = 1)
+    ("conv", 1, 32, (1, 4), (1, 2), (0, 1), (0, 0), 96, 60),                 # encodingBlock.py:43
+    ("conv", 256, 128, (1, 1), (1, 1), (0, 0), (0, 0), 6, 5),                # decoder.py:79
+    ("convT", 128, 64, (1, 3), (1, 3), (0, 0), (0, 0), 1, 1),                # decoder.py:43 (k == stride)
+    ("convT", 64, 64, (6, 1), (6, 1), (0, 0), (0, 0), 1, 3),                 # decoder.py:45
+    ("convT", 128, 64, (4, 4), (2, 2), (1, 1), (0, 1), 6, 3),                # decoder.py:116 (odd output width)
+    ("convT", 64, 32, (4, 4), (2, 2), (1, 1), (0, 0), 12, 15),               # decoder.py:73
+    ("convT", 64, 32, (3, 3), (2, 2), (1, 1), (1, 1), 12, 15),               # decoder.py:76
+]
+
+
+@pytest.mark.parametrize("spec", LAYERS, ids=lambda s: "%s_%dto%d_k%dx%d_s%dx%d" % (s[0], s[1], s[2], *s[3], *s[4]))
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_gemm_layer(spec, impl):
+    """forward / data-gradient / weight-gradient of one layer vs torch.nn.functional (fp32).
+    Tolerance: rel-Frobenius 2e-3 (fp32 outputs; operands are bf16-exact, so this is accumulation-order noise)."""
+    eng = pkg("engine")
+    lib = pkg("_lib")
+    kind, cin, cout, k, s, p, op, H, W = spec
+    torch.manual_seed(1)
+    B = 3
+    if kind == "conv":
+        m = nn.Conv2d(cin, cout, k, s, p, bias=True).cuda()
+    else:
+        m = nn.ConvTranspose2d(cin, cout, k, s, p, output_padding=op, bias=True).cuda()
+    with torch.no_grad():
+        m.weight.copy_(_bf(torch.randn_like(m.weight) * 0.2))
+        m.bias.copy_(_bf(torch.randn_like(m.bias)))
+    g = pkg("graph.encodingBlock").gemm_of(m)
+    x = _bf(torch.randn(B, cin, H, W, device="cuda")).requires_grad_(True)
+    ref = m(x)
+    OH, OW = ref.shape[2], ref.shape[3]
+    assert (OH, OW) == g.out_hw(H, W)
+    dyt = _bf(torch.randn_like(ref))
+    ref.backward(dyt)
+    ref_dx, ref_dw, ref_db = x.grad.clone(), m.weight.grad.clone(), m.bias.grad.clone()
+    m.weight.grad = None
+    m.bias.grad = None
+
+    eng.set_impl(lib.IMPL_SIMT if impl == "simt" else lib.IMPL_AUTO)
+    try:
+        xa = eng.Act(nhwc(x.detach()).to(BF16), B, H, W, cin)
+        y = eng.Act.empty(B, OH, OW, cout, dtype=torch.float32)
+        y.t.fill_(float("nan"))
+        g.forward(xa, y)
+        e_f = rel_fro(nchw(y.t), ref)
+        dya = eng.Act(nhwc(dyt).to(BF16), B, OH, OW, cout)
+        dx = eng.Act.empty(B, H, W, cin, dtype=torch.float32)
+        dx.t.fill_(float("nan"))
+        g.dgrad(dya, dx)
+        e_d = rel_fro(nchw(dx.t), ref_dx)
+        g.wgrad(xa, dya)
+        g.bias_grad(dya)
+        e_w = rel_fro(m.weight.grad, ref_dw)
+        e_b = rel_fro(m.bias.grad, ref_db)
+        # bf16 output + fused epilogue: bias, ReLU, addend, mask
+        y2 = eng.Act.empty(B, OH, OW, cout)
+        g.forward(xa, y2, act=True, slope=0.01)
+        e_a = rel_fro(nchw(y2.t.float()), F.leaky_relu(ref, 0.01))
+        add = eng.Act(torch.randn(B, H, W, cin, device="cuda").to(BF16), B, H, W, cin)
+        msk = eng.Act(torch.randn(B, H, W, cin, device="cuda").to(BF16), B, H, W, cin)
+        dx2 = eng.Act.empty(B, H, W, cin)
+        g.dgrad(dya, dx2, addend=add, mask=msk, mask_slope=0.01)
+        want = (ref_dx + nchw(add.t.float())) * torch.where(nchw(msk.t.float()) > 0, 1.0, 0.01)
+        e_m = rel_fro(nchw(dx2.t.float()), want)
+    finally:
+        eng.set_impl(lib.IMPL_AUTO)
+    report(test="gemm_layer", impl=impl, spec=str(spec), fwd=e_f, dgrad=e_d, wgrad=e_w, bias=e_b, act=e_a, mask=e_m)
+    assert e_f < 2e-3 and e_d < 2e-3 and e_w < 2e-3 and e_b < 2e-3, (e_f, e_d, e_w, e_b)
+    assert e_a < 6e-3 and e_m < 6e-3, (e_a, e_m)        # bf16 output rounding (2^-9 per element)
+
+
+def _torch_block(y, gamma, beta, cb, res_mode, slope, res):
+    """fp32 reference of the fused norm block, NCHW (the same ops the reference modules call)."""
+    u = F.instance_norm(y, None, None, gamma, beta, True, 0.01, 1e-5)
+    if cb is None:
+        out = u
+    else:
+        w1, w2, wsp = cb
+        a = F.conv2d(F.relu(F.conv2d(F.adaptive_avg_pool2d(u, 1), w1)), w2)
+        m = F.conv2d(F.relu(F.conv2d(F.adaptive_max_pool2d(u, 1), w1)), w2)
+        u1 = u * torch.sigmoid(a + m)
+        sa = torch.cat([u1.mean(1, keepdim=True), u1.max(1, keepdim=True)[0]], 1)
+        c = u1 * torch.sigmoid(F.conv2d(sa, wsp, padding=1))
+        out = {1: u + c, 2: (res + c) if res is not None else c, 3: c}[res_mode]
+    return F.leaky_relu(out, slope) if slope != 0 else F.relu(out)
+
+
+@pytest.mark.parametrize("C,H,W", [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60)])
+@pytest.mark.parametrize("mode", ["plain", "self", "ext"])
+@pytest.mark.parametrize("raw", ["f32", "bf16"])
+def test_norm_block(C, H, W, mode, raw):
+    """InstanceNorm(+CBAM)(+residual)+act, forward and backward, vs PyTorch fp32 autograd.
+    Tolerance: rel-Frobenius 1.5e-2 on activations and gradients (bf16 storage of uhat / out / dy)."""
+    if raw == "bf16" and (C, H, W) not in [(64, 12, 8), (128, 24, 15)]:
+        pytest.skip("bf16 raw input covered on two shapes")
+    eng = pkg("engine")
+    torch.manual_seed(C + H)
+    B = 3
+    dev = "cuda"
+    slope = 0.01 if C == 32 else 0.0
+    y = torch.randn(B, C, H, W, device=dev) * 2.0 + torch.randn(1, C, 1, 1, device=dev) * 3.0
+    if raw == "bf16":
+        y = _bf(y)
+    gamma = (1 + 0.3 * torch.randn(C, device=dev)).requires_grad_(True)
+    beta = (0.3 * torch.randn(C, device=dev)).requires_grad_(True)
+    gamma.data[0] = -0.7                                     # negative gamma: max-pool of u follows min of y
+    res_mode = {"plain": 0, "self": 1, "ext": 2}[mode]
+    cb = None
+    if mode != "plain":
+        cb = ((torch.randn(C // 16, C, 1, 1, device=dev) * (2.0 / math.sqrt(C))).requires_grad_(True),
+              (torch.randn(C, C // 16, 1, 1, device=dev) * (2.0 / math.sqrt(C // 16))).requires_grad_(True),
+              (torch.randn(1, 2, 3, 3, device=dev) * 0.5).requires_grad_(True))
+    res = _bf(torch.randn(B, C, H, W, device=dev)).requires_grad_(True) if mode == "ext" else None
+    yr = y.clone().requires_grad_(True)
+    ref = _torch_block(yr, gamma, beta, cb, res_mode, slope, res)
+    dout = _bf(torch.randn_like(ref))
+    ref.backward(dout)
+
+    params = [gamma, beta] + (list(cb) if cb else [])
+    ref_grads = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    nb = eng.NormBlock(C, gamma, beta, cb, res_mode, slope)
+    ya = eng.Act(nhwc(y).to(torch.float32 if raw == "f32" else BF16), B, H, W, C)
+    out = eng.Act.empty(B, H, W, C)
+    ra = eng.Act(nhwc(res.detach()).to(BF16), B, H, W, C) if res is not None else None
+    ctx = nb.forward(ya, out, ra)
+    e_out = rel_fro(nchw(out.t.float()), ref)
+    dy = eng.Act.empty(B, H, W, C)
+    dres = eng.Act.empty(B, H, W, C) if res is not None else None
+    nb.backward(ctx, eng.Act(nhwc(dout).to(BF16), B, H, W, C), dy, dres)
+    e_dy = rel_fro(nchw(dy.t.float()), yr.grad)
+    errs = {"out": e_out, "dy": e_dy}
+    if res is not None:
+        errs["dres"] = rel_fro(nchw(dres.t.float()), res.grad)
+    names = ["dgamma", "dbeta", "dw1", "dw2", "dwsp"]
+    for nme, p, rg in zip(names, params, ref_grads):
+        errs[nme] = rel_fro(p.grad, rg)
+    report(test="norm_block", C=C, H=H, W=W, mode=mode, raw=raw, **errs)
+    bad = {k: v for k, v in errs.items() if not v < 1.5e-2}
+    assert not bad, errs
+
+
+def test_fit_sigmoid_bce():
+    """fit2 + sigmoid + BCE forward/backward (decoder.py:175,220; bar_loss.py:23-33) vs torch fp32.
+    Tolerance: 1e-5 relative on the loss, 3e-3 rel-Frobenius on gradients (dx is stored in bf16)."""
+    lib = pkg("_lib")
+    L = lib.lib()
+    torch.manual_seed(3)
+    B, H, W, C = 3, 96, 60, 64
+    rows = B * H * W
+    x = _bf(torch.randn(rows, C, device="cuda")).requires_grad_(True)
+    w = (torch.randn(C, device="cuda") * 0.5).requires_grad_(True)
+    t = (torch.rand(rows, device="cuda") < 0.1).float()
+    for smoothing in (0, 1):
+        for p in (x, w):
+            p.grad = None
+        logits = x @ w
+        p_ref = torch.sigmoid(logits)
+        tt = t
+        if smoothing:
+            O = __import__("barvae_oracle")
+            prior = torch.tensor(O.PITCH_PRIOR, device="cuda") * 0.08
+            tt = (t.view(-1, 60) * 0.82 + 0.1 / 60 + prior).view(-1)
+        ref_loss = F.binary_cross_entropy(p_ref, tt)
+        ref_loss.backward()
+        xb = x.detach().to(BF16).contiguous()
+        recon = torch.empty(rows, device="cuda")
+        lg = torch.empty(rows, device="cuda")
+        st = lib.stream_ptr()
+        lib.check(L.bvae_fit_sigmoid_fwd(xb.data_ptr(), C, w.data_ptr(), rows, C, lg.data_ptr(), recon.data_ptr(), st))
+        acc = torch.zeros(2, device="cuda")
+        lib.check(L.bvae_bce_fwd(recon.data_ptr(), t.data_ptr(), rows, smoothing, acc.data_ptr(), st))
+        miss = float(((t - (p_ref > 0.3).float()) > 1e-4).float().sum())
+        dx = torch.empty(rows, C, device="cuda", dtype=BF16)
+        dw = torch.zeros(C, device="cuda")
+        lib.check(L.bvae_fit_sigmoid_bce_bwd(xb.data_ptr(), C, w.data_ptr(), recon.data_ptr(), t.data_ptr(), None,
+                                             1.0 / rows, smoothing, rows, C, dx.data_ptr(), C, dw.data_ptr(), st))
+        e = dict(recon=rel_fro(recon, p_ref), loss=abs(float(acc[0]) - float(ref_loss)) / float(ref_loss),
+                 miss=abs(float(acc[1]) - miss), dx=rel_fro(dx.float(), x.grad), dw=rel_fro(dw, w.grad))
+        report(test="fit_sigmoid_bce", smoothing=smoothing, **e)
+        assert e["recon"] < 1e-5 and e["loss"] < 1e-5 and e["miss"] <= 2 and e["dx"] < 3e-3 and e["dw"] < 1e-4, e
+
+
+def test_bce_clamp_edges(golden, oracle):
+    """the -100 log clamp and the 0.3 / 1e-4 thresholds on adversarial probabilities; golden from the reference Loss."""
+    Loss = pkg("graph.loss.bar_loss").Loss
+    c = golden["loss"]
+    p, t = c["probs"].cuda(), c["labels"].cuda()
+    for pre, key in ((True, "pre"), (False, "smooth")):
+        got = float(Loss()(p, t, pre))
+        want = float(c[key])
+        report(test="bce_clamp", pre=pre, got=got, want=want)
+        assert abs(got - want) <= 1e-5 * abs(want), (got, want)
+
+
+def test_reparam_kl(golden):
+    """reparameterise + KL vs the golden produced by old/graphs/models/bar_v1/encoder.py:60-63 and loss.py:16."""
+    M = pkg("graph.model")
+    c = golden["vae_head"]
+    mu = c["mean"].cuda().requires_grad_(True)
+    lv = c["logvar"].cuda().requires_grad_(True)
+    eps = c["eps"].cuda()
+    z = M.reparameterize(mu, lv, eps)
+    kl = M.kl_divergence(mu, lv)
+    assert rel_fro(z, c["z"]) < 1e-6
+    assert abs(float(kl) - float(c["kl"])) < 1e-4 * abs(float(c["kl"]))
+    g = torch.randn_like(z)
+    ((z * g).sum() + 0.5 * kl).backward()
+    mu2 = c["mean"].cuda().requires_grad_(True)
+    lv2 = c["logvar"].cuda().requires_grad_(True)
+    z2 = mu2 + eps * torch.exp(0.5 * lv2)
+    kl2 = -0.5 * torch.sum(1 + lv2 - mu2.pow(2) - lv2.exp())
+    ((z2 * g).sum() + 0.5 * kl2).backward()
+    assert rel_fro(mu.grad, mu2.grad) < 1e-5 and rel_fro(lv.grad, lv2.grad) < 1e-5
+
+
+def test_flat_adam():
+    """fused flat Adam vs torch.optim.Adam (agent/barGen.py:61-62), 3 steps.  Tolerance 1e-6 relative."""
+    eng = pkg("engine")
+    torch.manual_seed(5)
+    net = nn.Sequential(nn.Linear(37, 53), nn.Linear(53, 11)).cuda()
+    ref = nn.Sequential(nn.Linear(37, 53), nn.Linear(53, 11)).cuda()
+    ref.load_state_dict(net.state_dict())
+    flat = eng.flatten(net)
+    opt = torch.optim.Adam(ref.parameters(), lr=0.002)
+    for step in range(1, 4):
+        x = torch.randn(19, 37, device="cuda")
+        flat.attach_grads()
+        net(x).pow(2).mean().backward()
+        opt.zero_grad()
+        ref(x).pow(2).mean().backward()
+        opt.step()
+        eng.adam_step(flat, 0.002, step)
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert rel_fro(a, b) < 1e-6
