@@ -1,8 +1,657 @@
-// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM kernels (placeholder until the kernels land).
+// conv_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM kernels for sm_100a.
+//
+// conv_tc_kernel  (forward + data gradient, operands K-major):
+//   D[128 pixels x BN channels] (fp32, TMEM) = sum over (tap, channel block) A[128 x KB] * B[BN x KB]^T
+//   A = activation patch: ONE tiled TMA box {KB channels, bw, bh, bn} of an NHWC view per (tap, channel block);
+//       the tap shift is a coordinate offset, padding is TMA out-of-bounds zero fill, a strided (stride-2 / k==s)
+//       access is a view whose base pointer and strides select the sub-lattice -- no im2col buffer, no gather code.
+//   B = packed bf16 weights [Cout][tap][C], one 2-D TMA box {KB, BN}.
+//   Both land in shared memory in the canonical 128B (KB=64) / 64B (KB=32) swizzled K-major layout, are consumed by
+//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) issued by one thread, accumulate in TMEM and are read
+//   back with tcgen05.ld for the fused epilogue (bias, (Leaky)ReLU, addend, ReLU-backward mask, bf16/fp32 store
+//   with the phase's output stride).
+//
+// wgrad_tc_kernel (weight gradient, operands MN-major):
+//   D_tap[128 anchor channels x NS shifted channels] = sum over pixel blocks  Anchor[pix x 128]^T * Shifted_tap[pix x NS]
+//   the contraction index (pixels) is the slow axis of both NHWC tensors, so both operands are MN-major; the same
+//   pixel-box TMA loads feed it.  Split over pixel ranges across CTAs, reduced with fp32 red.global.add into the
+//   parameter-layout gradient.
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
 #include "common.cuh"
+
 namespace bvae {
-int conv_tc_eligible(const bvae_conv_desc*) { return 0; }
-int conv_tc_launch(const bvae_conv_desc*, cudaStream_t) { set_error("tcgen05 conv not built"); return BVAE_ERR_UNSUPPORTED; }
-int wgrad_tc_eligible(const bvae_wgrad_desc*) { return 0; }
-int wgrad_tc_launch(const bvae_wgrad_desc*, cudaStream_t) { set_error("tcgen05 wgrad not built"); return BVAE_ERR_UNSUPPORTED; }
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout type [61,64)  (2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// parameters (passed as one __grid_constant__ struct; tensor maps must stay 64-byte aligned)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int MAX_VIEWS = 6;
+
+struct alignas(64) ConvTcParams {
+  CUtensorMap amap[MAX_VIEWS];
+  CUtensorMap bmap;
+  int tap_view[BVAE_MAX_TAPS];
+  int tap_ex[BVAE_MAX_TAPS];
+  int tap_ey[BVAE_MAX_TAPS];
+  int ntaps, kchunks, C;
+  int bw, bh, bn, tiles_w, tiles_h, tiles_n, n_tiles;
+  int N, QH, QW, Cout;
+  void* y;
+  const float* bias;
+  const void* addend;
+  const void* mask;
+  int OH, OW, y_pitch, osy, osx, ooy, oox, add_pitch, mask_pitch, act, out_f32;
+  float slope, mask_slope;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// forward / dgrad kernel.  128 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// then all four warps run the epilogue (warp w owns TMEM lanes 32w..32w+31 = tile rows).
+// ---------------------------------------------------------------------------------------------------------
+template <int KB, int BN, int STAGES>
+__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int A_BYTES = 128 * KB * 2;
+  constexpr int B_BYTES = BN * KB * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr uint32_t LAYOUT = KB == 64 ? 2u : 4u;           // SWIZZLE_128B : SWIZZLE_64B
+  constexpr uint32_t SBO = 8 * KB * 2;                      // 8 rows of KB bf16
+  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  float* s_bias = (float*)(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % p.n_tiles;
+  int m_tile = blockIdx.x / p.n_tiles;
+  const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+  const int th = m_tile % p.tiles_h;
+  const int tn = m_tile / p.tiles_h;
+  const int KT = p.ntaps * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.bmap);
+    tma_prefetch_desc(&p.amap[0]);
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < BN; i += 128) s_bias[i] = p.bias ? p.bias[n_tile * BN + i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    const uint32_t tx = (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + B_BYTES);
+    int kb = 0;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const CUtensorMap* am = &p.amap[p.tap_view[t]];
+      const int cw = tw * p.bw + p.tap_ex[t], ch = th * p.bh + p.tap_ey[t], cn = tn * p.bn;
+      for (int kc = 0; kc < p.kchunks; ++kc, ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar + s, ph ^ 1u);
+        mbar_expect_tx(full_bar + s, tx);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        tma_load_4d(sa, am, full_bar + s, kc * KB, cw, ch, cn);
+        tma_load_2d(sa + A_BYTES, &p.bmap, full_bar + s, t * p.C + kc * KB, n_tile * BN);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    for (int kb = 0; kb < KT; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+      const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
+      const uint64_t bdesc = make_sdesc(sa + A_BYTES, 16, SBO, LAYOUT);
+#pragma unroll
+      for (int j = 0; j < KB / 16; ++j)      // +32 bytes (= 2 in the >>4 encoded start address) per K=16 step
+        umma_f16(tmem_base, adesc + 2 * j, bdesc + 2 * j, IDESC, (kb | j) ? 1u : 0u);
+      umma_commit(empty_bar + s);            // frees the smem slot when these MMAs retire
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+
+  // ---------------- epilogue: TMEM -> registers -> global ----------------
+  const int r = threadIdx.x;
+  const int rows_box = p.bn * p.bh * p.bw;
+  const int nn = r / (p.bh * p.bw), hh = (r / p.bw) % p.bh, ww = r % p.bw;
+  const int n = tn * p.bn + nn, qy = th * p.bh + hh, qx = tw * p.bw + ww;
+  const bool valid = r < rows_box && n < p.N && qy < p.QH && qx < p.QW;
+  const int64_t opix = ((int64_t)n * p.OH + (qy * p.osy + p.ooy)) * p.OW + (qx * p.osx + p.oox);
+  const int col0 = n_tile * BN;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+    if (!valid) continue;
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      f[i] = __uint_as_float(v[i]) + s_bias[c0 + i];
+      if (p.act) f[i] = act_fwd(f[i], p.slope);
+    }
+    if (p.addend) {
+      if (p.out_f32) {
+        const float* ap = (const float*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + i);
+          f[i] += a.x; f[i + 1] += a.y; f[i + 2] += a.z; f[i + 3] += a.w;
+        }
+      } else {
+        const bf16* ap = (const bf16*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float a[8];
+          unpack8(ldg8(ap + i), a);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[i + k] += a[k];
+        }
+      }
+    }
+    if (p.mask) {
+      const bf16* mp = (const bf16*)p.mask + opix * p.mask_pitch + col0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float a[8];
+        unpack8(ldg8(mp + i), a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[i + k] *= (a[k] > 0.f) ? 1.f : p.mask_slope;
+      }
+    }
+    if (p.out_f32) {
+      float* yp = (float*)p.y + opix * p.y_pitch + col0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    } else {
+      bf16* yp = (bf16*)p.y + opix * p.y_pitch + col0 + c0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) stg8(yp + i, pack8(f + i));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight-gradient kernel
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) WgradTcParams {
+  CUtensorMap amap;                 // anchor tensor, box {64 ch, bw, bh, bn}
+  CUtensorMap smap[MAX_VIEWS];      // shifted tensor views, same box
+  int tap_view[BVAE_MAX_TAPS];
+  int tap_ex[BVAE_MAX_TAPS];
+  int tap_ey[BVAE_MAX_TAPS];
+  int tap_idx[BVAE_MAX_TAPS];
+  int ntaps, T, tpc, tap_groups;    // taps per CTA, number of tap groups
+  int bw, bh, bn, chunks_w, chunks_h, chunks_n, nchunks, chunks_per_split, splits;
+  int a_atoms;                      // 64-channel atoms of the anchor tile actually loaded (1 or 2)
+  int ra_tiles, rs_tiles;
+  int Ca, Cs;
+  float* dw;
+};
+
+// NS = shifted-channel tile (multiple of 64, <= 256); KP = 64 pixel rows per stage
+template <int NS, int STAGES>
+__global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+  constexpr int KP = 64;
+  constexpr int ATOM_BYTES = KP * 128;                 // [64 pixel rows][64 channels] bf16, 128B-swizzled
+  constexpr int S_ATOMS = NS / 64;
+  constexpr int MAX_TPC = 512 / NS;
+  constexpr int STAGE_BYTES = (2 + MAX_TPC * S_ATOMS) * ATOM_BYTES;
+  constexpr uint32_t IDESC = make_idesc(128, NS, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int b = blockIdx.x;
+  const int split = b % p.splits; b /= p.splits;
+  const int tg = b % p.tap_groups; b /= p.tap_groups;
+  const int rs_tile = b % p.rs_tiles;
+  const int ra_tile = b / p.rs_tiles;
+  const int tap0 = tg * p.tpc;
+  const int ntap = min(p.tpc, p.ntaps - tap0);
+  const int ck0 = split * p.chunks_per_split;
+  const int ck1 = min(p.nchunks, ck0 + p.chunks_per_split);
+  const int rows_box = p.bn * p.bh * p.bw;             // <= 64, the rest of each atom stays zero
+
+  // zero the whole pipeline buffer once: rows a box never writes must contribute exactly 0 to the contraction
+  for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.amap);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    const uint32_t tx = (uint32_t)(rows_box * 128 * (p.a_atoms + ntap * S_ATOMS));
+    int it = 0;
+    for (int ck = ck0; ck < ck1; ++ck, ++it) {
+      int q = ck;
+      const int cw = (q % p.chunks_w) * p.bw; q /= p.chunks_w;
+      const int ch = (q % p.chunks_h) * p.bh;
+      const int cn = (q / p.chunks_h) * p.bn;
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(empty_bar + s, ph ^ 1u);
+      mbar_expect_tx(full_bar + s, tx);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      for (int a = 0; a < p.a_atoms; ++a)
+        tma_load_4d(st + a * ATOM_BYTES, &p.amap, full_bar + s, (ra_tile * 2 + a) * 64, cw, ch, cn);
+      for (int t = 0; t < ntap; ++t) {
+        const int tap = tap0 + t;
+        const CUtensorMap* sm = &p.smap[p.tap_view[tap]];
+        for (int a = 0; a < S_ATOMS; ++a)
+          tma_load_4d(st + (2 + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * 64,
+                      cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn);
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const int ksteps = (rows_box + 15) / 16;
+    int it = 0;
+    for (int ck = ck0; ck < ck1; ++ck, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar + s, ph);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+      // MN-major, 128B swizzle: LBO = distance between 64-channel atoms, SBO = 8 pixel rows (1024 B)
+      const uint64_t adesc = make_sdesc(st, ATOM_BYTES, 1024, 2);
+      for (int t = 0; t < ntap; ++t) {
+        const uint64_t bdesc = make_sdesc(st + (2 + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, 1024, 2);
+        for (int j = 0; j < ksteps; ++j)     // 16 pixel rows = 2048 B per K step
+          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + 128 * j, bdesc + 128 * j, IDESC, (it | j) ? 1u : 0u);
+      }
+      umma_commit(empty_bar + s);
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+
+  // epilogue: lane = anchor channel, columns = shifted channels; scatter-add into the parameter layout
+  const int ra = ra_tile * 128 + threadIdx.x;
+  const bool valid = threadIdx.x < p.a_atoms * 64 && ra < p.Ca;
+  for (int t = 0; t < ntap; ++t) {
+    const int tix = p.tap_idx[tap0 + t];
+#pragma unroll 1
+    for (int c0 = 0; c0 < NS; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NS + c0), v);
+      if (!valid || ck1 <= ck0) continue;
+      float* dst = p.dw + ((int64_t)ra * p.Cs + rs_tile * NS + c0) * p.T + tix;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)i * p.T, __uint_as_float(v[i]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps, tile selection, dispatch
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+// 4-D map over a (possibly strided) NHWC view: dims {C, Wv, Hv, N}
+static int make_view_map(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int N, int64_t sw_elems,
+                         int64_t sh_elems, int64_t sn_elems, int box_c, int bw, int bh, int bn, bool sw128) {
+  EncodeTiledFn enc = get_encode();
+  BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw_elems * 2, (cuuint64_t)sh_elems * 2, (cuuint64_t)sn_elems * 2};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA,
+               "cuTensorMapEncodeTiled(4d) failed: %d (dims %d,%d,%d,%d strides %lld,%lld,%lld box %d,%d,%d,%d)", (int)r, C, Wv,
+               Hv, N, (long long)sw_elems * 2, (long long)sh_elems * 2, (long long)sn_elems * 2, box_c, bw, bh, bn);
+  return BVAE_OK;
+}
+
+static int make_w_map(CUtensorMap* m, const void* base, int K, int rows, int pitch, int box_k, int box_rows, bool sw128) {
+  EncodeTiledFn enc = get_encode();
+  BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_k, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled(2d) failed: %d (K %d rows %d pitch %d box %d,%d)",
+               (int)r, K, rows, pitch, box_k, box_rows);
+  return BVAE_OK;
+}
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+// choose the pixel box (bn, bh, bw) with bn*bh*bw <= cap that needs the fewest boxes to cover [N, QH, QW]
+static void pick_box(int N, int QH, int QW, int cap, int* bw_, int* bh_, int* bn_) {
+  static std::mutex mu;
+  static std::unordered_map<uint64_t, uint32_t> cache;
+  const uint64_t key = ((uint64_t)N << 40) | ((uint64_t)QH << 24) | ((uint64_t)QW << 8) | (uint64_t)(cap & 0xff);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *bw_ = it->second & 0x3ff; *bh_ = (it->second >> 10) & 0x3ff; *bn_ = (it->second >> 20) & 0x3ff;
+      return;
+    }
+  }
+  long best = -1;
+  int bbw = 1, bbh = 1, bbn = 1;
+  for (int bw = 1; bw <= QW && bw <= cap; ++bw) {
+    if (bw < QW && bw * 2 <= QW && (QW % bw) && bw < 8) continue;       // prune silly narrow boxes
+    for (int bh = 1; bh <= QH && bh * bw <= cap; ++bh) {
+      int bn = cap / (bw * bh);
+      if (bn > N) bn = N;
+      if (bn > 256) bn = 256;
+      if (bn < 1) continue;
+      const long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, bn);
+      if (best < 0 || tiles < best || (tiles == best && bw > bbw)) { best = tiles; bbw = bw; bbh = bh; bbn = bn; }
+    }
+  }
+  *bw_ = bbw; *bh_ = bbh; *bn_ = bbn;
+  std::lock_guard<std::mutex> g(mu);
+  cache[key] = (uint32_t)bbw | ((uint32_t)bbh << 10) | ((uint32_t)bbn << 20);
+}
+
+// Build the strided views a tap list needs.  A tap reads pixel (q*s + d): with d = s*e + f (0 <= f < s) this is
+// element (q + e) of the sub-lattice f, f+s, f+2s, ... -> one tensor map per distinct (fy, fx).
+struct ViewPlan {
+  int nviews;
+  int fy[MAX_VIEWS], fx[MAX_VIEWS];
+  int tap_view[BVAE_MAX_TAPS], tap_ex[BVAE_MAX_TAPS], tap_ey[BVAE_MAX_TAPS];
+};
+static bool plan_views(int ntaps, const int* dy, const int* dx, int sy, int sx, ViewPlan* vp) {
+  vp->nviews = 0;
+  for (int t = 0; t < ntaps; ++t) {
+    const int ey = floordiv(dy[t], sy), ex = floordiv(dx[t], sx);
+    const int fy = dy[t] - ey * sy, fx = dx[t] - ex * sx;
+    int v = -1;
+    for (int i = 0; i < vp->nviews; ++i)
+      if (vp->fy[i] == fy && vp->fx[i] == fx) v = i;
+    if (v < 0) {
+      if (vp->nviews == MAX_VIEWS) return false;
+      v = vp->nviews++;
+      vp->fy[v] = fy; vp->fx[v] = fx;
+    }
+    vp->tap_view[t] = v; vp->tap_ex[t] = ex; vp->tap_ey[t] = ey;
+  }
+  return true;
+}
+
+static int pick_bn(int Cout) {
+  const int cands[5] = {256, 192, 128, 64, 32};
+  for (int i = 0; i < 5; ++i)
+    if (Cout % cands[i] == 0) return cands[i];
+  return 0;
+}
+
+int conv_tc_eligible(const bvae_conv_desc* d) {
+  if (d->C % 32 || d->Cout % 32 || d->x_pitch % 8 || d->y_pitch % 8 || d->w_pitch % 8) return 0;
+  if (((uintptr_t)d->x | (uintptr_t)d->w) & 15) return 0;
+  if ((uintptr_t)d->y & 15) return 0;
+  if (d->addend && (((uintptr_t)d->addend & 15) || d->add_pitch % 8)) return 0;
+  if (d->mask && (((uintptr_t)d->mask & 15) || d->mask_pitch % 8)) return 0;
+  ViewPlan vp;
+  if (!plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp)) return 0;
+  return pick_bn(d->Cout) != 0;
+}
+
+template <int KB, int BN, int STAGES>
+static int launch_conv(const ConvTcParams& P, int grid, cudaStream_t stream) {
+  constexpr int smem = 1024 + STAGES * (128 * KB * 2 + BN * KB * 2) + (2 * STAGES + 1) * 8 + 8 + BN * 4;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<KB, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "conv_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  conv_tc_kernel<KB, BN, STAGES><<<grid, 128, smem, stream>>>(P);
+  return check_launch("conv_tc");
+}
+
+int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
+  ConvTcParams P;
+  memset(&P, 0, sizeof(P));
+  const bool sw128 = (d->C % 64 == 0);
+  const int KB = sw128 ? 64 : 32;
+  const int BN = pick_bn(d->Cout);
+  ViewPlan vp;
+  BVAE_REQUIRE(plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp), BVAE_ERR_UNSUPPORTED, "conv_tc: too many views");
+  pick_box(d->N, d->QH, d->QW, 128, &P.bw, &P.bh, &P.bn);
+  for (int v = 0; v < vp.nviews; ++v) {
+    const int Hv = ceil_div(d->H - vp.fy[v], d->sy), Wv = ceil_div(d->W - vp.fx[v], d->sx);
+    BVAE_REQUIRE(Hv > 0 && Wv > 0, BVAE_ERR_SHAPE, "conv_tc: empty view");
+    const bf16* base = (const bf16*)d->x + ((int64_t)vp.fy[v] * d->W + vp.fx[v]) * d->x_pitch;
+    int rc = make_view_map(&P.amap[v], base, d->C, Wv, Hv, d->N, (int64_t)d->sx * d->x_pitch,
+                           (int64_t)d->sy * d->W * d->x_pitch, (int64_t)d->H * d->W * d->x_pitch, KB, P.bw, P.bh, P.bn, sw128);
+    if (rc) return rc;
+  }
+  int rc = make_w_map(&P.bmap, d->w, d->ntaps * d->C, d->Cout, d->w_pitch, KB, BN, sw128);
+  if (rc) return rc;
+  for (int t = 0; t < d->ntaps; ++t) { P.tap_view[t] = vp.tap_view[t]; P.tap_ex[t] = vp.tap_ex[t]; P.tap_ey[t] = vp.tap_ey[t]; }
+  P.ntaps = d->ntaps; P.kchunks = d->C / KB; P.C = d->C;
+  P.tiles_w = ceil_div(d->QW, P.bw); P.tiles_h = ceil_div(d->QH, P.bh); P.tiles_n = ceil_div(d->N, P.bn);
+  P.n_tiles = d->Cout / BN;
+  P.N = d->N; P.QH = d->QH; P.QW = d->QW; P.Cout = d->Cout;
+  P.y = d->y; P.bias = d->bias; P.addend = d->addend; P.mask = d->mask;
+  P.OH = d->OH; P.OW = d->OW; P.y_pitch = d->y_pitch; P.osy = d->osy; P.osx = d->osx; P.ooy = d->ooy; P.oox = d->oox;
+  P.add_pitch = d->add_pitch; P.mask_pitch = d->mask_pitch; P.act = d->act; P.out_f32 = d->out_f32;
+  P.slope = d->slope; P.mask_slope = d->mask_slope;
+  const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
+  BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "conv_tc: grid too large");
+#define CONV_CASE(kb, bn, st) if (KB == kb && BN == bn) return launch_conv<kb, bn, st>(P, (int)grid, stream)
+  CONV_CASE(64, 256, 4); CONV_CASE(64, 192, 4); CONV_CASE(64, 128, 3); CONV_CASE(64, 64, 4); CONV_CASE(64, 32, 4);
+  CONV_CASE(32, 256, 4); CONV_CASE(32, 192, 4); CONV_CASE(32, 128, 4); CONV_CASE(32, 64, 4); CONV_CASE(32, 32, 4);
+#undef CONV_CASE
+  set_error("conv_tc: no kernel for KB=%d BN=%d", KB, BN);
+  return BVAE_ERR_UNSUPPORTED;
+}
+
+int wgrad_tc_eligible(const bvae_wgrad_desc* d) {
+  if (d->Ca % 64 || d->Cs % 64 || d->a_pitch % 8 || d->s_pitch % 8) return 0;
+  if (((uintptr_t)d->a | (uintptr_t)d->s) & 15) return 0;
+  ViewPlan vp;
+  return plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp) ? 1 : 0;
+}
+
+template <int NS, int STAGES>
+static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
+  constexpr int smem = 1024 + STAGES * (2 + (512 / NS) * (NS / 64)) * 8192 + (2 * STAGES + 1) * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<NS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  wgrad_tc_kernel<NS, STAGES><<<grid, 128, smem, stream>>>(P);
+  return check_launch("wgrad_tc");
+}
+
+int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
+  WgradTcParams P;
+  memset(&P, 0, sizeof(P));
+  ViewPlan vp;
+  BVAE_REQUIRE(plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp), BVAE_ERR_UNSUPPORTED, "wgrad_tc: too many views");
+  const int NS = d->Cs % 256 == 0 ? 256 : (d->Cs % 128 == 0 ? 128 : 64);
+  pick_box(d->N, d->AH, d->AW, 64, &P.bw, &P.bh, &P.bn);
+  int rc = make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
+                         (int64_t)d->AH * d->AW * d->a_pitch, 64, P.bw, P.bh, P.bn, true);
+  if (rc) return rc;
+  for (int v = 0; v < vp.nviews; ++v) {
+    const int Hv = ceil_div(d->SH - vp.fy[v], d->sy), Wv = ceil_div(d->SW - vp.fx[v], d->sx);
+    BVAE_REQUIRE(Hv > 0 && Wv > 0, BVAE_ERR_SHAPE, "wgrad_tc: empty view");
+    const bf16* base = (const bf16*)d->s + ((int64_t)vp.fy[v] * d->SW + vp.fx[v]) * d->s_pitch;
+    rc = make_view_map(&P.smap[v], base, d->Cs, Wv, Hv, d->N, (int64_t)d->sx * d->s_pitch,
+                       (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, 64, P.bw, P.bh, P.bn, true);
+    if (rc) return rc;
+  }
+  for (int t = 0; t < d->ntaps; ++t) {
+    P.tap_view[t] = vp.tap_view[t]; P.tap_ex[t] = vp.tap_ex[t]; P.tap_ey[t] = vp.tap_ey[t]; P.tap_idx[t] = d->tap_idx[t];
+  }
+  P.ntaps = d->ntaps; P.T = d->T;
+  const int max_tpc = 512 / NS;
+  P.tap_groups = ceil_div(d->ntaps, max_tpc);
+  P.tpc = ceil_div(d->ntaps, P.tap_groups);
+  P.chunks_w = ceil_div(d->AW, P.bw); P.chunks_h = ceil_div(d->AH, P.bh); P.chunks_n = ceil_div(d->N, P.bn);
+  P.nchunks = P.chunks_w * P.chunks_h * P.chunks_n;
+  P.ra_tiles = ceil_div(d->Ca, 128); P.rs_tiles = d->Cs / NS;
+  P.a_atoms = d->Ca >= 128 ? 2 : 1;
+  P.Ca = d->Ca; P.Cs = d->Cs; P.dw = d->dw;
+  const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
+  int splits = ceil_div(148 * 2, out_tiles);
+  const int max_splits = ceil_div(P.nchunks, 8);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  P.chunks_per_split = ceil_div(P.nchunks, splits);
+  P.splits = ceil_div(P.nchunks, P.chunks_per_split);
+  const long grid = (long)out_tiles * P.splits;
+  BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "wgrad_tc: grid too large");
+  if (NS == 256) return launch_wgrad<256, 2>(P, (int)grid, stream);
+  if (NS == 128) return launch_wgrad<128, 2>(P, (int)grid, stream);
+  return launch_wgrad<64, 2>(P, (int)grid, stream);
+}
+
+}  // namespace bvae

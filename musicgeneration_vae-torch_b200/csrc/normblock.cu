@@ -252,21 +252,22 @@ __device__ __forceinline__ float sa_conv(const float* __restrict__ sa_n, const f
 // forward 4 (CBAM only): gs = sigmoid(conv3x3(sa)); out = act(r + u*gc*gs)
 // grid (pchunks, N), block 256, dyn smem 3*C floats
 // ---------------------------------------------------------------------------------------------------
-template <int ITERS>
-__global__ void __launch_bounds__(256) nb_apply_kernel(const bf16* __restrict__ uhat, int H, int W, int C,
-                                                       const float* __restrict__ nc, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const float* __restrict__ wsp,
+template <bool F32, int ITERS>
+__global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ y, int y_pitch, int H, int W, int C,
+                                                       const float* __restrict__ nc, const float* __restrict__ wsp,
                                                        const float* __restrict__ sa, int res_mode,
                                                        const bf16* __restrict__ res, int res_pitch, float slope,
                                                        bf16* __restrict__ out, int out_pitch, float* __restrict__ gs,
                                                        int ppc) {
+  // u is recomputed from the raw fp32 conv output (not from the bf16 uhat) so that the sign of the block output --
+  // the ReLU mask the backward pass uses -- agrees with an fp32 evaluation
   extern __shared__ float sm[];
-  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C;
+  float* s_a = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C;
   __shared__ float s_w[18];
   const int n = blockIdx.y, HW = H * W;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    s_g[c] = gamma[c]; s_b[c] = beta[c];
-    s_gc[c] = nc[((int64_t)n * C + c) * NC_W + NC_GC];
+    const float* q = nc + ((int64_t)n * C + c) * NC_W;
+    s_a[c] = q[NC_A]; s_b[c] = q[NC_B]; s_gc[c] = q[NC_GC];
   }
   if (threadIdx.x < 18) s_w[threadIdx.x] = wsp[threadIdx.x];
   __syncthreads();
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const bf16* __restrict__ 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
-  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
+  const int64_t ybase = (int64_t)n * HW * y_pitch, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
   const float* sa_n = sa + (int64_t)n * HW * 2;
   for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
     const int p = pb + grp;
@@ -289,12 +290,12 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const bf16* __restrict__ 
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
-      float uh[8], r[8], o[8];
-      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
+      float v[8], r[8], o[8];
+      load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
       if (res_mode == 2) unpack8(ldg8(res + rbase + (int64_t)p * res_pitch + c), r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float u = s_g[c + i] * uh[i] + s_b[c + i];
+        const float u = s_a[c + i] * v[i] + s_b[c + i];
         const float cb = u * s_gc[c + i] * g;
         const float rr = res_mode == 1 ? u : (res_mode == 2 ? r[i] : 0.f);
         o[i] = act_fwd(rr + cb, slope);
@@ -434,7 +435,29 @@ __global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const floa
   if (threadIdx.x < 18) atomicAdd(dwsp + threadIdx.x, s_red[threadIdx.x]);
 }
 
-// backward 2: du (-> dy buffer, bf16), dres, and per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += ...
+// gradient wrt u for 8 channels of one pixel (shared by the reduction pass and the final pass, so that du is
+// never rounded to bf16 before the InstanceNorm projection removes its common-mode part)
+__device__ __forceinline__ void nb_du8(const float* uh, const float* o, const float* d, int c, const float* s_g,
+                                       const float* s_b, const float* s_gc, int has_cbam, int res_mode, float slope,
+                                       float g, float dmean, float dmax, int ci, float* du, float* dsv, float* dspu) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
+    dsv[i] = ds;
+    float v = (res_mode == 0 || res_mode == 1) ? ds : 0.f;
+    float su = 0.f;
+    if (has_cbam) {
+      const float gc = s_gc[c + i];
+      const float dsp = dmean + ((c + i) == ci ? dmax : 0.f);   // grad wrt u1 = u*gc from the spatial branch
+      v += ds * gc * g + dsp * gc;
+      su = dsp * (s_g[c + i] * uh[i] + s_b[c + i]);
+    }
+    du[i] = v;
+    dspu[i] = su;
+  }
+}
+
+// backward 2: per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += ...; writes dres
 template <int ITERS>
 __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
                                                       const bf16* __restrict__ out, int out_pitch,
@@ -459,7 +482,7 @@ __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ d
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
-  const int64_t ybase = (int64_t)n * HW * dy_pitch, rbase = (int64_t)n * HW * dres_pitch;
+  const int64_t rbase = (int64_t)n * HW * dres_pitch;
   const float invC = 1.f / (float)C;
   float a1[ITERS][8], a2[ITERS][8], a3[ITERS][8];
 #pragma unroll
@@ -481,26 +504,17 @@ __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ d
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
-      float uh[8], o[8], d[8], du[8], dsv[8];
+      float uh[8], o[8], d[8], du[8], dsv[8], dspu[8];
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
       unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
       unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
+      nb_du8(uh, o, d, c, s_g, s_b, s_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
-        dsv[i] = ds;
-        float v = (res_mode == 0 || res_mode == 1) ? ds : 0.f;
-        if (has_cbam) {
-          const float gc = s_gc[c + i];
-          const float dsp = dmean + ((c + i) == ci ? dmax : 0.f);   // grad wrt u1 = u*gc from the spatial branch
-          v += ds * gc * g + dsp * gc;
-          a3[it][i] += dsp * (s_g[c + i] * uh[i] + s_b[c + i]);
-        }
-        du[i] = v;
-        a1[it][i] += v;
-        a2[it][i] += v * uh[i];
+        a1[it][i] += du[i];
+        a2[it][i] += du[i] * uh[i];
+        a3[it][i] += dspu[i];
       }
-      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(du));
       if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * dres_pitch + c, pack8(dsv));
     }
   }
@@ -584,19 +598,27 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
   }
 }
 
-// backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2), in place over du
+// backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2); du is recomputed in fp32
 template <int ITERS>
-__global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ uhat, int HW, int C,
+__global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                      const bf16* __restrict__ out, int out_pitch,
+                                                      const bf16* __restrict__ uhat, int HW, int C,
                                                       const float* __restrict__ nc,
                                                       const int32_t* __restrict__ nc_idx,
-                                                      const float* __restrict__ bwd_nc, int has_cbam,
-                                                      bf16* __restrict__ dy, int dy_pitch, int ppc) {
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ gs, const int32_t* __restrict__ cidx,
+                                                      const float* __restrict__ bwd_px,
+                                                      const float* __restrict__ bwd_nc, int has_cbam, int res_mode,
+                                                      float slope, bf16* __restrict__ dy, int dy_pitch, int ppc) {
   extern __shared__ float sm[];
-  float* s_a = sm; float* s_m1 = sm + C; float* s_m2 = sm + 2 * C; float* s_dmx = sm + 3 * C;
-  int* s_idx = (int*)(sm + 4 * C);
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_a = sm + 3 * C;
+  float* s_m1 = sm + 4 * C; float* s_m2 = sm + 5 * C; float* s_dmx = sm + 6 * C;
+  int* s_idx = (int*)(sm + 7 * C);
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int64_t o = (int64_t)n * C + c;
+    s_g[c] = gamma[c]; s_b[c] = beta[c];
+    s_gc[c] = nc[o * NC_W + NC_GC];
     s_a[c] = nc[o * NC_W + NC_A];
     s_m1[c] = bwd_nc[o * BN_W + BN_S1];
     s_m2[c] = bwd_nc[o * BN_W + BN_S2];
@@ -608,22 +630,35 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ u
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
-  const int64_t ubase = (int64_t)n * HW * C, ybase = (int64_t)n * HW * dy_pitch;
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
+  const int64_t ybase = (int64_t)n * HW * dy_pitch;
+  const float invC = 1.f / (float)C;
   for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
     const int p = pb + grp;
     if (p >= p_end) continue;
+    float g = 0.f, dmean = 0.f, dmax = 0.f;
+    int ci = -1;
+    if (has_cbam) {
+      const int64_t o = (int64_t)n * HW + p;
+      g = gs[o];
+      dmean = bwd_px[o * BP_W + BP_DMEAN] * invC;
+      dmax = bwd_px[o * BP_W + BP_DMAX];
+      ci = cidx[o];
+    }
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
-      float uh[8], du[8], o[8];
+      float uh[8], o[8], d[8], du[8], dsv[8], dspu[8], r[8];
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
-      unpack8(ldg8(dy + ybase + (int64_t)p * dy_pitch + c), du);
+      unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
+      unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
+      nb_du8(uh, o, d, c, s_g, s_b, s_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float extra = (p == s_idx[c + i]) ? s_dmx[c + i] : 0.f;
-        o[i] = s_a[c + i] * (du[i] + extra - s_m1[c + i] - uh[i] * s_m2[c + i]);
+        r[i] = s_a[c + i] * (du[i] + extra - s_m1[c + i] - uh[i] * s_m2[c + i]);
       }
-      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(o));
+      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
     }
   }
 }
@@ -715,9 +750,14 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
 
   const size_t sm4 = 3 * C * sizeof(float);
   DISPATCH_ITERS(iters, {
-    nb_apply_kernel<IT><<<g3, 256, sm4, st>>>((const bf16*)d->uhat, d->H, d->W, C, d->nc, d->gamma, d->beta, d->wsp,
-                                               d->sa, d->res_mode, (const bf16*)d->res, d->res_pitch, d->slope,
-                                               (bf16*)d->out, d->out_pitch, d->gs, ppc);
+    if (d->y_f32)
+      nb_apply_kernel<true, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->wsp, d->sa, d->res_mode,
+                                                       (const bf16*)d->res, d->res_pitch, d->slope, (bf16*)d->out,
+                                                       d->out_pitch, d->gs, ppc);
+    else
+      nb_apply_kernel<false, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->wsp, d->sa, d->res_mode,
+                                                        (const bf16*)d->res, d->res_pitch, d->slope, (bf16*)d->out,
+                                                        d->out_pitch, d->gs, ppc);
   });
   return check_launch("nb_apply");
 }
@@ -759,9 +799,11 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   nb_bwd_coef_kernel<<<N, 256, smc, st>>>(HW, C, d->has_cbam, d->Cr, d->nc, d->beta, d->w1, d->w2, d->bwd_nc, d->dgamma,
                                           d->dbeta, d->dw1, d->dw2);
   if ((rc = check_launch("nb_bwd_coef"))) return rc;
-  const size_t sm5 = 5 * C * sizeof(float);
+  const size_t sm5 = 8 * C * sizeof(float);
   DISPATCH_ITERS(iters, {
-    nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->uhat, HW, C, d->nc, d->nc_idx, d->bwd_nc, d->has_cbam,
+    nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
+                                              (const bf16*)d->uhat, HW, C, d->nc, d->nc_idx, d->gamma, d->beta, d->gs,
+                                              d->cidx, d->bwd_px, d->bwd_nc, d->has_cbam, d->res_mode, d->slope,
                                               (bf16*)d->dy, d->dy_pitch, ppc);
   });
   return check_launch("nb_bwd3");

@@ -14,6 +14,9 @@ from gpu_util import nchw, nhwc, pkg, rel_fro, report
 
 pytestmark = pytest.mark.gpu
 BF16 = torch.bfloat16
+# the PyTorch side of every comparison must be true fp32 (cuDNN/cuBLAS default to TF32 for convs on this GPU)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def _bf(t):
@@ -119,7 +122,8 @@ def _torch_block(y, gamma, beta, cb, res_mode, slope, res):
 @pytest.mark.parametrize("raw", ["f32", "bf16"])
 def test_norm_block(C, H, W, mode, raw):
     """InstanceNorm(+CBAM)(+residual)+act, forward and backward, vs PyTorch fp32 autograd.
-    Tolerance: rel-Frobenius 1.5e-2 on activations and gradients (bf16 storage of uhat / out / dy)."""
+    Tolerance: rel-Frobenius 1e-2 on activations and gradients (bf16 storage of uhat / out / dy; a single ReLU
+    mask flip on the 3x2 maps is already 0.7 %)."""
     if raw == "bf16" and (C, H, W) not in [(64, 12, 8), (128, 24, 15)]:
         pytest.skip("bf16 raw input covered on two shapes")
     eng = pkg("engine")
@@ -166,7 +170,7 @@ def test_norm_block(C, H, W, mode, raw):
     for nme, p, rg in zip(names, params, ref_grads):
         errs[nme] = rel_fro(p.grad, rg)
     report(test="norm_block", C=C, H=H, W=W, mode=mode, raw=raw, **errs)
-    bad = {k: v for k, v in errs.items() if not v < 1.5e-2}
+    bad = {k: v for k, v in errs.items() if not v < 1e-2}
     assert not bad, errs
 
 
