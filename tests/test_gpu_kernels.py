@@ -41,15 +41,43 @@ LAYERS = [
 
 
 @pytest.mark.parametrize("spec", LAYERS, ids=lambda s: "%s_%dto%d_k%dx%d_s%dx%d" % (s[0], s[1], s[2], *s[3], *s[4]))
-@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 def test_gemm_layer(spec, impl):
     """forward / data-gradient / weight-gradient of one layer vs torch.nn.functional (fp32).
     Tolerance: rel-Frobenius 2e-3 (fp32 outputs; operands are bf16-exact, so this is accumulation-order noise)."""
     eng = pkg("engine")
     lib = pkg("_lib")
     kind, cin, cout, k, s, p, op, H, W = spec
+    if impl == "tc" and cin == 1:
+        pytest.skip("C_in = 1 stems run on the SIMT kernel by design")
+    _run_gemm_layer(spec, impl, 3)
+
+
+BIG_LAYERS = [
+    ("conv", 128, 256, (3, 3), (2, 2), (1, 1), (0, 0), 24, 15, 9),           # several M tiles, N tile 256
+    ("conv", 256, 256, (3, 3), (1, 1), (1, 1), (0, 0), 12, 8, 11),           # boxes spanning several samples
+    ("conv", 512, 1024, (3, 3), (2, 2), (1, 1), (0, 0), 6, 4, 7),            # 4 N tiles, K = 4608
+    ("conv", 2048, 1024, (1, 1), (1, 1), (0, 0), (0, 0), 6, 3, 5),           # decoder.fit1
+    ("conv", 2304, 1152, (1, 1), (1, 1), (0, 0), (0, 0), 1, 1, 130),         # Linear 2304 -> 1152 (N tile 192)
+    ("convT", 2304, 1024, (6, 1), (6, 1), (0, 0), (0, 0), 1, 1, 33),         # decoder.time.time
+    ("convT", 1024, 512, (4, 4), (2, 2), (1, 1), (0, 1), 6, 3, 6),           # decoder.layers.0.deConv1
+    ("convT", 128, 64, (3, 3), (2, 2), (1, 1), (1, 1), 48, 30, 2),           # decoder.layers.3.deConv2
+    ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 48, 30, 4),             # encoder.layers.0
+    ("conv", 32, 32, (1, 4), (1, 2), (0, 1), (0, 0), 192, 60, 2),            # phrase stem (KB = 32, SWIZZLE_64B)
+]
+
+
+@pytest.mark.parametrize("spec", BIG_LAYERS, ids=lambda s: "%s_%dto%d_k%dx%d_B%d" % (s[0], s[1], s[2], *s[3], s[9]))
+def test_gemm_layer_tc_big(spec):
+    """the tcgen05 kernels at multi-tile sizes (several M / N tiles, long K loops, split-K weight gradients)"""
+    _run_gemm_layer(spec[:9], "tc", spec[9])
+
+
+def _run_gemm_layer(spec, impl, B):
+    eng = pkg("engine")
+    lib = pkg("_lib")
+    kind, cin, cout, k, s, p, op, H, W = spec
     torch.manual_seed(1)
-    B = 3
     if kind == "conv":
         m = nn.Conv2d(cin, cout, k, s, p, bias=True).cuda()
     else:
@@ -68,7 +96,7 @@ def test_gemm_layer(spec, impl):
     m.weight.grad = None
     m.bias.grad = None
 
-    eng.set_impl(lib.IMPL_SIMT if impl == "simt" else lib.IMPL_AUTO)
+    eng.set_impl(lib.IMPL_SIMT if impl == "simt" else lib.IMPL_TC)
     try:
         xa = eng.Act(nhwc(x.detach()).to(BF16), B, H, W, cin)
         y = eng.Act.empty(B, OH, OW, cout, dtype=torch.float32)
@@ -96,7 +124,7 @@ def test_gemm_layer(spec, impl):
         e_m = rel_fro(nchw(dx2.t.float()), want)
     finally:
         eng.set_impl(lib.IMPL_AUTO)
-    report(test="gemm_layer", impl=impl, spec=str(spec), fwd=e_f, dgrad=e_d, wgrad=e_w, bias=e_b, act=e_a, mask=e_m)
+    report(test="gemm_layer", impl=impl, B=B, spec=str(spec), fwd=e_f, dgrad=e_d, wgrad=e_w, bias=e_b, act=e_a, mask=e_m)
     assert e_f < 2e-3 and e_d < 2e-3 and e_w < 2e-3 and e_b < 2e-3, (e_f, e_d, e_w, e_b)
     assert e_a < 6e-3 and e_m < 6e-3, (e_a, e_m)        # bf16 output rounding (2^-9 per element)
 
