@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- bar-VAE generator training throughput (bars/s) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libbarvae.so)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path over one batch of synthetic piano-roll bars: zero_grad, generator forward
+(phrase encoder, encoder x2, decoder), BCE loss, backward, (NCCL gradient all-reduce), Adam -- the pre-training
+branch of the reference's agent/barGen.py:249-252,302-335.  Workload = BASELINE.json configs[1]: batch 512 bars per
+GPU, bf16 tensor-core arithmetic with fp32 accumulation/statistics/parameters.  Weak scaling: 512 bars per GPU at
+every N (N = 8 is configs[2]'s global batch 4096).
+
+One JSON line on stdout (rank 0).  `value` = whole-job bars/s with inputs resident in HBM; `e2e` = the same step
+driven through the public nn.Module API from pinned HOST tensors (H2D copy of the batch and D2H read of the loss
+inside the timed region).  `roofline` = the contraction kernels (tcgen05 implicit GEMMs) timed live with CUDA events.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG = "musicgeneration_vae-torch_b200"
+
+# algorithmic work per bar: forward 9.8314 GFLOP, forward+backward 29.494 GFLOP
+GFLOP_PER_BAR_TRAIN = 29.494
+N_PARAMS = 89537290
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1383.1), d.get("hbm_gbs", 6547.8), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(B, seed, device, pin=False):
+    """binary piano-roll bars at ~5 % density (agent/barGen.py:134-141 shapes)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    note = (torch.rand(B, 1, 96, 60, generator=g) < 0.05).float()
+    pre_note = (torch.rand(B, 1, 96, 60, generator=g) < 0.05).float()
+    phrase = (torch.rand(B, 1, 384, 60, generator=g) < 0.05).float()
+    position = torch.randint(0, 332, (B,), generator=g)
+    ts = (note, pre_note, phrase, position)
+    if device is not None:
+        return tuple(t.to(device) for t in ts)
+    return tuple(t.pin_memory() for t in ts) if pin else ts
+
+
+def cpu_reference_arm(batch, steps, warmup):
+    """The reference algorithm (CPU oracle port of graph/*.py + bar_loss.py + torch.optim.Adam semantics) on all host
+    cores; returns bars/s.  Bounded sample: `batch` bars per step."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import barvae_oracle as O
+    from collections import OrderedDict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict(O.generator_spec(), 0, "reference")
+    b = O.make_inputs(batch, 1234)
+    m = OrderedDict((k, torch.zeros_like(v)) for k, v in sd.items())
+    v = OrderedDict((k, torch.zeros_like(t)) for k, t in sd.items())
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.train_step(sd, b, m, v, i + 1, 0.002, None, True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return batch / dt, dt, cores, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="barvae", choices=["barvae", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="bars per GPU")
+    ap.add_argument("--cpu-batch", type=int, default=16, help="bars per step of the CPU arm (BASELINE configs[0])")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = {"workload": "barGen bar-VAE generator training step (fwd+bwd+Adam), %d bars/GPU, synthetic 5%%-density "
+                       "piano-roll bars [B,1,96,60] + phrases [B,1,384,60], reference-init weights" % args.batch,
+           "bars_per_gpu": args.batch, "global_batch": args.batch * world, "parallelism": "dp%d" % world,
+           "l2": "per-step working set (~25 MB/bar of saved activations) is >> 126 MB L2; no flush needed"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 5))
+        warm = max(1, min(args.warmup, 1))
+        bars_s, dt, cores, threads = cpu_reference_arm(args.cpu_batch, steps, warm)
+        line = {"impl": "reference", "metric": "train_bars_per_sec", "value": bars_s, "unit": "bars/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": dict(cfg, cpu_sample="%d bars/step" % args.cpu_batch),
+                "cpu_baseline": {"value": bars_s, "unit": "bars/s", "cores": threads, "kind": "port",
+                                 "sample": "%d steps of %d bars (fwd+bwd+Adam), oracle port of the reference modules; "
+                                           "/root/reference is not present on the GPU box" % (steps, args.cpu_batch)},
+                "e2e": {"value": bars_s, "unit": "bars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module(PKG)
+    par = importlib.import_module(PKG + ".parallel")
+    Model = importlib.import_module(PKG + ".graph.model").Model
+    Trainer = importlib.import_module(PKG + ".trainer").GeneratorTrainer
+    eng = pkg.engine
+    rank, world, local = par.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = args.batch
+
+    torch.manual_seed(0)
+    model = Model().to(dev).train()          # reference initialisation (graph/weights_initializer.py semantics)
+    flat = model.flatten_parameters()
+    reducer = None
+    if world > 1:
+        reducer = par.GradReducer.for_model(model, flat)
+        reducer.broadcast_parameters(0)
+    trainer = Trainer(model, lr=0.002, reducer=reducer)
+
+    dbatch = synthetic_batch(B, 1234 + rank, dev)
+    hbatch = synthetic_batch(B, 4321 + rank, None, pin=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def step_resident():
+        trainer.step(*dbatch)
+
+    def step_e2e():
+        b = tuple(t.to(dev, non_blocking=True) for t in hbatch)
+        loss = trainer.step(*b)
+        return loss.item()               # D2H read of the step's result, as agent/barGen.py:335 does
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pkg.reset_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = pkg.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms * 1e-3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e = B * world * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in hbatch)
+
+    # live roofline of the contraction kernels: CUDA events around every bvae_conv_gemm / bvae_wgrad_gemm launch
+    roofline = None
+    extra = {}
+    if not args.no_profile:
+        prof_steps = 2
+        eng.profile_begin()
+        for _ in range(prof_steps):
+            step_resident()
+        torch.cuda.synchronize()
+        prof = eng.profile_end()
+        tf_peak, hbm_peak, how = measured_peaks()
+        gemm_ms = (prof.get("conv_gemm", 0.0) + prof.get("wgrad_gemm", 0.0)) / prof_steps
+        nb_ms = (prof.get("nb_forward", 0.0) + prof.get("nb_backward", 0.0)) / prof_steps
+        flops = GFLOP_PER_BAR_TRAIN * 1e9 * B
+        ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                    "traffic": None, "peak_source": how + " (sustained cuBLAS bf16)",
+                    "kernel": "conv_tc_kernel + wgrad_tc_kernel (all contraction launches of one step)",
+                    "kernel_ms_per_step": gemm_ms, "launches_per_step": prof.get("n_gemm", 0) / prof_steps}
+        extra = {"normblock_ms_per_step": nb_ms, "step_ms_under_event_profiling": prof.get("total_ms", 0.0) / prof_steps,
+                 "adam_gbs": None}
+        # fused Adam alone: 28 B/param
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(5):
+            eng.adam_step(flat, 0.0, 100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        extra["adam_gbs"] = flat.numel * 28 / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e9
+        extra["adam_frac_of_hbm_peak"] = extra["adam_gbs"] / hbm_peak
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        bars_s, dt, cores, threads = cpu_reference_arm(args.cpu_batch, 3, 1)
+        cpu = {"value": bars_s, "unit": "bars/s", "cores": threads, "kind": "port",
+               "sample": "3 steps of %d bars (fwd+bwd+Adam) of the oracle port, %.1f s/step" % (args.cpu_batch, dt)}
+    line = {"metric": "train_bars_per_sec", "value": value, "unit": "bars/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e, "unit": "bars/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "extra": extra}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

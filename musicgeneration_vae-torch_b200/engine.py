@@ -46,6 +46,41 @@ def bump_param_epoch():
     _PARAM_EPOCH[0] += 1
 
 
+# ---- live per-kernel-class timing with CUDA events (bench.py's roofline block) -----------------------------
+_PROF = [None]
+
+
+def profile_begin():
+    _PROF[0] = {"_start": torch.cuda.Event(enable_timing=True)}
+    _PROF[0]["_start"].record()
+
+
+def _timed(tag, fn, *args):
+    """run one library call; when profiling, bracket it with CUDA events on the launching stream"""
+    prof = _PROF[0]
+    if prof is None:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    prof.setdefault(tag, []).append((e0, e1))
+    return rc
+
+
+def profile_end() -> dict:
+    prof, _PROF[0] = _PROF[0], None
+    end = torch.cuda.Event(enable_timing=True)
+    end.record()
+    torch.cuda.synchronize()
+    out = {"total_ms": prof.pop("_start").elapsed_time(end)}
+    for tag, evs in prof.items():
+        out[tag] = sum(a.elapsed_time(b) for a, b in evs)
+        out["n_" + tag] = len(evs)
+    out["n_gemm"] = out.get("n_conv_gemm", 0) + out.get("n_wgrad_gemm", 0)
+    return out
+
+
 class Act:
     """NHWC activation view: element (n,h,w,c) lives at t.data_ptr() + (((n*H+h)*W+w)*pitch + off + c)*esize."""
     __slots__ = ("t", "N", "H", "W", "C", "pitch", "off")
@@ -244,7 +279,7 @@ class GemmLayer:
         mp = mask.ptr if mask is not None else None
         for d, woff in descs:
             d.x, d.w, d.y, d.bias, d.addend, d.mask = xp, wp + woff, yp, bp, ap, mp
-            _lib.check(lib.bvae_conv_gemm(C.byref(d), _IMPL[0], st), "conv_gemm[%s]" % tag)
+            _lib.check(_timed("conv_gemm", lib.bvae_conv_gemm, C.byref(d), _IMPL[0], st), "conv_gemm[%s]" % tag)
 
     def forward(self, x: Act, y: Act, act: bool = False, slope: float = 0.0, use_bias: bool = True):
         """y = epi(conv(x)); y geometry must be out_hw(x) with C == Cout."""
@@ -284,7 +319,7 @@ class GemmLayer:
                     d.dy[t], d.dx[t], d.tap_idx[t] = t // self.kw - self.py, t % self.kw - self.px, t
                 self._cache[key] = d
             d.a, d.s, d.dw = a.ptr, s.ptr, grad_ptr(self.weight)
-            _lib.check(lib.bvae_wgrad_gemm(C.byref(d), _IMPL[0], st), "wgrad_gemm")
+            _lib.check(_timed("wgrad_gemm", lib.bvae_wgrad_gemm, C.byref(d), _IMPL[0], st), "wgrad_gemm")
 
     def bias_grad(self, dy: Act):
         if self.bias is not None and self.bias.requires_grad:
@@ -337,7 +372,7 @@ class NormBlock:
         if self.res_mode == 2:
             assert res is not None
             d.res, d.res_pitch = res.ptr, res.pitch
-        _lib.check(_lib.lib().bvae_nb_forward(C.byref(d), _lib.stream_ptr()), "nb_forward")
+        _lib.check(_timed("nb_forward", _lib.lib().bvae_nb_forward, C.byref(d), _lib.stream_ptr()), "nb_forward")
         return ctx
 
     def backward(self, ctx: dict, dout: Act, dy: Act, dres: Optional[Act] = None):
@@ -357,7 +392,7 @@ class NormBlock:
             d.dw1, d.dw2, d.dwsp = (grad_ptr(p) for p in self.cbam)
         if self.res_mode == 2 and dres is not None:
             d.dres, d.dres_pitch = dres.ptr, dres.pitch
-        _lib.check(_lib.lib().bvae_nb_backward(C.byref(d), _lib.stream_ptr()), "nb_backward")
+        _lib.check(_timed("nb_backward", _lib.lib().bvae_nb_backward, C.byref(d), _lib.stream_ptr()), "nb_backward")
 
 
 # ---------------------------------------------------------------------------------------------------------

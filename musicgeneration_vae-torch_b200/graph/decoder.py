@@ -277,4 +277,7 @@ class Decoder(nn.Module):
         if emb_w.requires_grad:
             grad_ptr(emb_w)
             emb_w.grad.index_add_(0, position, dpc_f[:, 1152:])
+        cb = getattr(self, "_bvae_on_bwd_done", None)      # parallel.GradReducer: decoder gradients are complete
+        if cb is not None:
+            cb()
         return dbc_f[:, :1152].contiguous(), dbc_f[:, 1152:].contiguous(), dpc_f[:, :1152].contiguous()

@@ -80,6 +80,9 @@ class _EncoderTrunk(nn.Module):
             d = layer.bwd(c, d)
         self.time_pitch.bwd(c_tp, d.slice(32, 32))
         self.pitch_time.bwd(c_pt, d.slice(0, 32))
+        cb = getattr(self, "_bvae_on_bwd_done", None)      # parallel.GradReducer: this segment's gradients are complete
+        if cb is not None:
+            cb()
 
 
 class Encoder(_EncoderTrunk):

@@ -108,7 +108,10 @@ def _run_gemm_layer(spec, impl, B):
         dx.t.fill_(float("nan"))
         g.dgrad(dya, dx)
         e_d = rel_fro(nchw(dx.t), ref_dx)
+        if impl == "tc" and (cin % 64 or cout % 64):
+            eng.set_impl(lib.IMPL_AUTO)      # 32-channel weight gradients (encoder stems) stay on the SIMT kernel
         g.wgrad(xa, dya)
+        eng.set_impl(lib.IMPL_SIMT if impl == "simt" else lib.IMPL_TC)
         g.bias_grad(dya)
         e_w = rel_fro(m.weight.grad, ref_dw)
         e_b = rel_fro(m.bias.grad, ref_db)
