@@ -241,6 +241,10 @@ def main():
             step_resident()
         torch.cuda.synchronize()
         prof = eng.profile_end()
+        detail = prof.pop("detail", {})
+        if os.environ.get("BVAE_PROFILE_DETAIL") and rank == 0:
+            for k, (t, n) in sorted(detail.items(), key=lambda kv: -kv[1][0]):
+                print("%9.3f ms %4d  %s" % (t / prof_steps, n // prof_steps, k), file=sys.stderr)
         tf_peak, hbm_peak, how = measured_peaks()
         gemm_ms = (prof.get("conv_gemm", 0.0) + prof.get("wgrad_gemm", 0.0)) / prof_steps
         nb_ms = (prof.get("nb_forward", 0.0) + prof.get("nb_backward", 0.0)) / prof_steps

@@ -299,14 +299,20 @@ struct alignas(64) WgradTcParams {
   float* dw;
 };
 
-// NS = shifted-channel tile (multiple of 64, <= 256); KP = 64 pixel rows per stage
-template <int NS, int STAGES>
+// CB = channels per swizzle atom (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NS = shifted-channel tile (multiple of
+// CB, <= 256); KP = 64 pixel rows per stage
+template <int CB, int NS, int STAGES>
 __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
   constexpr int KP = 64;
-  constexpr int ATOM_BYTES = KP * 128;                 // [64 pixel rows][64 channels] bf16, 128B-swizzled
-  constexpr int S_ATOMS = NS / 64;
-  constexpr int MAX_TPC = 512 / NS;
-  constexpr int STAGE_BYTES = (2 + MAX_TPC * S_ATOMS) * ATOM_BYTES;
+  constexpr int ROW_BYTES = CB * 2;
+  constexpr int ATOM_BYTES = KP * ROW_BYTES;           // [64 pixel rows][CB channels] bf16, swizzled
+  constexpr int A_ATOMS = 128 / CB;                    // the MMA always spans M = 128 anchor channels
+  constexpr int S_ATOMS = NS / CB;
+  constexpr int MAX_TPC = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
+  constexpr int STAGE_BYTES = (A_ATOMS + MAX_TPC * S_ATOMS) * ATOM_BYTES;
+  constexpr uint32_t LAYOUT = CB == 64 ? 2u : 4u;
+  constexpr uint32_t SBO = 8 * ROW_BYTES;              // 8 pixel rows
+  constexpr uint32_t KSTEP = (16 * ROW_BYTES) >> 4;    // 16 pixel rows per MMA, in encoded (>>4) address units
   constexpr uint32_t IDESC = make_idesc(128, NS, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    const uint32_t tx = (uint32_t)(rows_box * 128 * (p.a_atoms + ntap * S_ATOMS));
+    const uint32_t tx = (uint32_t)(rows_box * ROW_BYTES * (p.a_atoms + ntap * S_ATOMS));
     int it = 0;
     for (int ck = ck0; ck < ck1; ++ck, ++it) {
       int q = ck;
@@ -357,12 +363,12 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       mbar_expect_tx(full_bar + s, tx);
       uint8_t* st = smem + s * STAGE_BYTES;
       for (int a = 0; a < p.a_atoms; ++a)
-        tma_load_4d(st + a * ATOM_BYTES, &p.amap, full_bar + s, (ra_tile * 2 + a) * 64, cw, ch, cn);
+        tma_load_4d(st + a * ATOM_BYTES, &p.amap, full_bar + s, (ra_tile * A_ATOMS + a) * CB, cw, ch, cn);
       for (int t = 0; t < ntap; ++t) {
         const int tap = tap0 + t;
         const CUtensorMap* sm = &p.smap[p.tap_view[tap]];
         for (int a = 0; a < S_ATOMS; ++a)
-          tma_load_4d(st + (2 + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * 64,
+          tma_load_4d(st + (A_ATOMS + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * CB,
                       cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn);
       }
     }
@@ -375,12 +381,12 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
       const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-      // MN-major, 128B swizzle: LBO = distance between 64-channel atoms, SBO = 8 pixel rows (1024 B)
-      const uint64_t adesc = make_sdesc(st, ATOM_BYTES, 1024, 2);
+      // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
+      const uint64_t adesc = make_sdesc(st, ATOM_BYTES, SBO, LAYOUT);
       for (int t = 0; t < ntap; ++t) {
-        const uint64_t bdesc = make_sdesc(st + (2 + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, 1024, 2);
-        for (int j = 0; j < ksteps; ++j)     // 16 pixel rows = 2048 B per K step
-          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + 128 * j, bdesc + 128 * j, IDESC, (it | j) ? 1u : 0u);
+        const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, SBO, LAYOUT);
+        for (int j = 0; j < ksteps; ++j)
+          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, IDESC, (it | j) ? 1u : 0u);
       }
       umma_commit(empty_bar + s);
     }
@@ -392,7 +398,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
 
   // epilogue: lane = anchor channel, columns = shifted channels; scatter-add into the parameter layout
   const int ra = ra_tile * 128 + threadIdx.x;
-  const bool valid = threadIdx.x < p.a_atoms * 64 && ra < p.Ca;
+  const bool valid = threadIdx.x < p.a_atoms * CB && ra < p.Ca;
   for (int t = 0; t < ntap; ++t) {
     const int tix = p.tap_idx[tap0 + t];
 #pragma unroll 1
@@ -591,22 +597,24 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
 }
 
 int wgrad_tc_eligible(const bvae_wgrad_desc* d) {
-  if (d->Ca % 64 || d->Cs % 64 || d->a_pitch % 8 || d->s_pitch % 8) return 0;
+  if (d->Ca % 32 || d->Cs % 32 || d->a_pitch % 8 || d->s_pitch % 8) return 0;
+  if (d->Ca > 128 && d->Ca % 128) return 0;
   if (((uintptr_t)d->a | (uintptr_t)d->s) & 15) return 0;
   ViewPlan vp;
   return plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp) ? 1 : 0;
 }
 
-template <int NS, int STAGES>
+template <int CB, int NS, int STAGES>
 static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
-  constexpr int smem = 1024 + STAGES * (2 + (512 / NS) * (NS / 64)) * 8192 + (2 * STAGES + 1) * 8 + 16;
+  constexpr int max_tpc = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
+  constexpr int smem = 1024 + STAGES * (128 / CB + max_tpc * (NS / CB)) * (64 * CB * 2) + (2 * STAGES + 1) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<NS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<CB, NS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_tc_kernel<NS, STAGES><<<grid, 128, smem, stream>>>(P);
+  wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
   return check_launch("wgrad_tc");
 }
 
@@ -615,30 +623,32 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   memset(&P, 0, sizeof(P));
   ViewPlan vp;
   BVAE_REQUIRE(plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp), BVAE_ERR_UNSUPPORTED, "wgrad_tc: too many views");
-  const int NS = d->Cs % 256 == 0 ? 256 : (d->Cs % 128 == 0 ? 128 : 64);
+  const bool sw128 = (d->Ca % 64 == 0) && (d->Cs % 64 == 0);
+  const int CB = sw128 ? 64 : 32;
+  const int NS = sw128 ? (d->Cs % 256 == 0 ? 256 : (d->Cs % 128 == 0 ? 128 : 64)) : (d->Cs % 64 == 0 ? 64 : 32);
   pick_box(d->N, d->AH, d->AW, 64, &P.bw, &P.bh, &P.bn);
   int rc = make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
-                         (int64_t)d->AH * d->AW * d->a_pitch, 64, P.bw, P.bh, P.bn, true);
+                         (int64_t)d->AH * d->AW * d->a_pitch, CB, P.bw, P.bh, P.bn, sw128);
   if (rc) return rc;
   for (int v = 0; v < vp.nviews; ++v) {
     const int Hv = ceil_div(d->SH - vp.fy[v], d->sy), Wv = ceil_div(d->SW - vp.fx[v], d->sx);
     BVAE_REQUIRE(Hv > 0 && Wv > 0, BVAE_ERR_SHAPE, "wgrad_tc: empty view");
     const bf16* base = (const bf16*)d->s + ((int64_t)vp.fy[v] * d->SW + vp.fx[v]) * d->s_pitch;
     rc = make_view_map(&P.smap[v], base, d->Cs, Wv, Hv, d->N, (int64_t)d->sx * d->s_pitch,
-                       (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, 64, P.bw, P.bh, P.bn, true);
+                       (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, CB, P.bw, P.bh, P.bn, sw128);
     if (rc) return rc;
   }
   for (int t = 0; t < d->ntaps; ++t) {
     P.tap_view[t] = vp.tap_view[t]; P.tap_ex[t] = vp.tap_ex[t]; P.tap_ey[t] = vp.tap_ey[t]; P.tap_idx[t] = d->tap_idx[t];
   }
   P.ntaps = d->ntaps; P.T = d->T;
-  const int max_tpc = 512 / NS;
+  const int max_tpc = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
   P.tap_groups = ceil_div(d->ntaps, max_tpc);
   P.tpc = ceil_div(d->ntaps, P.tap_groups);
   P.chunks_w = ceil_div(d->AW, P.bw); P.chunks_h = ceil_div(d->AH, P.bh); P.chunks_n = ceil_div(d->N, P.bn);
   P.nchunks = P.chunks_w * P.chunks_h * P.chunks_n;
   P.ra_tiles = ceil_div(d->Ca, 128); P.rs_tiles = d->Cs / NS;
-  P.a_atoms = d->Ca >= 128 ? 2 : 1;
+  P.a_atoms = d->Ca >= 128 ? 128 / CB : d->Ca / CB;
   P.Ca = d->Ca; P.Cs = d->Cs; P.dw = d->dw;
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
   int splits = ceil_div(148 * 2, out_tiles);
@@ -649,9 +659,10 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.splits = ceil_div(P.nchunks, P.chunks_per_split);
   const long grid = (long)out_tiles * P.splits;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "wgrad_tc: grid too large");
-  if (NS == 256) return launch_wgrad<256, 2>(P, (int)grid, stream);
-  if (NS == 128) return launch_wgrad<128, 2>(P, (int)grid, stream);
-  return launch_wgrad<64, 2>(P, (int)grid, stream);
+  if (CB == 32) return NS == 64 ? launch_wgrad<32, 64, 2>(P, (int)grid, stream) : launch_wgrad<32, 32, 2>(P, (int)grid, stream);
+  if (NS == 256) return launch_wgrad<64, 256, 2>(P, (int)grid, stream);
+  if (NS == 128) return launch_wgrad<64, 128, 2>(P, (int)grid, stream);
+  return launch_wgrad<64, 64, 2>(P, (int)grid, stream);
 }
 
 }  // namespace bvae

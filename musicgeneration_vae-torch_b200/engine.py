@@ -55,7 +55,7 @@ def profile_begin():
     _PROF[0]["_start"].record()
 
 
-def _timed(tag, fn, *args):
+def _timed(tag, fn, *args, detail=None):
     """run one library call; when profiling, bracket it with CUDA events on the launching stream"""
     prof = _PROF[0]
     if prof is None:
@@ -64,7 +64,7 @@ def _timed(tag, fn, *args):
     e0.record()
     rc = fn(*args)
     e1.record()
-    prof.setdefault(tag, []).append((e0, e1))
+    prof.setdefault(tag, []).append((e0, e1, detail))
     return rc
 
 
@@ -74,9 +74,16 @@ def profile_end() -> dict:
     end.record()
     torch.cuda.synchronize()
     out = {"total_ms": prof.pop("_start").elapsed_time(end)}
+    detail = {}
     for tag, evs in prof.items():
-        out[tag] = sum(a.elapsed_time(b) for a, b in evs)
+        out[tag] = sum(a.elapsed_time(b) for a, b, _ in evs)
         out["n_" + tag] = len(evs)
+        for a, b, d in evs:
+            if d is not None:
+                k = tag + ":" + d
+                t, n = detail.get(k, (0.0, 0))
+                detail[k] = (t + a.elapsed_time(b), n + 1)
+    out["detail"] = detail
     out["n_gemm"] = out.get("n_conv_gemm", 0) + out.get("n_wgrad_gemm", 0)
     return out
 
@@ -279,7 +286,10 @@ class GemmLayer:
         mp = mask.ptr if mask is not None else None
         for d, woff in descs:
             d.x, d.w, d.y, d.bias, d.addend, d.mask = xp, wp + woff, yp, bp, ap, mp
-            _lib.check(_timed("conv_gemm", lib.bvae_conv_gemm, C.byref(d), _IMPL[0], st), "conv_gemm[%s]" % tag)
+            _lib.check(_timed("conv_gemm", lib.bvae_conv_gemm, C.byref(d), _IMPL[0], st,
+                              detail="%s %s %d->%d k%dx%d s%dx%d in%dx%d" % (tag, self.kind, self.Cin, self.Cout, self.kh,
+                                                                             self.kw, self.sy, self.sx, x.H, x.W)),
+                       "conv_gemm[%s]" % tag)
 
     def forward(self, x: Act, y: Act, act: bool = False, slope: float = 0.0, use_bias: bool = True):
         """y = epi(conv(x)); y geometry must be out_hw(x) with C == Cout."""
@@ -319,7 +329,9 @@ class GemmLayer:
                     d.dy[t], d.dx[t], d.tap_idx[t] = t // self.kw - self.py, t % self.kw - self.px, t
                 self._cache[key] = d
             d.a, d.s, d.dw = a.ptr, s.ptr, grad_ptr(self.weight)
-            _lib.check(_timed("wgrad_gemm", lib.bvae_wgrad_gemm, C.byref(d), _IMPL[0], st), "wgrad_gemm")
+            _lib.check(_timed("wgrad_gemm", lib.bvae_wgrad_gemm, C.byref(d), _IMPL[0], st,
+                              detail="w %s %d->%d k%dx%d s%dx%d in%dx%d" % (self.kind, self.Cin, self.Cout, self.kh, self.kw,
+                                                                            self.sy, self.sx, x.H, x.W)), "wgrad_gemm")
 
     def bias_grad(self, dy: Act):
         if self.bias is not None and self.bias.requires_grad:
@@ -372,7 +384,8 @@ class NormBlock:
         if self.res_mode == 2:
             assert res is not None
             d.res, d.res_pitch = res.ptr, res.pitch
-        _lib.check(_timed("nb_forward", _lib.lib().bvae_nb_forward, C.byref(d), _lib.stream_ptr()), "nb_forward")
+        _lib.check(_timed("nb_forward", _lib.lib().bvae_nb_forward, C.byref(d), _lib.stream_ptr(),
+                          detail="C%d %dx%d cbam%d" % (Cc, H, W, int(self.cbam is not None))), "nb_forward")
         return ctx
 
     def backward(self, ctx: dict, dout: Act, dy: Act, dres: Optional[Act] = None):
@@ -392,7 +405,8 @@ class NormBlock:
             d.dw1, d.dw2, d.dwsp = (grad_ptr(p) for p in self.cbam)
         if self.res_mode == 2 and dres is not None:
             d.dres, d.dres_pitch = dres.ptr, dres.pitch
-        _lib.check(_timed("nb_backward", _lib.lib().bvae_nb_backward, C.byref(d), _lib.stream_ptr()), "nb_backward")
+        _lib.check(_timed("nb_backward", _lib.lib().bvae_nb_backward, C.byref(d), _lib.stream_ptr(),
+                          detail="C%d %dx%d cbam%d" % (Cc, H, W, int(self.cbam is not None))), "nb_backward")
 
 
 # ---------------------------------------------------------------------------------------------------------
