@@ -1,0 +1,185 @@
+"""Training / sampling entry point with the surface of the reference's agent/barGen.py: ``BarGen(config)`` with
+``run() / train() / train_epoch() / make_batch() / save_checkpoint() / load_checkpoint()``.
+
+What is kept: the pre-training generator step (agent/barGen.py:249-252,302-335: zero_grad, generator forward, Loss,
+backward, Adam lr 2e-3), the per-epoch ReduceLROnPlateau(mode='min', factor=0.8, cooldown=6) on the mean loss
+(:70-81,361-367), the checkpoint dictionary keys (:174-197, including the ``module.`` prefix nn.DataParallel adds),
+the data layout (.npz items concatenated by make_batch, :134-141) and the sampling loop used for the per-epoch
+samples (agent/barGen2.py:316-336 == maker_bar.py:32-44).
+What is different on purpose: one process per GPU with NCCL gradient all-reduce instead of nn.DataParallel
+(agent/barGen.py:96-105) -- launch with torchrun; no per-step ``.item()`` (the running loss stays on the device and
+is read once per logging interval); scalars go to a JSONL file when tensorboardX is absent.
+Out of scope: the GAN phase's discriminators; after ``pretraining_step_size``
+epochs the generator keeps training on the label-smoothed BCE (``Loss(..., is_pretraining=False)``)."""
+import json
+import logging
+import os
+import random
+import shutil
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader
+
+from .. import parallel
+from ..data.bar_dataset import NoteDataset, SyntheticBars
+from ..graph.model import Model
+from ..maker_bar import sample_songs
+from ..metrics import AverageMeter
+from ..trainer import GeneratorTrainer
+
+
+class _Plateau:
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(mode='min', factor, patience=10, cooldown, threshold=1e-4 rel)."""
+
+    def __init__(self, factor=0.8, patience=10, cooldown=6, threshold=1e-4):
+        self.factor, self.patience, self.cooldown, self.threshold = factor, patience, cooldown, threshold
+        self.best, self.bad, self.cool = float("inf"), 0, 0
+
+    def step(self, metric, lr):
+        if metric < self.best * (1 - self.threshold):
+            self.best, self.bad = metric, 0
+        else:
+            self.bad += 1
+        if self.cool > 0:
+            self.cool -= 1
+            self.bad = 0
+        if self.bad > self.patience:
+            self.cool, self.bad = self.cooldown, 0
+            return lr * self.factor
+        return lr
+
+
+class BarGen(object):
+    def __init__(self, config, dataset=None):
+        self.config = config
+        self.pretraining_step_size = config.pretraining_step_size
+        self.batch_size = config.batch_size
+        self.rank, self.world, self.local_rank = parallel.init_from_env()
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.logger = self.set_logger()
+
+        data_dir = os.path.join(config.root_path, config.data_path)
+        if dataset is not None:
+            self.dataset = dataset
+        elif os.path.isdir(data_dir):
+            self.dataset = NoteDataset(config.root_path, config)
+        else:
+            self.dataset = SyntheticBars(64, 4, self.batch_size)
+        # DistributedSampler semantics of agent/barGen_horovod.py:49-50: each rank takes a disjoint shard
+        b, e = parallel.shard_range(len(self.dataset), self.rank, self.world)
+        self.indices = list(range(b, e))
+        self.dataloader = DataLoader(torch.utils.data.Subset(self.dataset, self.indices), batch_size=self.batch_size,
+                                     shuffle=False, num_workers=1, pin_memory=config.pin_memory,
+                                     collate_fn=self.make_batch)
+
+        self.manual_seed = random.randint(1, 10000)
+        torch.manual_seed(self.manual_seed)
+        torch.cuda.manual_seed_all(self.manual_seed)
+        random.seed(self.manual_seed)
+
+        self.generator = Model(vae_head=getattr(config, "vae_head", False)).to(self.device)
+        flat = self.generator.flatten_parameters()
+        self.reducer = None
+        if self.world > 1:
+            self.reducer = parallel.GradReducer.for_model(self.generator, flat, getattr(config, "bucket_mb", 64))
+        self.lr_gen1 = config.learning_rate
+        self.opt_gen1 = GeneratorTrainer(self.generator, lr=self.lr_gen1, reducer=self.reducer)
+        self.scheduler_gen1 = _Plateau(factor=0.8, cooldown=6)
+        self.iteration = 0
+        self.epoch = 0
+        self.load_checkpoint(config.checkpoint_file)
+        if self.reducer is not None:                      # rank 0's weights / optimiser state win (horovod :130-134)
+            self.reducer.broadcast_parameters(0)
+        self.summary = None
+        if self.rank == 0:
+            os.makedirs(os.path.join(config.root_path, config.summary_dir), exist_ok=True)
+            self.summary = open(os.path.join(config.root_path, config.summary_dir, "scalars.jsonl"), "a")
+            print("Number of generator parameters: {}".format(sum(p.numel() for p in self.generator.parameters())))
+
+    def set_logger(self):
+        logger = logging.getLogger("barGen")
+        logger.setLevel(logging.DEBUG)
+        if self.rank == 0 and not logger.handlers:
+            h = logging.FileHandler(filename="train_epoch.log")
+            h.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(levelname)s - %(message)s"))
+            logger.addHandler(h)
+        return logger
+
+    def make_batch(self, samples):
+        cat = lambda k: np.concatenate([s[k] for s in samples], axis=0)
+        return (torch.tensor(cat("note"), dtype=torch.float), torch.tensor(cat("pre_note"), dtype=torch.float),
+                torch.tensor(cat("pre_phrase"), dtype=torch.float), torch.tensor(cat("position"), dtype=torch.long))
+
+    # ---- checkpoints (agent/barGen.py:151-197) -----------------------------------------------------------
+    def _ckpt_dir(self):
+        return os.path.join(self.config.root_path, self.config.checkpoint_dir)
+
+    def load_checkpoint(self, file_name):
+        filename = os.path.join(self._ckpt_dir(), file_name)
+        try:
+            ck = torch.load(filename, map_location=self.device, weights_only=False)
+        except OSError:
+            if self.rank == 0:
+                print("No checkpoint exists from '{}'. Skipping...".format(self._ckpt_dir()))
+            return
+        sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["generator_state_dict"].items()}
+        sd = {k: v for k, v in sd.items() if not k.startswith("refiner.")}       # the reference's Refiner is not built
+        self.generator.load_state_dict(sd, strict=False)
+        if isinstance(ck.get("gen_optimizer1"), dict) and "exp_avg" in ck["gen_optimizer1"]:
+            self.opt_gen1.load_state_dict(ck["gen_optimizer1"])
+        self.epoch = ck.get("epoch", 0)
+
+    def save_checkpoint(self, file_name, epoch):
+        if self.rank != 0:
+            return
+        os.makedirs(self._ckpt_dir(), exist_ok=True)
+        tmp_name = os.path.join(self._ckpt_dir(), "checkpoint_{}.pth.tar".format(epoch))
+        gen_sd = {"module." + k: v.detach().clone() for k, v in self.generator.state_dict().items()}
+        state = {"epoch": self.epoch, "generator_state_dict": gen_sd, "gen_optimizer1": self.opt_gen1.state_dict(),
+                 "gen_optimizer2": self.opt_gen1.state_dict(), "lr_gen": self.lr_gen1}
+        torch.save(state, tmp_name)
+        shutil.copyfile(tmp_name, os.path.join(self._ckpt_dir(), file_name))
+
+    # ---- training ---------------------------------------------------------------------------------------
+    def run(self):
+        try:
+            self.train()
+        except KeyboardInterrupt:
+            print("You have entered CTRL+C.. Wait to finalize")
+
+    def train(self):
+        for _ in range(self.config.epoch):
+            self.epoch += 1
+            self.train_epoch()
+            if self.epoch > self.pretraining_step_size + 50:
+                self.save_checkpoint(self.config.checkpoint_file, self.epoch)
+
+    def train_epoch(self):
+        self.generator.train()
+        self.opt_gen1.is_pretraining = self.epoch <= self.pretraining_step_size
+        avg_gen_loss = AverageMeter()
+        dev_sum, n = torch.zeros((), device=self.device), 0
+        for note, pre_note, pre_phrase, position in self.dataloader:
+            note, pre_note, pre_phrase, position = (t.to(self.device, non_blocking=self.config.async_loading)
+                                                    for t in (note, pre_note, pre_phrase, position))
+            self.iteration += 1
+            dev_sum += self.opt_gen1.step(note, pre_note, pre_phrase, position)     # stays on the device
+            n += 1
+        if n:
+            avg_gen_loss.update(float(dev_sum) / n, n)                                  # one D2H read per epoch
+        self.lr_gen1 = self.opt_gen1.lr = self.scheduler_gen1.step(avg_gen_loss.val, self.opt_gen1.lr)
+        if self.summary is not None:
+            tag = "pre_train/Generator_loss" if self.opt_gen1.is_pretraining else "train/Generator_loss"
+            self.summary.write(json.dumps({"tag": tag, "value": avg_gen_loss.val, "iteration": self.iteration,
+                                           "epoch": self.epoch, "lr": self.lr_gen1}) + "\n")
+            self.summary.flush()
+            self.logger.debug("pre_train lr: {}".format(self.lr_gen1))
+        return avg_gen_loss.val
+
+    def generate(self, music_length=2, songs=1, seed=0):
+        """per-epoch sample generation of agent/barGen2.py:316-336 (same loop as maker_bar.py)"""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        lat = torch.randn(music_length * 4, songs, 1152, device=self.device, generator=g)
+        return sample_songs(self.generator, lat, music_length)
