@@ -157,6 +157,7 @@ typedef struct bvae_nb_desc {
   float* dwsp;          /* accumulated */
   float* bwd_nc;        /* scratch [N][C][4]: dgc, S1, S2, dmx  (zeroed by the call) */
   float* bwd_px;        /* scratch [N][H*W][4]: dq, dsa_mean, dsa_max, spare */
+  float* bwd_h;         /* scratch [N][192]: per-sample channel-MLP factors (CBAM only) */
 } bvae_nb_desc;
 
 int bvae_nb_forward(const bvae_nb_desc* d, void* stream);

@@ -52,7 +52,7 @@ class NbDesc(C.Structure):
                 ("nc", c_vp), ("nc_idx", c_vp), ("sa", c_vp), ("cidx", c_vp), ("gs", c_vp),
                 ("dout", c_vp), ("dy", c_vp), ("dres", c_vp),
                 ("dgamma", c_vp), ("dbeta", c_vp), ("dw1", c_vp), ("dw2", c_vp), ("dwsp", c_vp),
-                ("bwd_nc", c_vp), ("bwd_px", c_vp)]
+                ("bwd_nc", c_vp), ("bwd_px", c_vp), ("bwd_h", c_vp)]
 
 
 _lib = None

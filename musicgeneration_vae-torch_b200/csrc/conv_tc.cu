@@ -17,6 +17,7 @@
 //   pixel-box TMA loads feed it.  Split over pixel ranges across CTAs, reduced with fp32 red.global.add into the
 //   parameter-layout gradient.
 #include <cuda.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include "common.cuh"
@@ -274,6 +275,186 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ Co
       bf16* yp = (bf16*)p.y + opix * p.y_pitch + col0 + c0;
 #pragma unroll
       for (int i = 0; i < 32; i += 8) stg8(yp + i, pack8(f + i));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent variant: one CTA per SM loops over output tiles.  256 threads: warp 0 = TMA producer, warp 1 = MMA
+// issuer, warp 2 = TMEM allocator, warps 4..7 = epilogue.  Two TMEM accumulator buffers (2 x BN columns) let the
+// epilogue of tile i overlap the main loop of tile i+1; barrier init / TMEM allocation are paid once per CTA.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KB, int BN, int STAGES>
+__global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int A_BYTES = 128 * KB * 2;
+  constexpr int B_BYTES = BN * KB * 2;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+  constexpr int TMEM_COLS = 2 * ACC_COLS;
+  constexpr uint32_t LAYOUT = KB == 64 ? 2u : 4u;
+  constexpr uint32_t SBO = 8 * KB * 2;
+  constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull = empty_bar + STAGES;       // [2]
+  uint64_t* tempty = tfull + 2;               // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KT = p.ntaps * p.kchunks;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total = m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.bmap);
+    tma_prefetch_desc(&p.amap[0]);
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    const uint32_t tx = (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + B_BYTES);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int tn = m_tile / p.tiles_h;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const CUtensorMap* am = &p.amap[p.tap_view[t]];
+        const int cw = tw * p.bw + p.tap_ex[t], ch = th * p.bh + p.tap_ey[t], cn = tn * p.bn;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + s, ph ^ 1u);
+          mbar_expect_tx(full_bar + s, tx);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          tma_load_4d(sa, am, full_bar + s, kc * KB, cw, ch, cn);
+          tma_load_2d(sa + A_BYTES, &p.bmap, full_bar + s, t * p.C + kc * KB, n_tile * BN);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    uint32_t it = 0, ti = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
+      const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
+      mbar_wait(tempty + ab, aph ^ 1u);            // epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ab * ACC_COLS;
+      for (int kb = 0; kb < KT; ++kb, ++it) {
+        const uint32_t s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1u;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
+        const uint64_t bdesc = make_sdesc(sa + A_BYTES, 16, SBO, LAYOUT);
+#pragma unroll
+        for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kb | j) ? 1u : 0u);
+        umma_commit(empty_bar + s);
+      }
+      umma_commit(tfull + ab);
+    }
+  } else if (warp >= 4) {
+    // ---------------- epilogue warps: TMEM -> registers -> global ----------------
+    const int wq = warp - 4;                       // TMEM lane quarter this warp may access (= warp id % 4)
+    const int r = wq * 32 + lane;
+    const int rows_box = p.bn * p.bh * p.bw;
+    const int nn = r / (p.bh * p.bw), hh = (r / p.bw) % p.bh, ww = r % p.bw;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
+      const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int tn = m_tile / p.tiles_h;
+      const int n = tn * p.bn + nn, qy = th * p.bh + hh, qx = tw * p.bw + ww;
+      const bool valid = r < rows_box && n < p.N && qy < p.QH && qx < p.QW;
+      const int64_t opix = ((int64_t)n * p.OH + (qy * p.osy + p.ooy)) * p.OW + (qx * p.osx + p.oox);
+      const int col0 = n_tile * BN;
+      mbar_wait(tfull + ab, aph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(wq * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tacc + (uint32_t)c0, v);
+        if (!valid) continue;
+        float f[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          }
+        }
+        if (p.act) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = act_fwd(f[i], p.slope);
+        }
+        if (p.addend) {
+          if (p.out_f32) {
+            const float* ap = (const float*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(ap + i);
+              f[i] += a.x; f[i + 1] += a.y; f[i + 2] += a.z; f[i + 3] += a.w;
+            }
+          } else {
+            const bf16* ap = (const bf16*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float a[8];
+              unpack8(ldg8(ap + i), a);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[i + k] += a[k];
+            }
+          }
+        }
+        if (p.mask) {
+          const bf16* mp = (const bf16*)p.mask + opix * p.mask_pitch + col0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            float a[8];
+            unpack8(ldg8(mp + i), a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[i + k] *= (a[k] > 0.f) ? 1.f : p.mask_slope;
+          }
+        }
+        if (p.out_f32) {
+          float* yp = (float*)p.y + opix * p.y_pitch + col0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+        } else {
+          bf16* yp = (bf16*)p.y + opix * p.y_pitch + col0 + c0;
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) stg8(yp + i, pack8(f + i));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty + ab);                    // 128 arrivals release the accumulator buffer
     }
   }
   tc_fence_before();
@@ -558,6 +739,33 @@ static int launch_conv(const ConvTcParams& P, int grid, cudaStream_t stream) {
   return check_launch("conv_tc");
 }
 
+template <int KB, int BN>
+static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) {
+  constexpr int STAGE = 128 * KB * 2 + BN * KB * 2;
+  constexpr int ST_RAW = (200 * 1024) / STAGE;
+  constexpr int STAGES = ST_RAW > 8 ? 8 : ST_RAW;
+  constexpr int smem = 1024 + STAGES * STAGE + (2 * STAGES + 4) * 8 + 16;
+  static bool attr_done = false;
+  static int num_sms = 148;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<KB, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "conv_tc2: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    attr_done = true;
+  }
+  const int grid = (int)(tiles < num_sms ? tiles : num_sms);
+  conv_tc2_kernel<KB, BN, STAGES><<<grid, 256, smem, stream>>>(P);
+  return check_launch("conv_tc2");
+}
+
+static bool use_conv_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   ConvTcParams P;
   memset(&P, 0, sizeof(P));
@@ -588,6 +796,12 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   P.slope = d->slope; P.mask_slope = d->mask_slope;
   const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "conv_tc: grid too large");
+  if (!use_conv_v1()) {
+#define CONV2_CASE(kb, bn) if (KB == kb && BN == bn) return launch_conv2<kb, bn>(P, grid, stream)
+    CONV2_CASE(64, 256); CONV2_CASE(64, 192); CONV2_CASE(64, 128); CONV2_CASE(64, 64); CONV2_CASE(64, 32);
+    CONV2_CASE(32, 256); CONV2_CASE(32, 192); CONV2_CASE(32, 128); CONV2_CASE(32, 64); CONV2_CASE(32, 32);
+#undef CONV2_CASE
+  }
 #define CONV_CASE(kb, bn, st) if (KB == kb && BN == bn) return launch_conv<kb, bn, st>(P, (int)grid, stream)
   CONV_CASE(64, 256, 4); CONV_CASE(64, 192, 4); CONV_CASE(64, 128, 3); CONV_CASE(64, 64, 4); CONV_CASE(64, 32, 4);
   CONV_CASE(32, 256, 4); CONV_CASE(32, 192, 4); CONV_CASE(32, 128, 4); CONV_CASE(32, 64, 4); CONV_CASE(32, 32, 4);

@@ -44,11 +44,12 @@ __global__ void __launch_bounds__(256) nb_stats_kernel(const void* __restrict__ 
   s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; s_kmax[threadIdx.x] = 0; s_kmin[threadIdx.x] = 0;
   __syncthreads();
 
-  float shift[8], sum[8], sq[8];
+  float shift[8], sum[8], sq[8], vmx[8], vmn[8];
+  int imx[8], imn[8];
   u64 kx[8], kn[8];
   load8<F32>(y, base + c0, shift);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; kx[i] = 0; kn[i] = 0; }
+  for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
   for (int p = p_begin + warp * gpw + grp; p < p_end; p += 8 * gpw) {
     float v[8];
     load8<F32>(y, base + (int64_t)p * pitch + c0, v);
@@ -57,10 +58,14 @@ __global__ void __launch_bounds__(256) nb_stats_kernel(const void* __restrict__ 
       const float dlt = v[i] - shift[i];
       sum[i] += dlt;
       sq[i] += dlt * dlt;
-      const u64 a = make_key(v[i], (uint32_t)p), b = make_key(-v[i], (uint32_t)p);
-      kx[i] = a > kx[i] ? a : kx[i];
-      kn[i] = b > kn[i] ? b : kn[i];
+      if (v[i] > vmx[i]) { vmx[i] = v[i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
+      if (v[i] < vmn[i]) { vmn[i] = v[i]; imn[i] = p; }
     }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {       // threads that saw no pixel contribute the neutral key 0
+    kx[i] = vmx[i] == -INFINITY ? 0ull : make_key(vmx[i], (uint32_t)imx[i]);
+    kn[i] = vmn[i] == INFINITY ? 0ull : make_key(-vmn[i], (uint32_t)imn[i]);
   }
   for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
@@ -181,6 +186,21 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  float h_mean[8];
+  float h_rstd[8];
+  float h_a[8];
+  float h_b[8];
+  float h_gc[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_mean[i] = s_mean[sub * 8 + i];
+      h_rstd[i] = s_rstd[sub * 8 + i];
+      h_a[i] = s_a[sub * 8 + i];
+      h_b[i] = s_b[sub * 8 + i];
+      h_gc[i] = s_gc[sub * 8 + i];
+    }
+  }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ybase = (int64_t)n * HW * y_pitch, ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch;
   for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
@@ -192,22 +212,27 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int c = (it * G + sub) * 8;
+        const float* p_mean = (ITERS == 1) ? h_mean : (s_mean + c);
+        const float* p_rstd = (ITERS == 1) ? h_rstd : (s_rstd + c);
+        const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
+        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
         float v[8], uh[8];
         load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) uh[i] = (v[i] - s_mean[c + i]) * s_rstd[c + i];
+        for (int i = 0; i < 8; ++i) uh[i] = (v[i] - p_mean[i]) * p_rstd[i];
         stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
         if (has_cbam) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float u1 = (s_a[c + i] * v[i] + s_b[c + i]) * s_gc[c + i];
+            const float u1 = (p_a[i] * v[i] + p_b[i]) * p_gc[i];
             sum += u1;
             if (u1 > mx) { mx = u1; mxc = c + i; }
           }
         } else {
           float o[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = act_fwd(s_a[c + i] * v[i] + s_b[c + i], slope);
+          for (int i = 0; i < 8; ++i) o[i] = act_fwd(p_a[i] * v[i] + p_b[i], slope);
           stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
         }
       }
@@ -274,6 +299,17 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ 
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  float h_a[8];
+  float h_b[8];
+  float h_gc[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_a[i] = s_a[sub * 8 + i];
+      h_b[i] = s_b[sub * 8 + i];
+      h_gc[i] = s_gc[sub * 8 + i];
+    }
+  }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ybase = (int64_t)n * HW * y_pitch, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
   const float* sa_n = sa + (int64_t)n * HW * 2;
@@ -290,13 +326,16 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ 
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
+        const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
+        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
       float v[8], r[8], o[8];
       load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
       if (res_mode == 2) unpack8(ldg8(res + rbase + (int64_t)p * res_pitch + c), r);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float u = s_a[c + i] * v[i] + s_b[c + i];
-        const float cb = u * s_gc[c + i] * g;
+        const float u = p_a[i] * v[i] + p_b[i];
+        const float cb = u * p_gc[i] * g;
         const float rr = res_mode == 1 ? u : (res_mode == 2 ? r[i] : 0.f);
         o[i] = act_fwd(rr + cb, slope);
       }
@@ -350,6 +389,17 @@ __global__ void __launch_bounds__(256) nb_bwd1_kernel(const bf16* __restrict__ d
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  float h_g[8];
+  float h_b[8];
+  float h_gc[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_g[i] = s_g[sub * 8 + i];
+      h_b[i] = s_b[sub * 8 + i];
+      h_gc[i] = s_gc[sub * 8 + i];
+    }
+  }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
   float acc[ITERS][8];
@@ -366,6 +416,9 @@ __global__ void __launch_bounds__(256) nb_bwd1_kernel(const bf16* __restrict__ d
 #pragma unroll
       for (int it = 0; it < ITERS; ++it) {
         const int c = (it * G + sub) * 8;
+        const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
+        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
         float uh[8], o[8], d[8];
         unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
         unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
@@ -373,8 +426,8 @@ __global__ void __launch_bounds__(256) nb_bwd1_kernel(const bf16* __restrict__ d
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
-          const float t = ds * (s_g[c + i] * uh[i] + s_b[c + i]);
-          dgs += t * s_gc[c + i];
+          const float t = ds * (p_g[i] * uh[i] + p_b[i]);
+          dgs += t * p_gc[i];
           acc[it][i] += t * g;
         }
       }
@@ -437,8 +490,8 @@ __global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const floa
 
 // gradient wrt u for 8 channels of one pixel (shared by the reduction pass and the final pass, so that du is
 // never rounded to bf16 before the InstanceNorm projection removes its common-mode part)
-__device__ __forceinline__ void nb_du8(const float* uh, const float* o, const float* d, int c, const float* s_g,
-                                       const float* s_b, const float* s_gc, int has_cbam, int res_mode, float slope,
+__device__ __forceinline__ void nb_du8(const float* uh, const float* o, const float* d, int c, const float* p_g,
+                                       const float* p_b, const float* p_gc, int has_cbam, int res_mode, float slope,
                                        float g, float dmean, float dmax, int ci, float* du, float* dsv, float* dspu) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -447,10 +500,10 @@ __device__ __forceinline__ void nb_du8(const float* uh, const float* o, const fl
     float v = (res_mode == 0 || res_mode == 1) ? ds : 0.f;
     float su = 0.f;
     if (has_cbam) {
-      const float gc = s_gc[c + i];
+      const float gc = p_gc[i];
       const float dsp = dmean + ((c + i) == ci ? dmax : 0.f);   // grad wrt u1 = u*gc from the spatial branch
       v += ds * gc * g + dsp * gc;
-      su = dsp * (s_g[c + i] * uh[i] + s_b[c + i]);
+      su = dsp * (p_g[i] * uh[i] + p_b[i]);
     }
     du[i] = v;
     dspu[i] = su;
@@ -480,6 +533,17 @@ __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ d
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  float h_g[8];
+  float h_b[8];
+  float h_gc[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_g[i] = s_g[sub * 8 + i];
+      h_b[i] = s_b[sub * 8 + i];
+      h_gc[i] = s_gc[sub * 8 + i];
+    }
+  }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
   const int64_t rbase = (int64_t)n * HW * dres_pitch;
@@ -504,11 +568,14 @@ __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ d
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
+      const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
+      const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+      const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
       float uh[8], o[8], d[8], du[8], dsv[8], dspu[8];
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
       unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
       unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8(uh, o, d, c, s_g, s_b, s_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+      nb_du8(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         a1[it][i] += du[i];
@@ -531,8 +598,7 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
                                                           const float* __restrict__ beta,
                                                           const float* __restrict__ w1, const float* __restrict__ w2,
                                                           float* __restrict__ bwd_nc, float* __restrict__ dgamma,
-                                                          float* __restrict__ dbeta, float* __restrict__ dw1,
-                                                          float* __restrict__ dw2) {
+                                                          float* __restrict__ dbeta, float* __restrict__ bwd_h) {
   extern __shared__ float sm[];
   float* s_avg = sm;            // [C]
   float* s_mx = sm + C;         // [C]
@@ -565,18 +631,16 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
       if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; s_dh[j] = dh; }
     }
     __syncthreads();
-    // dW2[c][j] += dv_c * (relu(ha_j) + relu(hm_j));  dW1[j][c] += dh_j*[ha_j>0]*avg_c + dh_j*[hm_j>0]*mx_c
-    for (int e = threadIdx.x; e < C * Cr; e += blockDim.x) {
-      const int c = e / Cr, j = e % Cr;
-      const float h = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[j], 0.f);
-      const float v = s_dv[c] * h;
-      if (v != 0.f) atomicAdd(dw2 + (int64_t)c * Cr + j, v);
+    // the weight gradients dW2[c][j] = sum_n dv[n,c] * (relu(ha)+relu(hm))[n,j] and
+    // dW1[j][c] = sum_n dh[n,j] * ([ha>0] avg_c + [hm>0] mx[n,c]) are reduced over samples by nb_bwd_w_kernel;
+    // here only the per-sample factors are written out (no per-sample atomics on the weight gradients)
+    for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+      float* hq = bwd_h + (int64_t)n * 192;
+      hq[j] = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[j], 0.f);
+      hq[64 + j] = s_ha[j] > 0.f ? s_dh[j] : 0.f;
+      hq[128 + j] = s_hm[j] > 0.f ? s_dh[j] : 0.f;
     }
-    for (int e = threadIdx.x; e < C * Cr; e += blockDim.x) {
-      const int j = e / C, c = e % C;
-      const float v = s_dh[j] * ((s_ha[j] > 0.f ? s_avg[c] : 0.f) + (s_hm[j] > 0.f ? s_mx[c] : 0.f));
-      if (v != 0.f) atomicAdd(dw1 + (int64_t)j * C + c, v);
-    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) bn[c * BN_W + BN_DGC] = s_dv[c];
   }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float d_avg = 0.f, d_mx = 0.f;
@@ -596,6 +660,30 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
     bn[c * BN_W + BN_S1] = S1 * inv;   // m1
     bn[c * BN_W + BN_S2] = S2 * inv;   // m2
   }
+}
+
+// channel-attention MLP weight gradients, reduced over the batch: one thread per weight element, samples split
+// over blockIdx.y
+__global__ void __launch_bounds__(256) nb_bwd_w_kernel(int N, int C, int Cr, const float* __restrict__ nc,
+                                                       const float* __restrict__ beta,
+                                                       const float* __restrict__ bwd_nc,
+                                                       const float* __restrict__ bwd_h, float* __restrict__ dw1,
+                                                       float* __restrict__ dw2, int n_per_block) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= C * Cr) return;
+  const int c = e % C, j = e / C;
+  const int n0 = blockIdx.y * n_per_block, n1 = min(N, n0 + n_per_block);
+  const float avg = beta[c];
+  float a1 = 0.f, a2 = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float* hq = bwd_h + (int64_t)n * 192;
+    const float dv = bwd_nc[((int64_t)n * C + c) * BN_W + BN_DGC];
+    const float mx = nc[((int64_t)n * C + c) * NC_W + NC_EXTU];
+    a2 += dv * hq[j];
+    a1 += hq[64 + j] * avg + hq[128 + j] * mx;
+  }
+  atomicAdd(dw2 + (int64_t)c * Cr + j, a2);
+  atomicAdd(dw1 + (int64_t)j * C + c, a1);
 }
 
 // backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2); du is recomputed in fp32
@@ -629,6 +717,27 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
+  float h_g[8];
+  float h_b[8];
+  float h_gc[8];
+  float h_a[8];
+  float h_m1[8];
+  float h_m2[8];
+  float h_dmx[8];
+  int h_idx[8];
+  if (ITERS == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_g[i] = s_g[sub * 8 + i];
+      h_b[i] = s_b[sub * 8 + i];
+      h_gc[i] = s_gc[sub * 8 + i];
+      h_a[i] = s_a[sub * 8 + i];
+      h_m1[i] = s_m1[sub * 8 + i];
+      h_m2[i] = s_m2[sub * 8 + i];
+      h_dmx[i] = s_dmx[sub * 8 + i];
+      h_idx[i] = s_idx[sub * 8 + i];
+    }
+  }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
   const int64_t ybase = (int64_t)n * HW * dy_pitch;
@@ -648,15 +757,23 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
+      const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
+      const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+      const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
+      const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
+      const float* p_m1 = (ITERS == 1) ? h_m1 : (s_m1 + c);
+      const float* p_m2 = (ITERS == 1) ? h_m2 : (s_m2 + c);
+      const float* p_dmx = (ITERS == 1) ? h_dmx : (s_dmx + c);
+      const int* p_idx = (ITERS == 1) ? h_idx : (s_idx + c);
       float uh[8], o[8], d[8], du[8], dsv[8], dspu[8], r[8];
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
       unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
       unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8(uh, o, d, c, s_g, s_b, s_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+      nb_du8(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float extra = (p == s_idx[c + i]) ? s_dmx[c + i] : 0.f;
-        r[i] = s_a[c + i] * (du[i] + extra - s_m1[c + i] - uh[i] * s_m2[c + i]);
+        const float extra = (p == p_idx[i]) ? p_dmx[i] : 0.f;
+        r[i] = p_a[i] * (du[i] + extra - p_m1[i] - uh[i] * p_m2[i]);
       }
       stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
     }
@@ -797,8 +914,18 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   if ((rc = check_launch("nb_bwd2"))) return rc;
   const size_t smc = (3 * C + 192) * sizeof(float);
   nb_bwd_coef_kernel<<<N, 256, smc, st>>>(HW, C, d->has_cbam, d->Cr, d->nc, d->beta, d->w1, d->w2, d->bwd_nc, d->dgamma,
-                                          d->dbeta, d->dw1, d->dw2);
+                                          d->dbeta, d->bwd_h);
   if ((rc = check_launch("nb_bwd_coef"))) return rc;
+  if (d->has_cbam) {
+    int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
+    if (nsplit > N) nsplit = N;
+    if (nsplit > 32) nsplit = 32;
+    if (nsplit < 1) nsplit = 1;
+    const int npb = ceil_div(N, nsplit);
+    dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
+    nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
+    if ((rc = check_launch("nb_bwd_w"))) return rc;
+  }
   const size_t sm5 = 8 * C * sizeof(float);
   DISPATCH_ITERS(iters, {
     nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,

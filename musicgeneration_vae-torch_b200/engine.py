@@ -401,6 +401,8 @@ class NormBlock:
         if self.cbam is not None:
             bwd_px = torch.empty((N, H * W, 4), dtype=torch.float32, device=dev)
             d.bwd_px = bwd_px.data_ptr()
+            bwd_h = torch.empty((N, 192), dtype=torch.float32, device=dev)
+            d.bwd_h = bwd_h.data_ptr()
             d.sa, d.cidx, d.gs = ctx["sa"].data_ptr(), ctx["cidx"].data_ptr(), ctx["gs"].data_ptr()
             d.dw1, d.dw2, d.dwsp = (grad_ptr(p) for p in self.cbam)
         if self.res_mode == 2 and dres is not None:

@@ -8,7 +8,7 @@ front of every InstanceNorm, fp32 statistics / losses / parameters.  Stated tole
              7e-4 per tensor; rounding ONLY the weights to bf16 in the fp32 oracle moves the gradients by a median
              30 % per tensor -- max-pool/argmax routing and ReLU masks switch).  The test therefore measures that
              floor (oracle with bf16-rounded weights vs oracle) and requires, per tensor carrying >= 0.1 % of the
-             gradient norm, rel-Frobenius error <= 0.10 + 3 x floor; a wiring bug shows up as >= 100 %.
+             gradient norm, rel-Frobenius error <= 0.15 + 3 x floor; a wiring bug shows up as >= 100 %.
 The per-kernel tests (tests/test_gpu_kernels.py) hold every block to 2e-3 where no such amplification exists.
 With the reference initialisation N(-1,1) (graph/weights_initializer.py) the fp32 CPU oracle itself is not
 reproducible across thread counts in backward (tests/test_oracle_golden.py), so only forward quantities are held."""
@@ -80,8 +80,8 @@ def test_model_train_step_vs_oracle(golden, oracle, kind):
                 continue
             floor = float((l2[k].grad - ograds[k]).norm()) / (n + 1e-30)
             rel = e / (n + 1e-30)
-            worst = max(worst, rel / (0.10 + 3 * floor))
-            if rel > 0.10 + 3 * floor:
+            worst = max(worst, rel / (0.15 + 3 * floor))
+            if rel > 0.15 + 3 * floor:
                 bad.append((k, round(rel, 3), round(floor, 3)))
         m.update(worst_ratio=worst, bad=bad[:8])
     report(**m)
