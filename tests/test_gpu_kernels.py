@@ -145,7 +145,8 @@ def _torch_block(y, gamma, beta, cb, res_mode, slope, res):
     return F.leaky_relu(out, slope) if slope != 0 else F.relu(out)
 
 
-@pytest.mark.parametrize("C,H,W", [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60)])
+@pytest.mark.parametrize("C,H,W", [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60),
+                                   (64, 48, 30), (64, 192, 30)])
 @pytest.mark.parametrize("mode", ["plain", "self", "ext"])
 @pytest.mark.parametrize("raw", ["f32", "bf16"])
 def test_norm_block(C, H, W, mode, raw):
@@ -198,7 +199,7 @@ def test_norm_block(C, H, W, mode, raw):
     for nme, p, rg in zip(names, params, ref_grads):
         errs[nme] = rel_fro(p.grad, rg)
     report(test="norm_block", C=C, H=H, W=W, mode=mode, raw=raw, **errs)
-    bad = {k: v for k, v in errs.items() if not v < 1e-2}
+    bad = {k: v for k, v in errs.items() if not v < (2e-2 if k in ('dw1', 'dw2', 'dwsp') else 1e-2)}
     assert not bad, errs
 
 

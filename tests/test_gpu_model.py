@@ -7,8 +7,9 @@ front of every InstanceNorm, fp32 statistics / losses / parameters.  Stated tole
   backward : this network's backward pass amplifies perturbations by ~1e4 (fp32 vs fp64 on CPU already differ by
              7e-4 per tensor; rounding ONLY the weights to bf16 in the fp32 oracle moves the gradients by a median
              30 % per tensor -- max-pool/argmax routing and ReLU masks switch).  The test therefore measures that
-             floor (oracle with bf16-rounded weights vs oracle) and requires, per tensor carrying >= 0.1 % of the
-             gradient norm, rel-Frobenius error <= 0.15 + 3 x floor; a wiring bug shows up as >= 100 %.
+             floor (oracle with bf16-rounded weights vs oracle) and requires, per tensor carrying >= 1 % of the
+             gradient norm (the contraction weights), rel-Frobenius error <= 0.15 + 3 x floor; global gradient
+             cosine >= 0.95; every tensor's norm within [0.02, 50] x the oracle's.  A wiring bug shows up as >= 100 %.
 The per-kernel tests (tests/test_gpu_kernels.py) hold every block to 2e-3 where no such amplification exists.
 With the reference initialisation N(-1,1) (graph/weights_initializer.py) the fp32 CPU oracle itself is not
 reproducible across thread counts in backward (tests/test_oracle_golden.py), so only forward quantities are held."""
@@ -76,7 +77,13 @@ def test_model_train_step_vs_oracle(golden, oracle, kind):
         O.loss_forward(g2, batch[0], True).backward()
         bad, worst = [], 0.0
         for k, (e, n) in errs.items():
-            if n < 1e-3 * gnorm:
+            share = n / gnorm
+            mine = float(model.get_parameter(k).grad.double().norm())
+            if n > 1e-6 * gnorm and not (0.02 < mine / n < 50):      # gross sanity on EVERY tensor that carries signal
+                bad.append((k, "norm ratio", round(mine / n, 4)))
+            if share < 1e-2:
+                # small tensors (CBAM MLPs, norm affine) are single ReLU-boundary / argmax decisions away from O(1)
+                # changes at batch 2 (e.g. encoder.pitch_time.cbam: a hidden pre-activation of +0.0097 in the oracle)
                 continue
             floor = float((l2[k].grad - ograds[k]).norm()) / (n + 1e-30)
             rel = e / (n + 1e-30)
@@ -90,7 +97,7 @@ def test_model_train_step_vs_oracle(golden, oracle, kind):
         assert m["z"] < 2e-2 and m["pre_z"] < 2e-2 and m["pf"] < 2e-2, m
         assert abs(m["loss"] - m["loss_want"]) < 1.5e-2 * abs(m["loss_want"]), m
         assert not m["bad"], m
-        assert cos > 0.9, m
+        assert cos > 0.95, m
     else:
         assert m["gen_meanabs"] < 5e-3, m
         assert m["z"] < 1e-2 and m["pre_z"] < 1e-2 and m["pf"] < 1e-2, m
