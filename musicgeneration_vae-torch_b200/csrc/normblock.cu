@@ -26,7 +26,7 @@ __device__ __forceinline__ void load8(const void* base, int64_t off, float* f) {
 // grid (ceil(C/256), psplit, N), block 256
 // ---------------------------------------------------------------------------------------------------
 template <bool F32>
-__global__ void __launch_bounds__(256) nb_stats_kernel(const void* __restrict__ y, int pitch, int HW, int C,
+__global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict__ y, int pitch, int HW, int C,
                                                        int psplit, float2* __restrict__ ss, u64* __restrict__ kmax,
                                                        u64* __restrict__ kmin) {
   __shared__ float s_sum[256], s_sq[256];
@@ -273,28 +273,37 @@ __device__ __forceinline__ float sa_conv(const float* __restrict__ sa_n, const f
   return q;
 }
 
+// forward 3b (CBAM only): gs = sigmoid(conv3x3_{2->1}(sa)), one thread per pixel (the map is 1/C of the tensor)
+__global__ void __launch_bounds__(256) nb_gate_kernel(int H, int W, const float* __restrict__ wsp,
+                                                      const float* __restrict__ sa, float* __restrict__ gs) {
+  __shared__ float s_w[18];
+  if (threadIdx.x < 18) s_w[threadIdx.x] = wsp[threadIdx.x];
+  __syncthreads();
+  const int n = blockIdx.y, HW = H * W;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  gs[(int64_t)n * HW + p] = 1.f / (1.f + expf(-sa_conv(sa + (int64_t)n * HW * 2, s_w, H, W, p / W, p % W)));
+}
+
 // ---------------------------------------------------------------------------------------------------
-// forward 4 (CBAM only): gs = sigmoid(conv3x3(sa)); out = act(r + u*gc*gs)
+// forward 4 (CBAM only): out = act(r + u*gc*gs)
 // grid (pchunks, N), block 256, dyn smem 3*C floats
 // ---------------------------------------------------------------------------------------------------
 template <bool F32, int ITERS>
 __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ y, int y_pitch, int H, int W, int C,
-                                                       const float* __restrict__ nc, const float* __restrict__ wsp,
-                                                       const float* __restrict__ sa, int res_mode,
+                                                       const float* __restrict__ nc, int res_mode,
                                                        const bf16* __restrict__ res, int res_pitch, float slope,
-                                                       bf16* __restrict__ out, int out_pitch, float* __restrict__ gs,
-                                                       int ppc) {
+                                                       bf16* __restrict__ out, int out_pitch,
+                                                       const float* __restrict__ gs, int ppc) {
   // u is recomputed from the raw fp32 conv output (not from the bf16 uhat) so that the sign of the block output --
   // the ReLU mask the backward pass uses -- agrees with an fp32 evaluation
   extern __shared__ float sm[];
   float* s_a = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C;
-  __shared__ float s_w[18];
   const int n = blockIdx.y, HW = H * W;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* q = nc + ((int64_t)n * C + c) * NC_W;
     s_a[c] = q[NC_A]; s_b[c] = q[NC_B]; s_gc[c] = q[NC_GC];
   }
-  if (threadIdx.x < 18) s_w[threadIdx.x] = wsp[threadIdx.x];
   __syncthreads();
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -312,17 +321,10 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ 
   }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ybase = (int64_t)n * HW * y_pitch, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
-  const float* sa_n = sa + (int64_t)n * HW * 2;
   for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
     const int p = pb + grp;
-    const bool valid = p < p_end;
-    float g = 0.f;
-    if (valid && sub == 0) {
-      g = 1.f / (1.f + expf(-sa_conv(sa_n, s_w, H, W, p / W, p % W)));
-      gs[(int64_t)n * HW + p] = g;
-    }
-    g = __shfl_sync(0xffffffffu, g, grp * G);
-    if (!valid) continue;
+    if (p >= p_end) continue;
+    const float g = gs[(int64_t)n * HW + p];
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
@@ -447,13 +449,12 @@ __global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const floa
   if (threadIdx.x < 18) { s_w[threadIdx.x] = wsp[threadIdx.x]; s_red[threadIdx.x] = 0.f; }
   __syncthreads();
   const int n = blockIdx.y, HW = H * W;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const float* sa_n = sa + (int64_t)n * HW * 2;
   float* px_n = bwd_px + (int64_t)n * HW * BP_W;
   float part[18];
 #pragma unroll
   for (int i = 0; i < 18; ++i) part[i] = 0.f;
-  if (p < HW) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += gridDim.x * blockDim.x) {
     const int py = p / W, px = p % W;
     const float dq = px_n[(int64_t)p * BP_W + BP_DQ];
     float dmean = 0.f, dmax = 0.f;
@@ -472,8 +473,8 @@ __global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const floa
         const int y2 = py + ky - 1, x2 = px + kx - 1;
         if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
           const float2 v = *reinterpret_cast<const float2*>(sa_n + ((int64_t)y2 * W + x2) * 2);
-          part[ky * 3 + kx] = dq * v.x;
-          part[9 + ky * 3 + kx] = dq * v.y;
+          part[ky * 3 + kx] += dq * v.x;
+          part[9 + ky * 3 + kx] += dq * v.y;
         }
       }
     px_n[(int64_t)p * BP_W + BP_DMEAN] = dmean;
@@ -490,6 +491,7 @@ __global__ void __launch_bounds__(256) nb_bwd_sp_kernel(int H, int W, const floa
 
 // gradient wrt u for 8 channels of one pixel (shared by the reduction pass and the final pass, so that du is
 // never rounded to bf16 before the InstanceNorm projection removes its common-mode part)
+template <bool NEED_U>
 __device__ __forceinline__ void nb_du8(const float* uh, const float* o, const float* d, int c, const float* p_g,
                                        const float* p_b, const float* p_gc, int has_cbam, int res_mode, float slope,
                                        float g, float dmean, float dmax, int ci, float* du, float* dsv, float* dspu) {
@@ -503,7 +505,7 @@ __device__ __forceinline__ void nb_du8(const float* uh, const float* o, const fl
       const float gc = p_gc[i];
       const float dsp = dmean + ((c + i) == ci ? dmax : 0.f);   // grad wrt u1 = u*gc from the spatial branch
       v += ds * gc * g + dsp * gc;
-      su = dsp * (p_g[i] * uh[i] + p_b[i]);
+      if (NEED_U) su = dsp * (p_g[i] * uh[i] + p_b[i]);
     }
     du[i] = v;
     dspu[i] = su;
@@ -512,7 +514,7 @@ __device__ __forceinline__ void nb_du8(const float* uh, const float* o, const fl
 
 // backward 2: per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += ...; writes dres
 template <int ITERS>
-__global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
+__global__ void __launch_bounds__(256, ITERS == 1 ? 2 : 1) nb_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
                                                       const bf16* __restrict__ out, int out_pitch,
                                                       const bf16* __restrict__ uhat, int HW, int C,
                                                       const float* __restrict__ nc, const float* __restrict__ gamma,
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(256) nb_bwd2_kernel(const bf16* __restrict__ d
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
       unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
       unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+      nb_du8<true>(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         a1[it][i] += du[i];
@@ -688,7 +690,7 @@ __global__ void __launch_bounds__(256) nb_bwd_w_kernel(int N, int C, int Cr, con
 
 // backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2); du is recomputed in fp32
 template <int ITERS>
-__global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ dout, int dout_pitch,
+__global__ void __launch_bounds__(256, ITERS == 1 ? 3 : 1) nb_bwd3_kernel(const bf16* __restrict__ dout, int dout_pitch,
                                                       const bf16* __restrict__ out, int out_pitch,
                                                       const bf16* __restrict__ uhat, int HW, int C,
                                                       const float* __restrict__ nc,
@@ -699,26 +701,23 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
                                                       const float* __restrict__ bwd_nc, int has_cbam, int res_mode,
                                                       float slope, bf16* __restrict__ dy, int dy_pitch, int ppc) {
   extern __shared__ float sm[];
-  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_a = sm + 3 * C;
-  float* s_m1 = sm + 4 * C; float* s_m2 = sm + 5 * C; float* s_dmx = sm + 6 * C;
-  int* s_idx = (int*)(sm + 7 * C);
+  float* s_gc = sm; float* s_a = sm + C; float* s_m1 = sm + 2 * C; float* s_m2 = sm + 3 * C; float* s_dmx = sm + 4 * C;
+  int* s_idx = (int*)(sm + 5 * C);
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int64_t o = (int64_t)n * C + c;
-    s_g[c] = gamma[c]; s_b[c] = beta[c];
+    const float a = nc[o * NC_W + NC_A];
     s_gc[c] = nc[o * NC_W + NC_GC];
-    s_a[c] = nc[o * NC_W + NC_A];
-    s_m1[c] = bwd_nc[o * BN_W + BN_S1];
-    s_m2[c] = bwd_nc[o * BN_W + BN_S2];
-    s_dmx[c] = bwd_nc[o * BN_W + BN_DMX];
+    s_a[c] = a;
+    s_m1[c] = a * bwd_nc[o * BN_W + BN_S1];      // pre-multiplied by a: dy = a*du + a*extra - a*m1 - uhat*(a*m2)
+    s_m2[c] = a * bwd_nc[o * BN_W + BN_S2];
+    s_dmx[c] = a * bwd_nc[o * BN_W + BN_DMX];
     s_idx[c] = has_cbam ? nc_idx[o] : -1;
   }
   __syncthreads();
   const int G = min(32, C / 8);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % G, grp = lane / G, gpw = 32 / G;
-  float h_g[8];
-  float h_b[8];
   float h_gc[8];
   float h_a[8];
   float h_m1[8];
@@ -728,8 +727,6 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
   if (ITERS == 1) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      h_g[i] = s_g[sub * 8 + i];
-      h_b[i] = s_b[sub * 8 + i];
       h_gc[i] = s_gc[sub * 8 + i];
       h_a[i] = s_a[sub * 8 + i];
       h_m1[i] = s_m1[sub * 8 + i];
@@ -757,8 +754,6 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
 #pragma unroll
     for (int it = 0; it < ITERS; ++it) {
       const int c = (it * G + sub) * 8;
-      const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
-      const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
       const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
       const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
       const float* p_m1 = (ITERS == 1) ? h_m1 : (s_m1 + c);
@@ -769,11 +764,11 @@ __global__ void __launch_bounds__(256) nb_bwd3_kernel(const bf16* __restrict__ d
       unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
       unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
       unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+      nb_du8<false>(uh, o, d, c, p_gc, p_gc, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float extra = (p == p_idx[i]) ? p_dmx[i] : 0.f;
-        r[i] = p_a[i] * (du[i] + extra - p_m1[i] - uh[i] * p_m2[i]);
+        r[i] = p_a[i] * du[i] + extra - p_m1[i] - uh[i] * p_m2[i];
       }
       stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
     }
@@ -825,13 +820,11 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   u64* kmax = (u64*)(ss + NC);
   u64* kmin = kmax + NC;
   const int cchunks = ceil_div(C, 256);
-  int psplit = 1;
-  if ((int64_t)N * cchunks < 148 * 2) {
-    psplit = ceil_div(148 * 2, N * cchunks);
-    const int maxsplit = ceil_div(HW, 64);
-    if (psplit > maxsplit) psplit = maxsplit;
-    if (psplit < 1) psplit = 1;
-  }
+  // enough CTAs for ~8 per SM; every CTA should still stream >= 256 pixels
+  int psplit = ceil_div(148 * 8, N * cchunks);
+  const int maxsplit = HW / 256 > 0 ? HW / 256 : 1;
+  if (psplit > maxsplit) psplit = maxsplit;
+  if (psplit < 1) psplit = 1;
   if (psplit > 1) {
     if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
   }
@@ -866,13 +859,16 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   if (!d->has_cbam) return BVAE_OK;
 
   const size_t sm4 = 3 * C * sizeof(float);
+  dim3 gg(ceil_div(HW, 256), N);
+  nb_gate_kernel<<<gg, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->gs);
+  if ((rc = check_launch("nb_gate"))) return rc;
   DISPATCH_ITERS(iters, {
     if (d->y_f32)
-      nb_apply_kernel<true, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->wsp, d->sa, d->res_mode,
+      nb_apply_kernel<true, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->res_mode,
                                                        (const bf16*)d->res, d->res_pitch, d->slope, (bf16*)d->out,
                                                        d->out_pitch, d->gs, ppc);
     else
-      nb_apply_kernel<false, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->wsp, d->sa, d->res_mode,
+      nb_apply_kernel<false, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->res_mode,
                                                         (const bf16*)d->res, d->res_pitch, d->slope, (bf16*)d->out,
                                                         d->out_pitch, d->gs, ppc);
   });
@@ -901,7 +897,7 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
                                                 d->bwd_nc, d->bwd_px, ppc);
     });
     if ((rc = check_launch("nb_bwd1"))) return rc;
-    dim3 gs(ceil_div(HW, 256), N);
+    dim3 gs(ceil_div(HW, 256 * 8), N);          // up to 8 pixels per thread, one block reduction of dwsp
     nb_bwd_sp_kernel<<<gs, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->bwd_px, d->dwsp);
     if ((rc = check_launch("nb_bwd_sp"))) return rc;
   }
@@ -926,7 +922,7 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
     if ((rc = check_launch("nb_bwd_w"))) return rc;
   }
-  const size_t sm5 = 8 * C * sizeof(float);
+  const size_t sm5 = 6 * C * sizeof(float);
   DISPATCH_ITERS(iters, {
     nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
                                               (const bf16*)d->uhat, HW, C, d->nc, d->nc_idx, d->gamma, d->beta, d->gs,
