@@ -96,6 +96,8 @@ typedef struct bvae_wgrad_desc {
   const void* a;  /* bf16 NHWC [N, AH, AW, Ca], pitch a_pitch */
   const void* s;  /* bf16 NHWC [N, SH, SW, Cs], pitch s_pitch */
   float* dw;
+  float* scratch; /* optional fp32 [Ca*T*Cs], all zeros on entry and on exit: lets the tcgen05 kernel reduce with
+                     16-byte vector atomics into a packed [ra][tap][rs] layout before unpacking into dw */
   int32_t N, AH, AW, Ca, a_pitch;
   int32_t SH, SW, Cs, s_pitch;
   int32_t sy, sx;

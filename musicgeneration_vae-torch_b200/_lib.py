@@ -33,7 +33,7 @@ class ConvDesc(C.Structure):
 
 class WgradDesc(C.Structure):
     """struct bvae_wgrad_desc."""
-    _fields_ = [("a", c_vp), ("s", c_vp), ("dw", c_vp),
+    _fields_ = [("a", c_vp), ("s", c_vp), ("dw", c_vp), ("scratch", c_vp),
                 ("N", c_i32), ("AH", c_i32), ("AW", c_i32), ("Ca", c_i32), ("a_pitch", c_i32),
                 ("SH", c_i32), ("SW", c_i32), ("Cs", c_i32), ("s_pitch", c_i32),
                 ("sy", c_i32), ("sx", c_i32), ("ntaps", c_i32), ("T", c_i32),

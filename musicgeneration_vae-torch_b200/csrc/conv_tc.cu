@@ -477,7 +477,9 @@ struct alignas(64) WgradTcParams {
   int a_atoms;                      // 64-channel atoms of the anchor tile actually loaded (1 or 2)
   int ra_tiles, rs_tiles;
   int Ca, Cs;
-  float* dw;
+  float* dw;                        // destination of the reduction (parameter gradient or packed scratch)
+  long long s_ra, s_t;              // element strides of the anchor channel / the tap; the shifted channel stride is
+  int s_rs;                         // 1 (vector reductions) or T (scalar reductions straight into [ra][rs][tap])
 };
 
 // CB = channels per swizzle atom (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NS = shifted-channel tile (multiple of
@@ -494,7 +496,6 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   constexpr uint32_t LAYOUT = CB == 64 ? 2u : 4u;
   constexpr uint32_t SBO = 8 * ROW_BYTES;              // 8 pixel rows
   constexpr uint32_t KSTEP = (16 * ROW_BYTES) >> 4;    // 16 pixel rows per MMA, in encoded (>>4) address units
-  constexpr uint32_t IDESC = make_idesc(128, NS, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -564,10 +565,15 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
       // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
       const uint64_t adesc = make_sdesc(st, ATOM_BYTES, SBO, LAYOUT);
-      for (int t = 0; t < ntap; ++t) {
+      // the atoms of consecutive taps are contiguous in smem and their accumulators are contiguous TMEM columns, so
+      // up to 256/NS taps go into ONE instruction with N = taps*NS (A is read once for all of them)
+      constexpr int TG = 256 / NS;
+      for (int t = 0; t < ntap; t += TG) {
+        const int tg = min(TG, ntap - t);
+        const uint32_t idesc = make_idesc(128, tg * NS, 1, 1);
         const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, SBO, LAYOUT);
         for (int j = 0; j < ksteps; ++j)
-          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, IDESC, (it | j) ? 1u : 0u);
+          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, idesc, (it | j) ? 1u : 0u);
       }
       umma_commit(empty_bar + s);
     }
@@ -587,14 +593,41 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * NS + c0), v);
       if (!valid || ck1 <= ck0) continue;
-      float* dst = p.dw + ((int64_t)ra * p.Cs + rs_tile * NS + c0) * p.T + tix;
+      if (p.s_rs == 1) {
+        float* dst = p.dw + (int64_t)ra * p.s_ra + (int64_t)tix * p.s_t + rs_tile * NS + c0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)i * p.T, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 4)
+          atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                   __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+      } else {
+        float* dst = p.dw + ((int64_t)ra * p.Cs + rs_tile * NS + c0) * p.T + tix;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)i * p.T, __uint_as_float(v[i]));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// packed scratch [ra][tap][rs] -> parameter layout [ra][rs][tap] (accumulating), and re-zero the scratch.
+// One CTA per (ra, RC shifted channels): float4 reads of T x RC floats, coalesced read-modify-write of RC*T floats.
+template <int RC>
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(float* __restrict__ scratch, float* __restrict__ dw, int Cs, int T) {
+  __shared__ float s[BVAE_MAX_TAPS][RC + 1];
+  const int ra = blockIdx.y, rs0 = blockIdx.x * RC;
+  float* src = scratch + ((int64_t)ra * T) * Cs + rs0;
+  for (int e = threadIdx.x; e < T * (RC / 4); e += blockDim.x) {
+    const int t = e / (RC / 4), r = (e % (RC / 4)) * 4;
+    float4* q = reinterpret_cast<float4*>(src + (int64_t)t * Cs + r);
+    const float4 v = *q;
+    *q = make_float4(0.f, 0.f, 0.f, 0.f);
+    s[t][r] = v.x; s[t][r + 1] = v.y; s[t][r + 2] = v.z; s[t][r + 3] = v.w;
+  }
+  __syncthreads();
+  float* dst = dw + ((int64_t)ra * Cs + rs0) * T;
+  for (int e = threadIdx.x; e < T * RC; e += blockDim.x) dst[e] += s[e % T][e / T];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -863,7 +896,8 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.nchunks = P.chunks_w * P.chunks_h * P.chunks_n;
   P.ra_tiles = ceil_div(d->Ca, 128); P.rs_tiles = d->Cs / NS;
   P.a_atoms = d->Ca >= 128 ? 128 / CB : d->Ca / CB;
-  P.Ca = d->Ca; P.Cs = d->Cs; P.dw = d->dw;
+  P.Ca = d->Ca; P.Cs = d->Cs;
+
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
   int splits = ceil_div(148 * 2, out_tiles);
   const int max_splits = ceil_div(P.nchunks, 8);
@@ -871,12 +905,28 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   if (splits < 1) splits = 1;
   P.chunks_per_split = ceil_div(P.nchunks, splits);
   P.splits = ceil_div(P.nchunks, P.chunks_per_split);
+  // Reduction target.  Many pixel splits over a small weight (encoder front, decoder back): vector atomics into the
+  // packed scratch, then one unpack pass.  Few splits over a large weight: scalar atomics straight into dw are cheaper
+  // than an extra pass over the weight.
+  const bool packed = d->T > 1 && d->scratch != nullptr && P.splits >= 3;
+  if (d->T == 1) { P.dw = d->dw; P.s_ra = d->Cs; P.s_t = 0; P.s_rs = 1; }
+  else if (packed) { P.dw = d->scratch; P.s_ra = (long long)d->T * d->Cs; P.s_t = d->Cs; P.s_rs = 1; }
+  else { P.dw = d->dw; P.s_ra = 0; P.s_t = 0; P.s_rs = d->T; }
   const long grid = (long)out_tiles * P.splits;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "wgrad_tc: grid too large");
-  if (CB == 32) return NS == 64 ? launch_wgrad<32, 64, 2>(P, (int)grid, stream) : launch_wgrad<32, 32, 2>(P, (int)grid, stream);
-  if (NS == 256) return launch_wgrad<64, 256, 2>(P, (int)grid, stream);
-  if (NS == 128) return launch_wgrad<64, 128, 2>(P, (int)grid, stream);
-  return launch_wgrad<64, 64, 2>(P, (int)grid, stream);
+  if (CB == 32) rc = NS == 64 ? launch_wgrad<32, 64, 2>(P, (int)grid, stream) : launch_wgrad<32, 32, 2>(P, (int)grid, stream);
+  else if (NS == 256) rc = launch_wgrad<64, 256, 2>(P, (int)grid, stream);
+  else if (NS == 128) rc = launch_wgrad<64, 128, 2>(P, (int)grid, stream);
+  else rc = launch_wgrad<64, 64, 2>(P, (int)grid, stream);
+  if (rc || !packed) return rc;
+  if (d->Cs % 128 == 0) {
+    dim3 ug(d->Cs / 128, d->Ca);
+    wgrad_unpack_kernel<128><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+  } else {
+    dim3 ug(d->Cs / 32, d->Ca);
+    wgrad_unpack_kernel<32><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+  }
+  return check_launch("wgrad_unpack");
 }
 
 }  // namespace bvae

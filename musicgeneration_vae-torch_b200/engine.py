@@ -212,6 +212,7 @@ class GemmLayer:
             self.f_src = (Cin * T, T)
             self.d_src = (T, Cin * T)
         self._wf = self._wd = None
+        self._wscratch = None       # zero-in / zero-out fp32 scratch for the packed weight-gradient reduction
         self._wf_key = self._wd_key = None
         self._cache: Dict[tuple, object] = {}
 
@@ -329,6 +330,10 @@ class GemmLayer:
                     d.dy[t], d.dx[t], d.tap_idx[t] = t // self.kw - self.py, t % self.kw - self.px, t
                 self._cache[key] = d
             d.a, d.s, d.dw = a.ptr, s.ptr, grad_ptr(self.weight)
+            if self.T > 1 and self.Cin % 32 == 0 and self.Cout % 32 == 0:
+                if self._wscratch is None or self._wscratch.device != self.weight.device:
+                    self._wscratch = torch.zeros(self.weight.numel(), dtype=torch.float32, device=self.weight.device)
+                d.scratch = self._wscratch.data_ptr()
             _lib.check(_timed("wgrad_gemm", lib.bvae_wgrad_gemm, C.byref(d), _IMPL[0], st,
                               detail="w %s %d->%d k%dx%d s%dx%d in%dx%d" % (self.kind, self.Cin, self.Cout, self.kh, self.kw,
                                                                             self.sy, self.sx, x.H, x.W)), "wgrad_gemm")
