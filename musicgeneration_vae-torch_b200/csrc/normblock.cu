@@ -102,6 +102,30 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
   }
 }
 
+// ---- channel-attention MLP helpers: W2 is [C][Cr] row-major, so a row is read by the lanes of ONE warp (coalesced)
+// v[c] = sum_j W2[c][j] * h[j]
+__device__ __forceinline__ void mlp_rows_dot(const float* __restrict__ w2, int C, int Cr, const float* s_h, float* s_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int c = warp; c < C; c += nw) {
+    float p = 0.f;
+    for (int j = lane; j < Cr; j += 32) p += w2[(int64_t)c * Cr + j] * s_h[j];
+    p = warp_sum(p);
+    if (lane == 0) s_out[c] = p;
+  }
+}
+// dh[j] += sum_c W2[c][j] * dv[c]   (s_dh must be zero on entry; Cr <= 64)
+__device__ __forceinline__ void mlp_cols_dot(const float* __restrict__ w2, int C, int Cr, const float* s_dv, float* s_dh) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  for (int c = warp; c < C; c += nw) {
+    const float dv = s_dv[c];
+    if (lane < Cr) a0 += w2[(int64_t)c * Cr + lane] * dv;
+    if (lane + 32 < Cr) a1 += w2[(int64_t)c * Cr + lane + 32] * dv;
+  }
+  if (lane < Cr) atomicAdd(&s_dh[lane], a0);
+  if (lane + 32 < Cr) atomicAdd(&s_dh[lane + 32], a1);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward 2: per-sample coefficients (mean, rstd, a, b), max-pooled value, channel-attention MLP -> gc
 // grid N, block 256, dynamic smem (2*C + 64) floats
@@ -158,11 +182,10 @@ __global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y
     if (lane == 0) s_h[j] = fmaxf(pa, 0.f) + fmaxf(pm, 0.f);   // W2 is linear: W2 ha + W2 hm = W2 (ha + hm)
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float v = 0.f;
-    for (int j = 0; j < Cr; ++j) v += w2[(int64_t)c * Cr + j] * s_h[j];
-    nc[((int64_t)n * C + c) * NC_W + NC_GC] = 1.f / (1.f + expf(-v));
-  }
+  mlp_rows_dot(w2, C, Cr, s_h, s_avg);            // s_avg is free now: reuse it for the pre-sigmoid gate
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    nc[((int64_t)n * C + c) * NC_W + NC_GC] = 1.f / (1.f + expf(-s_avg[c]));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -620,18 +643,19 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
       s_mx[c] = q0[c * NC_W + NC_EXTU];
       s_dv[c] = bn[c * BN_W + BN_DGC] * gc * (1.f - gc);
     }
+    if (threadIdx.x < 64) s_dh[threadIdx.x] = 0.f;
     __syncthreads();
     for (int j = warp; j < Cr; j += 8) {
-      float pa = 0.f, pm = 0.f, dh = 0.f;
+      float pa = 0.f, pm = 0.f;
       for (int c = lane; c < C; c += 32) {
         const float w = w1[(int64_t)j * C + c];
         pa += w * s_avg[c];
         pm += w * s_mx[c];
-        dh += w2[(int64_t)c * Cr + j] * s_dv[c];
       }
-      pa = warp_sum(pa); pm = warp_sum(pm); dh = warp_sum(dh);
-      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; s_dh[j] = dh; }
+      pa = warp_sum(pa); pm = warp_sum(pm);
+      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; }
     }
+    mlp_cols_dot(w2, C, Cr, s_dv, s_dh);
     __syncthreads();
     // the weight gradients dW2[c][j] = sum_n dv[n,c] * (relu(ha)+relu(hm))[n,j] and
     // dW1[j][c] = sum_n dh[n,j] * ([ha>0] avg_c + [hm>0] mx[n,c]) are reduced over samples by nb_bwd_w_kernel;
@@ -776,6 +800,397 @@ __global__ void __launch_bounds__(256, ITERS == 1 ? 3 : 1) nb_bwd3_kernel(const 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Small maps (H*W <= 128: the 6x3 / 3x2 / 12x2 / 6x4 / 12x7 / 24x4 / 12x8 sites with 256..1024 channels).
+// One CTA owns one sample, so every per-(n,c) and per-pixel reduction is CTA-local: the whole forward (stats,
+// coefficients, channel MLP, spatial pooling, gate, apply) is ONE kernel and the whole backward is ONE kernel,
+// phases separated by __syncthreads instead of launches; the sample's tensors (<= 200 KB) are re-read from L1/L2.
+// Thread (cv, pl): channel vector cv = t % NV (8 channels), pixel lane pl = t / NV; NV = C/8, PL = 256/NV.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SMALL_HW = 128;
+
+// combine a per-thread partial over 8 channels of pixel p into the per-pixel accumulator
+__device__ __forceinline__ void pix_add(float v, int G, float* dst) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & (G - 1)) == 0) atomicAdd(dst, v);
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d) {
+  extern __shared__ float sm[];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = 256 / NV;
+  float* s_mean = sm; float* s_rstd = sm + C; float* s_a = sm + 2 * C; float* s_b = sm + 3 * C;
+  float* s_gc = sm + 4 * C; float* s_mx = sm + 5 * C; float* s_sum = sm + 6 * C; float* s_sq = sm + 7 * C;
+  u64* s_kmax = (u64*)(sm + 8 * C);
+  u64* s_kmin = s_kmax + C;
+  float* s_psum = (float*)(s_kmin + C);         // [128]
+  u64* s_pkey = (u64*)(s_psum + SMALL_HW);      // [128]
+  float* s_sa = (float*)(s_pkey + SMALL_HW);    // [128][2]
+  float* s_gs = s_sa + 2 * SMALL_HW;            // [128]
+  float* s_h = s_gs + SMALL_HW;                 // [64]
+  float* s_w = s_h + 64;                        // [18]
+  const int n = blockIdx.x, t = threadIdx.x;
+  const int cv = t % NV, pl = t / NV, c0 = cv * 8;
+  const int G = NV < 32 ? NV : 32;              // lanes of a warp that share a pixel
+  const int lane = t & 31, warp = t >> 5;
+  const int64_t ybase = (int64_t)n * HW * d.y_pitch, ubase = (int64_t)n * HW * C;
+  const int64_t obase = (int64_t)n * HW * d.out_pitch, rbase = (int64_t)n * HW * d.res_pitch;
+  bf16* uhat = (bf16*)d.uhat;
+  bf16* out = (bf16*)d.out;
+  const bf16* res = (const bf16*)d.res;
+
+  for (int c = t; c < C; c += 256) { s_sum[c] = 0.f; s_sq[c] = 0.f; s_kmax[c] = 0; s_kmin[c] = 0; }
+  if (t < SMALL_HW) { s_psum[t] = 0.f; s_pkey[t] = 0; }
+  if (t < 18 && d.has_cbam) s_w[t] = d.wsp[t];
+  __syncthreads();
+
+  // ---- phase A: per-channel shifted sums and extrema
+  {
+    float shift[8], sum[8], sq[8], vmx[8], vmn[8];
+    int imx[8], imn[8];
+    load8<F32>(d.y, ybase + c0, shift);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
+    for (int p = pl; p < HW; p += PL) {
+      float v[8];
+      load8<F32>(d.y, ybase + (int64_t)p * d.y_pitch + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dl = v[i] - shift[i];
+        sum[i] += dl; sq[i] += dl * dl;
+        if (v[i] > vmx[i]) { vmx[i] = v[i]; imx[i] = p; }
+        if (v[i] < vmn[i]) { vmn[i] = v[i]; imn[i] = p; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_sum[c0 + i], sum[i]);
+      atomicAdd(&s_sq[c0 + i], sq[i]);
+      if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
+      if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)HW;
+  for (int c = t; c < C; c += 256) {
+    const int64_t o = (int64_t)n * C + c;
+    const float shift = F32 ? ((const float*)d.y)[ybase + c] : bf2f(((const bf16*)d.y)[ybase + c]);
+    const float md = s_sum[c] * inv;
+    const float mean = shift + md;
+    const float var = fmaxf(s_sq[c] * inv - md * md, 0.f);
+    const float rstd = rsqrtf(var + d.eps);
+    const float g = d.gamma[c], b0 = d.beta[c];
+    const float a = g * rstd, b = b0 - mean * a;
+    float yext; uint32_t idx;
+    if (a >= 0.f) { const u64 k = s_kmax[c]; yext = key_val(k); idx = key_idx(k); }
+    else { const u64 k = s_kmin[c]; yext = -key_val(k); idx = key_idx(k); }
+    const float ext_uhat = (yext - mean) * rstd;
+    const float ext_u = g * ext_uhat + b0;
+    float* q = d.nc + o * NC_W;
+    q[NC_MEAN] = mean; q[NC_RSTD] = rstd; q[NC_A] = a; q[NC_B] = b;
+    q[NC_EXTU] = ext_u; q[NC_EXTUHAT] = ext_uhat; q[NC_GC] = 1.f; q[NC_SPARE] = 0.f;
+    d.nc_idx[o] = (int32_t)idx;
+    s_mean[c] = mean; s_rstd[c] = rstd; s_a[c] = a; s_b[c] = b; s_mx[c] = ext_u; s_gc[c] = 1.f;
+  }
+  __syncthreads();
+
+  // ---- phase B: channel-attention MLP (avg pool of an instance-normalised map is exactly beta)
+  if (d.has_cbam) {
+    for (int j = warp; j < d.Cr; j += 8) {
+      float pa = 0.f, pm = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float w = d.w1[(int64_t)j * C + c];
+        pa += w * d.beta[c];
+        pm += w * s_mx[c];
+      }
+      pa = warp_sum(pa); pm = warp_sum(pm);
+      if (lane == 0) s_h[j] = fmaxf(pa, 0.f) + fmaxf(pm, 0.f);
+    }
+    __syncthreads();
+    mlp_rows_dot(d.w2, C, d.Cr, s_h, s_sum);       // s_sum is free after phase A
+    __syncthreads();
+    for (int c = t; c < C; c += 256) {
+      const float gc = 1.f / (1.f + expf(-s_sum[c]));
+      s_gc[c] = gc;
+      d.nc[((int64_t)n * C + c) * NC_W + NC_GC] = gc;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase C: write uhat; per-pixel mean / max / argmax over channels of u*gc (or the final output without CBAM)
+  for (int pb = 0; pb < HW; pb += PL) {
+    const int p = pb + pl;
+    const bool valid = p < HW;
+    float sum = 0.f, mx = -INFINITY;
+    int mxc = 0;
+    if (valid) {
+      float v[8], uh[8], o[8];
+      load8<F32>(d.y, ybase + (int64_t)p * d.y_pitch + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uh[i] = (v[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+        const float u = s_a[c0 + i] * v[i] + s_b[c0 + i];
+        const float u1 = u * s_gc[c0 + i];
+        sum += u1;
+        if (u1 > mx) { mx = u1; mxc = c0 + i; }
+        o[i] = act_fwd(u, d.slope);
+      }
+      stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
+      if (!d.has_cbam) stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
+    }
+    if (d.has_cbam) {
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+        if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+      }
+      if (valid && (t & (G - 1)) == 0) {
+        atomicAdd(&s_psum[p], sum);
+        atomicMax(&s_pkey[p], make_key(mx, (uint32_t)mxc));     // max value, smallest channel index on ties
+      }
+    }
+  }
+  if (!d.has_cbam) return;
+  __syncthreads();
+  if (t < HW) {
+    const u64 k = s_pkey[t];
+    const float mean_c = s_psum[t] / (float)C, max_c = key_val(k);
+    s_sa[2 * t] = mean_c; s_sa[2 * t + 1] = max_c;
+    const int64_t o = (int64_t)n * HW + t;
+    d.sa[o * 2] = mean_c; d.sa[o * 2 + 1] = max_c;
+    d.cidx[o] = (int32_t)key_idx(k);
+  }
+  __syncthreads();
+  // ---- phase D: spatial gate
+  if (t < HW) {
+    const float g = 1.f / (1.f + expf(-sa_conv(s_sa, s_w, H, W, t / W, t % W)));
+    s_gs[t] = g;
+    d.gs[(int64_t)n * HW + t] = g;
+  }
+  __syncthreads();
+  // ---- phase E: out = act(r + u*gc*gs)
+  for (int p = pl; p < HW; p += PL) {
+    float v[8], r[8], o[8];
+    load8<F32>(d.y, ybase + (int64_t)p * d.y_pitch + c0, v);
+    if (d.res_mode == 2) unpack8(ldg8(res + rbase + (int64_t)p * d.res_pitch + c0), r);
+    const float g = s_gs[p];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float u = s_a[c0 + i] * v[i] + s_b[c0 + i];
+      const float cb = u * s_gc[c0 + i] * g;
+      const float rr = d.res_mode == 1 ? u : (d.res_mode == 2 ? r[i] : 0.f);
+      o[i] = act_fwd(rr + cb, d.slope);
+    }
+    stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
+  }
+}
+
+__global__ void __launch_bounds__(256) nb_small_bwd_kernel(const bvae_nb_desc d) {
+  extern __shared__ float sm[];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = 256 / NV, Cr = d.Cr;
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_a = sm + 3 * C;
+  float* s_dgc = sm + 4 * C; float* s_S1 = sm + 5 * C; float* s_S2 = sm + 6 * C; float* s_dv = sm + 7 * C;
+  float* s_m1 = sm + 8 * C; float* s_m2 = sm + 9 * C; float* s_dmx = sm + 10 * C;
+  int* s_idx = (int*)(sm + 11 * C);
+  float* s_gs = sm + 12 * C;                    // [128]
+  float* s_dq = s_gs + SMALL_HW;                // [128]  (first dgs, then dq)
+  float* s_dmean = s_dq + SMALL_HW;             // [128]
+  float* s_dmax = s_dmean + SMALL_HW;           // [128]
+  int* s_cidx = (int*)(s_dmax + SMALL_HW);      // [128]
+  float* s_sa = (float*)(s_cidx + SMALL_HW);    // [128][2]
+  float* s_ha = s_sa + 2 * SMALL_HW;            // [64]
+  float* s_hm = s_ha + 64; float* s_dh = s_hm + 64;
+  float* s_w = s_dh + 64;                       // [18]
+  float* s_dw = s_w + 18;                       // [18]
+  const int n = blockIdx.x, t = threadIdx.x;
+  const int cv = t % NV, pl = t / NV, c0 = cv * 8;
+  const int G = NV < 32 ? NV : 32;
+  const int lane = t & 31, warp = t >> 5;
+  const int has_cbam = d.has_cbam, res_mode = d.res_mode;
+  const float slope = d.slope;
+  const bf16* dout = (const bf16*)d.dout; const bf16* out = (const bf16*)d.out; const bf16* uhat = (const bf16*)d.uhat;
+  bf16* dy = (bf16*)d.dy; bf16* dres = (bf16*)d.dres;
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * d.out_pitch, dbase = (int64_t)n * HW * d.dout_pitch;
+  const int64_t ybase = (int64_t)n * HW * d.dy_pitch, rbase = (int64_t)n * HW * d.dres_pitch;
+  const float* q0 = d.nc + (int64_t)n * C * NC_W;
+
+  for (int c = t; c < C; c += 256) {
+    s_g[c] = d.gamma[c]; s_b[c] = d.beta[c];
+    s_gc[c] = q0[c * NC_W + NC_GC]; s_a[c] = q0[c * NC_W + NC_A];
+    s_dgc[c] = 0.f; s_S1[c] = 0.f; s_S2[c] = 0.f;
+    s_idx[c] = has_cbam ? d.nc_idx[(int64_t)n * C + c] : -1;
+  }
+  if (t < SMALL_HW) {
+    const bool v = has_cbam && t < HW;
+    const int64_t o = (int64_t)n * HW + t;
+    s_gs[t] = v ? d.gs[o] : 0.f;
+    s_cidx[t] = v ? d.cidx[o] : -1;
+    s_sa[2 * t] = v ? d.sa[o * 2] : 0.f; s_sa[2 * t + 1] = v ? d.sa[o * 2 + 1] : 0.f;
+    s_dq[t] = 0.f; s_dmean[t] = 0.f; s_dmax[t] = 0.f;
+  }
+  if (t < 18) { s_w[t] = has_cbam ? d.wsp[t] : 0.f; s_dw[t] = 0.f; }
+  __syncthreads();
+
+  if (has_cbam) {
+    // ---- phase 1: dgs[p] = sum_c ds*u*gc ; dgc[c] += sum_p ds*u*gs
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int pb = 0; pb < HW; pb += PL) {
+      const int p = pb + pl;
+      float dgs = 0.f;
+      if (p < HW) {
+        float uh[8], o[8], dd[8];
+        unpack8(ldg8(uhat + ubase + (int64_t)p * C + c0), uh);
+        unpack8(ldg8(out + obase + (int64_t)p * d.out_pitch + c0), o);
+        unpack8(ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0), dd);
+        const float g = s_gs[p];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          const float tt = ds * (s_g[c0 + i] * uh[i] + s_b[c0 + i]);
+          dgs += tt * s_gc[c0 + i];
+          acc[i] += tt * g;
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (p < HW && (t & (G - 1)) == 0) atomicAdd(&s_dq[p], dgs);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&s_dgc[c0 + i], acc[i]);
+    __syncthreads();
+    // ---- phase 2: dq, then the 3x3 transpose conv and the attention-conv weight gradient
+    if (t < HW) { const float g = s_gs[t]; s_dq[t] = s_dq[t] * g * (1.f - g); }
+    __syncthreads();
+    float part[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) part[i] = 0.f;
+    if (t < HW) {
+      const int py = t / W, px = t % W;
+      const float dq = s_dq[t];
+      float dmean = 0.f, dmax = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py - (ky - 1), xx = px - (kx - 1);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float dqq = s_dq[yy * W + xx];
+            dmean += s_w[ky * 3 + kx] * dqq;
+            dmax += s_w[9 + ky * 3 + kx] * dqq;
+          }
+          const int y2 = py + ky - 1, x2 = px + kx - 1;
+          if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            part[ky * 3 + kx] = dq * s_sa[2 * (y2 * W + x2)];
+            part[9 + ky * 3 + kx] = dq * s_sa[2 * (y2 * W + x2) + 1];
+          }
+        }
+      s_dmean[t] = dmean / (float)C;
+      s_dmax[t] = dmax;
+    }
+    if (t < SMALL_HW) {          // warps 0..3 hold all pixels
+#pragma unroll
+      for (int i = 0; i < 18; ++i) {
+        const float v = warp_sum(part[i]);
+        if (lane == 0) atomicAdd(&s_dw[i], v);
+      }
+    }
+    __syncthreads();
+    if (t < 18) atomicAdd(d.dwsp + t, s_dw[t]);
+  }
+
+  // ---- phase 3: S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u ; dres
+  {
+    float a1[8], a2[8], a3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1[i] = 0.f; a2[i] = 0.f; a3[i] = 0.f; }
+    for (int p = pl; p < HW; p += PL) {
+      float uh[8], o[8], dd[8], du[8], dsv[8], dspu[8];
+      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c0), uh);
+      unpack8(ldg8(out + obase + (int64_t)p * d.out_pitch + c0), o);
+      unpack8(ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0), dd);
+      nb_du8<true>(uh, o, dd, c0, s_g + c0, s_b + c0, s_gc + c0, has_cbam, res_mode, slope, s_gs[p], s_dmean[p], s_dmax[p],
+                   s_cidx[p], du, dsv, dspu);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a1[i] += du[i]; a2[i] += du[i] * uh[i]; a3[i] += dspu[i]; }
+      if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * d.dres_pitch + c0, pack8(dsv));
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&s_S1[c0 + i], a1[i]);
+      atomicAdd(&s_S2[c0 + i], a2[i]);
+      if (has_cbam) atomicAdd(&s_dgc[c0 + i], a3[i]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 4: channel-MLP backward, dgamma / dbeta, InstanceNorm-backward means
+  if (has_cbam) {
+    for (int c = t; c < C; c += 256) { const float gc = s_gc[c]; s_dv[c] = s_dgc[c] * gc * (1.f - gc); }
+    if (t < 64) s_dh[t] = 0.f;
+    __syncthreads();
+    for (int j = warp; j < Cr; j += 8) {
+      float pa = 0.f, pm = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float w = d.w1[(int64_t)j * C + c];
+        pa += w * s_b[c];
+        pm += w * q0[c * NC_W + NC_EXTU];
+      }
+      pa = warp_sum(pa); pm = warp_sum(pm);
+      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; }
+    }
+    mlp_cols_dot(d.w2, C, Cr, s_dv, s_dh);
+    __syncthreads();
+    for (int j = t; j < Cr; j += 256) {
+      float* hq = d.bwd_h + (int64_t)n * 192;
+      hq[j] = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[j], 0.f);
+      hq[64 + j] = s_ha[j] > 0.f ? s_dh[j] : 0.f;
+      hq[128 + j] = s_hm[j] > 0.f ? s_dh[j] : 0.f;
+    }
+  }
+  const float inv = 1.f / (float)HW;
+  for (int c = t; c < C; c += 256) {
+    float d_avg = 0.f, d_mx = 0.f;
+    if (has_cbam) {
+      for (int j = 0; j < Cr; ++j) {
+        const float w = d.w1[(int64_t)j * C + c];
+        if (s_ha[j] > 0.f) d_avg += w * s_dh[j];
+        if (s_hm[j] > 0.f) d_mx += w * s_dh[j];
+      }
+      d.bwd_nc[((int64_t)n * C + c) * BN_W + BN_DGC] = s_dv[c];      // consumed by nb_bwd_w_kernel
+    }
+    const float ext_uhat = q0[c * NC_W + NC_EXTUHAT];
+    const float S1 = s_S1[c] + d_mx;
+    const float S2 = s_S2[c] + d_mx * ext_uhat;
+    atomicAdd(d.dbeta + c, S1 + d_avg);
+    atomicAdd(d.dgamma + c, S2);
+    const float a = s_a[c];
+    s_dmx[c] = a * d_mx; s_m1[c] = a * S1 * inv; s_m2[c] = a * S2 * inv;
+  }
+  __syncthreads();
+
+  // ---- phase 5: dy = a*du + [p == argmax] a*d_mx - a*m1 - uhat*(a*m2)
+  for (int p = pl; p < HW; p += PL) {
+    float uh[8], o[8], dd[8], du[8], dsv[8], dspu[8], r[8];
+    unpack8(ldg8(uhat + ubase + (int64_t)p * C + c0), uh);
+    unpack8(ldg8(out + obase + (int64_t)p * d.out_pitch + c0), o);
+    unpack8(ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0), dd);
+    nb_du8<false>(uh, o, dd, c0, s_gc + c0, s_gc + c0, s_gc + c0, has_cbam, res_mode, slope, s_gs[p], s_dmean[p], s_dmax[p],
+                  s_cidx[p], du, dsv, dspu);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float extra = (p == s_idx[c0 + i]) ? s_dmx[c0 + i] : 0.f;
+      r[i] = s_a[c0 + i] * du[i] + extra - s_m1[c0 + i] - uh[i] * s_m2[c0 + i];
+    }
+    stg8(dy + ybase + (int64_t)p * d.dy_pitch + c0, pack8(r));
+  }
+}
+
+static bool nb_small_ok(const bvae_nb_desc* d) { return d->H * d->W <= SMALL_HW && d->C >= 32 && d->C <= 1024; }
+static size_t nb_small_fwd_smem(int C) { return (size_t)(8 * C) * 4 + (size_t)2 * C * 8 + SMALL_HW * (4 + 8 + 8 + 4) + (64 + 18 + 14) * 4; }
+static size_t nb_small_bwd_smem(int C) { return (size_t)(12 * C) * 4 + SMALL_HW * 7 * 4 + (3 * 64 + 18 + 18 + 12) * 4; }
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int pick_ppc(int HW, int N, int G) {
@@ -814,6 +1229,17 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   int rc = validate(d, "nb_forward");
   if (rc) return rc;
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  if (nb_small_ok(d)) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(nb_small_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_small_fwd_smem(1024));
+      cudaFuncSetAttribute(nb_small_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_small_fwd_smem(1024));
+      attr = true;
+    }
+    if (d->y_f32) nb_small_fwd_kernel<true><<<N, 256, nb_small_fwd_smem(C), st>>>(*d);
+    else nb_small_fwd_kernel<false><<<N, 256, nb_small_fwd_smem(C), st>>>(*d);
+    return check_launch("nb_small_fwd");
+  }
   const int64_t NC = (int64_t)N * C;
   // scratch layout inside d->stats: [NC] float2 | [NC] u64 max keys | [NC] u64 min keys
   float2* ss = (float2*)d->stats;
@@ -881,6 +1307,26 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   if (rc) return rc;
   BVAE_REQUIRE(d->dout_pitch % 8 == 0 && d->dy_pitch % 8 == 0, BVAE_ERR_ALIGN, "nb_backward: pitches % 8 != 0");
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  if (nb_small_ok(d)) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(nb_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nb_small_bwd_smem(1024));
+      attr = true;
+    }
+    nb_small_bwd_kernel<<<N, 256, nb_small_bwd_smem(C), st>>>(*d);
+    if ((rc = check_launch("nb_small_bwd"))) return rc;
+    if (d->has_cbam) {
+      int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
+      if (nsplit > N) nsplit = N;
+      if (nsplit > 32) nsplit = 32;
+      if (nsplit < 1) nsplit = 1;
+      const int npb = ceil_div(N, nsplit);
+      dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
+      nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
+      if ((rc = check_launch("nb_bwd_w"))) return rc;
+    }
+    return BVAE_OK;
+  }
   const int G = C / 8 < 32 ? C / 8 : 32;
   const int iters = C / (8 * G);
   const int ppc = pick_ppc(HW, N, G);
