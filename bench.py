@@ -127,6 +127,53 @@ def cpu_reference_arm(batch, steps, warmup):
     return batch / dt, dt, cores, torch.get_num_threads()
 
 
+def decode_bench(args, pkg, Model, dev, rank, world):
+    """BASELINE configs[4]: the maker_bar.py:32-44 sampling loop, S songs in lock-step per GPU (songs are independent,
+    so ranks need no collective).  One step = one 4-bar phrase: phrase encoder once, then 4 x (encoder + decoder)."""
+    import torch
+    import torch.distributed as dist
+    maker = importlib.import_module(PKG + ".maker_bar")
+    model = Model().to(dev).eval()
+    S = args.songs
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    def run(phrases):
+        lat = torch.randn(phrases * 4, S, 1152, device=dev, generator=g)
+        return maker.sample_songs(model, lat, phrases)
+
+    run(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pkg.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    roll = run(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    bars = S * 4 * args.steps * world
+    # algorithmic work per bar with the phrase feature cached per 4 bars (SURVEY.md section 8d): 5.3223 GFLOP
+    tf_peak, _, how = measured_peaks()
+    val = bars / (ms * 1e-3)
+    print(json.dumps({"metric": "decode_bars_per_sec", "value": val, "unit": "bars/s", "n_gpus": world,
+                      "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                      "config": {"workload": "maker_bar sampling loop, %d songs/GPU in lock-step, 4 bars per step, phrase "
+                                             "feature computed once per phrase, threshold 0.3 on device" % S,
+                                 "songs_per_gpu": S, "parallelism": "dp%d (independent songs, no collective)" % world},
+                      "gpu_launches": pkg.launch_count(), "tflops_end_to_end": 5.3223e9 * val / 1e12,
+                      "frac_of_tensor_peak": 5.3223e9 * val / 1e12 / tf_peak, "peak_source": how,
+                      "notes_on": float(roll.mean())}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,6 +184,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16, help="bars per step of the CPU arm (BASELINE configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--mode", default="train", choices=["train", "decode"],
+                    help="train = BASELINE configs[1] (the driver's default); decode = configs[4], maker_bar sampling")
+    ap.add_argument("--songs", type=int, default=8192, help="decode: songs generated in lock-step per GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -176,6 +226,8 @@ def main():
     B = args.batch
 
     torch.manual_seed(0)
+    if args.mode == "decode":
+        return decode_bench(args, pkg, Model, dev, rank, world)
     model = Model().to(dev).train()          # reference initialisation (graph/weights_initializer.py semantics)
     flat = model.flatten_parameters()
     reducer = None
@@ -268,6 +320,8 @@ def main():
         extra["adam_frac_of_hbm_peak"] = extra["adam_gbs"] / hbm_peak
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -282,6 +336,8 @@ def main():
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "extra": extra}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
