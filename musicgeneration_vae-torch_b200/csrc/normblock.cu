@@ -102,28 +102,60 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
   }
 }
 
-// ---- channel-attention MLP helpers: W2 is [C][Cr] row-major, so a row is read by the lanes of ONE warp (coalesced)
-// v[c] = sum_j W2[c][j] * h[j]
-__device__ __forceinline__ void mlp_rows_dot(const float* __restrict__ w2, int C, int Cr, const float* s_h, float* s_out) {
+// ---- channel-attention MLP helpers.  These run once per sample on weights that live in L2; what matters is how
+// many independent loads are in flight, not arithmetic.
+// h[j] = relu(W1[j,:] . a) + relu(W1[j,:] . m) (or the raw pre-activations): warp per hidden unit, every lane issues
+// its whole share of the row as independent 16-byte loads.  W1 is [Cr][C] row-major, C % 128 == 0 or C in {32, 64}.
+__device__ __forceinline__ void mlp_hidden(const float* __restrict__ w1, int C, int Cr, const float* s_a, const float* s_m,
+                                           float* s_pa, float* s_pm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int c = warp; c < C; c += nw) {
-    float p = 0.f;
-    for (int j = lane; j < Cr; j += 32) p += w2[(int64_t)c * Cr + j] * s_h[j];
-    p = warp_sum(p);
-    if (lane == 0) s_out[c] = p;
+  for (int j = warp; j < Cr; j += nw) {
+    const float* row = w1 + (int64_t)j * C;
+    float pa = 0.f, pm = 0.f;
+    if (C >= 128) {
+#pragma unroll 8
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + c));
+        pa += w.x * s_a[c] + w.y * s_a[c + 1] + w.z * s_a[c + 2] + w.w * s_a[c + 3];
+        pm += w.x * s_m[c] + w.y * s_m[c + 1] + w.z * s_m[c + 2] + w.w * s_m[c + 3];
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) { const float w = __ldg(row + c); pa += w * s_a[c]; pm += w * s_m[c]; }
+    }
+    pa = warp_sum(pa); pm = warp_sum(pm);
+    if (lane == 0) { s_pa[j] = pa; s_pm[j] = pm; }
   }
 }
-// dh[j] += sum_c W2[c][j] * dv[c]   (s_dh must be zero on entry; Cr <= 64)
+// v[c] = sum_j W2[c][j] * h[j]: one thread per row (Cr <= 64 floats = at most two full cache lines, all loads independent)
+__device__ __forceinline__ void mlp_rows_dot(const float* __restrict__ w2, int C, int Cr, const float* s_h, float* s_out) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float* row = w2 + (int64_t)c * Cr;
+    float v = 0.f;
+    if (Cr >= 4) {
+#pragma unroll 16
+      for (int j = 0; j < Cr; j += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + j));
+        v += w.x * s_h[j] + w.y * s_h[j + 1] + w.z * s_h[j + 2] + w.w * s_h[j + 3];
+      }
+    } else {
+      for (int j = 0; j < Cr; ++j) v += __ldg(row + j) * s_h[j];
+    }
+    s_out[c] = v;
+  }
+}
+// dh[j] += sum_c W2[c][j] * dv[c]   (s_dh must be zero on entry; Cr <= 64): lanes over j, warps over rows
 __device__ __forceinline__ void mlp_cols_dot(const float* __restrict__ w2, int C, int Cr, const float* s_dv, float* s_dh) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float a0 = 0.f, a1 = 0.f;
+  const bool l0 = lane < Cr, l1 = lane + 32 < Cr;
+#pragma unroll 8
   for (int c = warp; c < C; c += nw) {
     const float dv = s_dv[c];
-    if (lane < Cr) a0 += w2[(int64_t)c * Cr + lane] * dv;
-    if (lane + 32 < Cr) a1 += w2[(int64_t)c * Cr + lane + 32] * dv;
+    if (l0) a0 += __ldg(w2 + (int64_t)c * Cr + lane) * dv;
+    if (l1) a1 += __ldg(w2 + (int64_t)c * Cr + lane + 32) * dv;
   }
-  if (lane < Cr) atomicAdd(&s_dh[lane], a0);
-  if (lane + 32 < Cr) atomicAdd(&s_dh[lane + 32], a1);
+  if (l0) atomicAdd(&s_dh[lane], a0);
+  if (l1) atomicAdd(&s_dh[lane + 32], a1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -169,18 +201,10 @@ __global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y
   }
   if (!has_cbam) return;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int j = warp; j < Cr; j += 8) {
-    float pa = 0.f, pm = 0.f;
-    for (int c = lane; c < C; c += 32) {
-      const float w = w1[(int64_t)j * C + c];
-      pa += w * s_avg[c];
-      pm += w * s_mx[c];
-    }
-    pa = warp_sum(pa);
-    pm = warp_sum(pm);
-    if (lane == 0) s_h[j] = fmaxf(pa, 0.f) + fmaxf(pm, 0.f);   // W2 is linear: W2 ha + W2 hm = W2 (ha + hm)
-  }
+  float* s_pm = s_h + 64;
+  mlp_hidden(w1, C, Cr, s_avg, s_mx, s_h, s_pm);
+  __syncthreads();
+  if (threadIdx.x < Cr) s_h[threadIdx.x] = fmaxf(s_h[threadIdx.x], 0.f) + fmaxf(s_pm[threadIdx.x], 0.f);   // W2 is linear
   __syncthreads();
   mlp_rows_dot(w2, C, Cr, s_h, s_avg);            // s_avg is free now: reuse it for the pre-sigmoid gate
   __syncthreads();
@@ -645,16 +669,7 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
     }
     if (threadIdx.x < 64) s_dh[threadIdx.x] = 0.f;
     __syncthreads();
-    for (int j = warp; j < Cr; j += 8) {
-      float pa = 0.f, pm = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float w = w1[(int64_t)j * C + c];
-        pa += w * s_avg[c];
-        pm += w * s_mx[c];
-      }
-      pa = warp_sum(pa); pm = warp_sum(pm);
-      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; }
-    }
+    mlp_hidden(w1, C, Cr, s_avg, s_mx, s_ha, s_hm);
     mlp_cols_dot(w2, C, Cr, s_dv, s_dh);
     __syncthreads();
     // the weight gradients dW2[c][j] = sum_n dv[n,c] * (relu(ha)+relu(hm))[n,j] and
@@ -827,7 +842,7 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
   float* s_sa = (float*)(s_pkey + SMALL_HW);    // [128][2]
   float* s_gs = s_sa + 2 * SMALL_HW;            // [128]
   float* s_h = s_gs + SMALL_HW;                 // [64]
-  float* s_w = s_h + 64;                        // [18]
+  float* s_w = s_h + 64;                        // [18] attention conv weights, [32..96) MLP scratch
   const int n = blockIdx.x, t = threadIdx.x;
   const int cv = t % NV, pl = t / NV, c0 = cv * 8;
   const int G = NV < 32 ? NV : 32;              // lanes of a warp that share a pixel
@@ -895,16 +910,11 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
 
   // ---- phase B: channel-attention MLP (avg pool of an instance-normalised map is exactly beta)
   if (d.has_cbam) {
-    for (int j = warp; j < d.Cr; j += 8) {
-      float pa = 0.f, pm = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float w = d.w1[(int64_t)j * C + c];
-        pa += w * d.beta[c];
-        pm += w * s_mx[c];
-      }
-      pa = warp_sum(pa); pm = warp_sum(pm);
-      if (lane == 0) s_h[j] = fmaxf(pa, 0.f) + fmaxf(pm, 0.f);
-    }
+    for (int c = t; c < C; c += 256) s_sq[c] = d.beta[c];       // s_sq is free after phase A: the avg-pooled vector
+    __syncthreads();
+    mlp_hidden(d.w1, C, d.Cr, s_sq, s_mx, s_h, s_w + 32);
+    __syncthreads();
+    if (t < d.Cr) s_h[t] = fmaxf(s_h[t], 0.f) + fmaxf(s_w[32 + t], 0.f);
     __syncthreads();
     mlp_rows_dot(d.w2, C, d.Cr, s_h, s_sum);       // s_sum is free after phase A
     __syncthreads();
@@ -1129,16 +1139,9 @@ __global__ void __launch_bounds__(256) nb_small_bwd_kernel(const bvae_nb_desc d)
     for (int c = t; c < C; c += 256) { const float gc = s_gc[c]; s_dv[c] = s_dgc[c] * gc * (1.f - gc); }
     if (t < 64) s_dh[t] = 0.f;
     __syncthreads();
-    for (int j = warp; j < Cr; j += 8) {
-      float pa = 0.f, pm = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        const float w = d.w1[(int64_t)j * C + c];
-        pa += w * s_b[c];
-        pm += w * q0[c * NC_W + NC_EXTU];
-      }
-      pa = warp_sum(pa); pm = warp_sum(pm);
-      if (lane == 0) { s_ha[j] = pa; s_hm[j] = pm; }
-    }
+    for (int c = t; c < C; c += 256) s_m1[c] = q0[c * NC_W + NC_EXTU];      // s_m1 is written only after this phase
+    __syncthreads();
+    mlp_hidden(d.w1, C, Cr, s_b, s_m1, s_ha, s_hm);
     mlp_cols_dot(d.w2, C, Cr, s_dv, s_dh);
     __syncthreads();
     for (int j = t; j < Cr; j += 256) {
@@ -1187,7 +1190,7 @@ __global__ void __launch_bounds__(256) nb_small_bwd_kernel(const bvae_nb_desc d)
 }
 
 static bool nb_small_ok(const bvae_nb_desc* d) { return d->H * d->W <= SMALL_HW && d->C >= 32 && d->C <= 1024; }
-static size_t nb_small_fwd_smem(int C) { return (size_t)(8 * C) * 4 + (size_t)2 * C * 8 + SMALL_HW * (4 + 8 + 8 + 4) + (64 + 18 + 14) * 4; }
+static size_t nb_small_fwd_smem(int C) { return (size_t)(8 * C) * 4 + (size_t)2 * C * 8 + SMALL_HW * (4 + 8 + 8 + 4) + (64 + 96 + 16) * 4; }
 static size_t nb_small_bwd_smem(int C) { return (size_t)(12 * C) * 4 + SMALL_HW * 7 * 4 + (3 * 64 + 18 + 18 + 12) * 4; }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1259,7 +1262,7 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   else nb_stats_kernel<false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
   if ((rc = check_launch("nb_stats"))) return rc;
 
-  const size_t sm2 = (2 * C + 64) * sizeof(float);
+  const size_t sm2 = (2 * C + 128) * sizeof(float);
   if (d->y_f32)
     nb_coef_kernel<true><<<N, 256, sm2, st>>>(d->y, d->y_pitch, HW, C, ss, kmax, kmin, d->gamma, d->beta, d->eps,
                                               d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx);
