@@ -707,7 +707,8 @@ static void pick_box(int N, int QH, int QW, int cap, int* bw_, int* bh_, int* bn
       if (bn > N) bn = N;
       if (bn > 256) bn = 256;
       if (bn < 1) continue;
-      const long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, bn);
+      long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, bn);
+      if (cap == 64) tiles *= ceil_div(bw * bh * bn, 16);      // weight-gradient K chunks cost one MMA per 16 pixel rows
       if (best < 0 || tiles < best || (tiles == best && bw > bbw)) { best = tiles; bbw = bw; bbh = bh; bbn = bn; }
     }
   }
@@ -899,10 +900,20 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.Ca = d->Ca; P.Cs = d->Cs;
 
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
-  int splits = ceil_div(148 * 2, out_tiles);
+  // pixel splits: aim at ~2 waves of 148 CTAs and pick the candidate that fills its last wave best
   const int max_splits = ceil_div(P.nchunks, 8);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int splits = 1;
+  {
+    const int centre = ceil_div(148 * 2, out_tiles);
+    double best_fill = -1.0;
+    for (int sp = (centre > 3 ? centre - 2 : 1); sp <= centre + 2; ++sp) {
+      if (sp > max_splits) break;
+      const long ctas = (long)out_tiles * sp;
+      const long waves = (ctas + 147) / 148;
+      const double fill = (double)ctas / (double)(waves * 148);
+      if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
+    }
+  }
   P.chunks_per_split = ceil_div(P.nchunks, splits);
   P.splits = ceil_div(P.nchunks, P.chunks_per_split);
   // Reduction target.  Many pixel splits over a small weight (encoder front, decoder back): vector atomics into the
