@@ -2,6 +2,8 @@
 // All kernels are HBM-bound sweeps over NHWC tensors: a pixel's C channels are covered by G = min(32, C/8)
 // lanes doing 16-byte loads (ITERS = C/(8G) rounds), per-pixel reductions are warp shuffles inside the lane
 // group, per-(n,c) reductions go registers -> shuffle -> shared atomics -> one global atomic per CTA.
+#include <cooperative_groups.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace bvae {
@@ -1194,6 +1196,532 @@ static size_t nb_small_fwd_smem(int C) { return (size_t)(8 * C) * 4 + (size_t)2 
 static size_t nb_small_bwd_smem(int C) { return (size_t)(12 * C) * 4 + SMALL_HW * 7 * 4 + (3 * 64 + 18 + 18 + 12) * 4; }
 
 // ---------------------------------------------------------------------------------------------------
+// Cluster kernels: ONE thread-block cluster owns one sample (CL = 1 CTA for maps <= 128 pixels, 4 or 8 CTAs for the
+// large maps; CTA r owns the pixel slice [r*slice, (r+1)*slice)).  Every per-(n,c) reduction is a CTA-local shared
+// memory reduction followed by an all-reduce over the cluster's distributed shared memory, every phase boundary is a
+// cluster barrier instead of a kernel launch, and because the whole sample is swept by co-scheduled CTAs back to back
+// the 2nd and 3rd sweeps of the forward (and of the backward) hit L2 instead of HBM.
+// ---------------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int CLT = 256;   // threads per CTA
+
+__device__ __forceinline__ float cl_sum(cg::cluster_group& cl, float* s_arr, int c, int CLn) {
+  float v = 0.f;
+  for (int r = 0; r < CLn; ++r) v += cl.map_shared_rank(s_arr, r)[c];
+  return v;
+}
+__device__ __forceinline__ u64 cl_max(cg::cluster_group& cl, u64* s_arr, int c, int CLn) {
+  u64 v = 0;
+  for (int r = 0; r < CLn; ++r) { const u64 o = cl.map_shared_rank(s_arr, r)[c]; v = o > v ? o : v; }
+  return v;
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d, int CLn, int slice) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ float sm[];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV;
+  float* s_mean = sm; float* s_rstd = sm + C; float* s_a = sm + 2 * C; float* s_b = sm + 3 * C;
+  float* s_gc = sm + 4 * C; float* s_mx = sm + 5 * C; float* s_sum = sm + 6 * C; float* s_sq = sm + 7 * C;
+  u64* s_kmax = (u64*)(sm + 8 * C);
+  u64* s_kmin = s_kmax + C;
+  float* s_h = (float*)(s_kmin + C);            // [64]
+  float* s_t = s_h + 64;                        // [64]
+  float* s_w = s_t + 64;                        // [32]
+  u64* s_pkey = (u64*)(s_w + 32);               // [slice]
+  float* s_psum = (float*)(s_pkey + slice);     // [slice]
+  float* s_gs = s_psum + slice;                 // [slice]
+  const int rank = CLn > 1 ? (int)cl.block_rank() : 0;
+  const int n = blockIdx.x / CLn, t = threadIdx.x;
+  const int cv = t % NV, pl = t / NV, c0 = cv * 8;
+  const int G = NV < 32 ? NV : 32;
+  const int p_lo = rank * slice, p_hi = min(HW, p_lo + slice), np = max(0, p_hi - p_lo);
+  const int64_t ybase = (int64_t)n * HW * d.y_pitch, ubase = (int64_t)n * HW * C;
+  const int64_t obase = (int64_t)n * HW * d.out_pitch, rbase = (int64_t)n * HW * d.res_pitch;
+  bf16* uhat = (bf16*)d.uhat;
+  bf16* out = (bf16*)d.out;
+  const bf16* res = (const bf16*)d.res;
+
+  for (int c = t; c < C; c += CLT) { s_sum[c] = 0.f; s_sq[c] = 0.f; s_kmax[c] = 0; s_kmin[c] = 0; }
+  for (int i = t; i < slice; i += CLT) { s_psum[i] = 0.f; s_pkey[i] = 0; }
+  if (t < 18 && d.has_cbam) s_w[t] = d.wsp[t];
+  __syncthreads();
+
+  // ---- phase A: per-channel shifted sums and extrema over this CTA's pixel slice
+  {
+    float shift[8], sum[8], sq[8], vmx[8], vmn[8];
+    int imx[8], imn[8];
+    load8<F32>(d.y, ybase + c0, shift);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
+    for (int pb = p_lo + pl; pb < p_hi; pb += 4 * PL) {
+      float vv[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)                       // issue all loads of the batch before touching any of them
+        if (pb + u * PL < p_hi) load8<F32>(d.y, ybase + (int64_t)(pb + u * PL) * d.y_pitch + c0, vv[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = pb + u * PL;
+        if (p >= p_hi) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dl = vv[u][i] - shift[i];
+          sum[i] += dl; sq[i] += dl * dl;
+          if (vv[u][i] > vmx[i]) { vmx[i] = vv[u][i]; imx[i] = p; }
+          if (vv[u][i] < vmn[i]) { vmn[i] = vv[u][i]; imn[i] = p; }
+        }
+      }
+    }
+    // lanes of a warp with equal cv hold different pixel lanes: combine them first when NV < 32
+    for (int o = G; o < 32; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], o);
+        sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
+        const float ox = __shfl_xor_sync(0xffffffffu, vmx[i], o), on = __shfl_xor_sync(0xffffffffu, vmn[i], o);
+        const int oix = __shfl_xor_sync(0xffffffffu, imx[i], o), oin = __shfl_xor_sync(0xffffffffu, imn[i], o);
+        if (ox > vmx[i] || (ox == vmx[i] && oix < imx[i])) { vmx[i] = ox; imx[i] = oix; }
+        if (on < vmn[i] || (on == vmn[i] && oin < imn[i])) { vmn[i] = on; imn[i] = oin; }
+      }
+    }
+    if ((t & 31) < G) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_sum[c0 + i], sum[i]);
+        atomicAdd(&s_sq[c0 + i], sq[i]);
+        if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
+        if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
+      }
+    }
+  }
+  if (CLn > 1) cl.sync(); else __syncthreads();
+  const float inv = 1.f / (float)HW;
+  for (int c = t; c < C; c += CLT) {
+    const int64_t o = (int64_t)n * C + c;
+    const float shift = F32 ? ((const float*)d.y)[ybase + c] : bf2f(((const bf16*)d.y)[ybase + c]);
+    const float tsum = CLn > 1 ? cl_sum(cl, s_sum, c, CLn) : s_sum[c];
+    const float tsq = CLn > 1 ? cl_sum(cl, s_sq, c, CLn) : s_sq[c];
+    const u64 kx = CLn > 1 ? cl_max(cl, s_kmax, c, CLn) : s_kmax[c];
+    const u64 kn = CLn > 1 ? cl_max(cl, s_kmin, c, CLn) : s_kmin[c];
+    const float md = tsum * inv;
+    const float mean = shift + md;
+    const float var = fmaxf(tsq * inv - md * md, 0.f);
+    const float rstd = rsqrtf(var + d.eps);
+    const float g = d.gamma[c], b0 = d.beta[c];
+    const float a = g * rstd, b = b0 - mean * a;
+    float yext; uint32_t idx;
+    if (a >= 0.f) { yext = key_val(kx); idx = key_idx(kx); }
+    else { yext = -key_val(kn); idx = key_idx(kn); }
+    const float ext_uhat = (yext - mean) * rstd;
+    const float ext_u = g * ext_uhat + b0;
+    if (rank == 0) {
+      float* q = d.nc + o * NC_W;
+      q[NC_MEAN] = mean; q[NC_RSTD] = rstd; q[NC_A] = a; q[NC_B] = b;
+      q[NC_EXTU] = ext_u; q[NC_EXTUHAT] = ext_uhat; q[NC_GC] = 1.f; q[NC_SPARE] = 0.f;
+      d.nc_idx[o] = (int32_t)idx;
+    }
+    s_mean[c] = mean; s_rstd[c] = rstd; s_a[c] = a; s_b[c] = b; s_mx[c] = ext_u; s_gc[c] = 1.f;
+  }
+  // all remote reads of the partial arrays are done before any CTA of the cluster may overwrite them or exit
+  if (CLn > 1) cl.sync(); else __syncthreads();
+
+  // ---- phase B: channel-attention MLP (every CTA of the cluster computes it redundantly: C <= 256 there)
+  if (d.has_cbam) {
+    for (int c = t; c < C; c += CLT) s_sq[c] = d.beta[c];        // avg pool of an instance-normalised map == beta
+    __syncthreads();
+    mlp_hidden(d.w1, C, d.Cr, s_sq, s_mx, s_h, s_t);
+    __syncthreads();
+    if (t < d.Cr) s_h[t] = fmaxf(s_h[t], 0.f) + fmaxf(s_t[t], 0.f);
+    __syncthreads();
+    mlp_rows_dot(d.w2, C, d.Cr, s_h, s_sum);
+    __syncthreads();
+    for (int c = t; c < C; c += CLT) {
+      const float gc = 1.f / (1.f + expf(-s_sum[c]));
+      s_gc[c] = gc;
+      if (rank == 0) d.nc[((int64_t)n * C + c) * NC_W + NC_GC] = gc;
+    }
+    __syncthreads();
+  }
+
+  // ---- phase C: write uhat; per-pixel mean / max / argmax over channels of u*gc (or the final output without CBAM)
+#pragma unroll 2
+  for (int pb = 0; pb < np; pb += PL) {
+    const int lp = pb + pl, p = p_lo + lp;
+    const bool valid = lp < np;
+    float sum = 0.f, mx = -INFINITY;
+    int mxc = 0;
+    if (valid) {
+      float v[8], uh[8], o[8];
+      load8<F32>(d.y, ybase + (int64_t)p * d.y_pitch + c0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uh[i] = (v[i] - s_mean[c0 + i]) * s_rstd[c0 + i];
+        const float u = s_a[c0 + i] * v[i] + s_b[c0 + i];
+        const float u1 = u * s_gc[c0 + i];
+        sum += u1;
+        if (u1 > mx) { mx = u1; mxc = c0 + i; }
+        o[i] = act_fwd(u, d.slope);
+      }
+      stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
+      if (!d.has_cbam) stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
+    }
+    if (d.has_cbam) {
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+        const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+        if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+      }
+      if (valid && (t & (G - 1)) == 0) {
+        atomicAdd(&s_psum[lp], sum);
+        atomicMax(&s_pkey[lp], make_key(mx, (uint32_t)mxc));
+      }
+    }
+  }
+  if (!d.has_cbam) return;
+  __syncthreads();
+  for (int lp = t; lp < np; lp += CLT) {
+    const u64 k = s_pkey[lp];
+    const int64_t o = (int64_t)n * HW + p_lo + lp;
+    d.sa[o * 2] = s_psum[lp] / (float)C;
+    d.sa[o * 2 + 1] = key_val(k);
+    d.cidx[o] = (int32_t)key_idx(k);
+  }
+  if (CLn > 1) cl.sync(); else __syncthreads();      // the 3x3 gate conv reads the neighbouring slices' sa from global/L2
+  // ---- phase D: spatial gate for this slice
+  for (int lp = t; lp < np; lp += CLT) {
+    const int p = p_lo + lp;
+    const float g = 1.f / (1.f + expf(-sa_conv(d.sa + (int64_t)n * HW * 2, s_w, H, W, p / W, p % W)));
+    s_gs[lp] = g;
+    d.gs[(int64_t)n * HW + p] = g;
+  }
+  __syncthreads();
+  // ---- phase E: out = act(r + u*gc*gs)
+  for (int lb = pl; lb < np; lb += 4 * PL) {
+    float vv[4][8];
+    bf16x8 rr4[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int lp = lb + u * PL;
+      if (lp < np) {
+        load8<F32>(d.y, ybase + (int64_t)(p_lo + lp) * d.y_pitch + c0, vv[u]);
+        if (d.res_mode == 2) rr4[u] = ldg8(res + rbase + (int64_t)(p_lo + lp) * d.res_pitch + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int lp = lb + u * PL;
+      if (lp >= np) break;
+      const int p = p_lo + lp;
+      float r[8], o[8];
+      if (d.res_mode == 2) unpack8(rr4[u], r);
+      const float g = s_gs[lp];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float u_ = s_a[c0 + i] * vv[u][i] + s_b[c0 + i];
+        const float cb = u_ * s_gc[c0 + i] * g;
+        const float rr = d.res_mode == 1 ? u_ : (d.res_mode == 2 ? r[i] : 0.f);
+        o[i] = act_fwd(rr + cb, d.slope);
+      }
+      stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d, int CLn, int slice) {
+  cg::cluster_group cl = cg::this_cluster();
+  extern __shared__ float sm[];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV, Cr = d.Cr;
+  float* s_g = sm; float* s_b = sm + C; float* s_gc = sm + 2 * C; float* s_a = sm + 3 * C;
+  float* s_dgc = sm + 4 * C; float* s_S1 = sm + 5 * C; float* s_S2 = sm + 6 * C; float* s_dv = sm + 7 * C;
+  float* s_m1 = sm + 8 * C; float* s_m2 = sm + 9 * C; float* s_dmx = sm + 10 * C;
+  int* s_idx = (int*)(sm + 11 * C);
+  float* s_ha = sm + 12 * C;                    // [64]
+  float* s_hm = s_ha + 64; float* s_dh = s_hm + 64;
+  float* s_w = s_dh + 64;                       // [32]
+  float* s_dw = s_w + 32;                       // [32]
+  float* s_gs = s_dw + 32;                      // [slice]
+  float* s_dq = s_gs + slice;                   // [slice]  (dgs, then unused)
+  float* s_dmean = s_dq + slice;                // [slice]
+  float* s_dmax = s_dmean + slice;              // [slice]
+  int* s_cidx = (int*)(s_dmax + slice);         // [slice]
+  const int rank = CLn > 1 ? (int)cl.block_rank() : 0;
+  const int n = blockIdx.x / CLn, t = threadIdx.x;
+  const int cv = t % NV, pl = t / NV, c0 = cv * 8;
+  const int G = NV < 32 ? NV : 32;
+  const int lane = t & 31;
+  const int p_lo = rank * slice, p_hi = min(HW, p_lo + slice), np = max(0, p_hi - p_lo);
+  const int has_cbam = d.has_cbam, res_mode = d.res_mode;
+  const float slope = d.slope;
+  const bf16* dout = (const bf16*)d.dout; const bf16* out = (const bf16*)d.out; const bf16* uhat = (const bf16*)d.uhat;
+  bf16* dy = (bf16*)d.dy; bf16* dres = (bf16*)d.dres;
+  const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * d.out_pitch, dbase = (int64_t)n * HW * d.dout_pitch;
+  const int64_t ybase = (int64_t)n * HW * d.dy_pitch, rbase = (int64_t)n * HW * d.dres_pitch;
+  const float* q0 = d.nc + (int64_t)n * C * NC_W;
+  float* px_n = d.bwd_px + (int64_t)n * HW * BP_W;
+
+  for (int c = t; c < C; c += CLT) {
+    s_g[c] = d.gamma[c]; s_b[c] = d.beta[c];
+    s_gc[c] = q0[c * NC_W + NC_GC]; s_a[c] = q0[c * NC_W + NC_A];
+    s_dgc[c] = 0.f; s_S1[c] = 0.f; s_S2[c] = 0.f;
+    s_idx[c] = has_cbam ? d.nc_idx[(int64_t)n * C + c] : -1;
+  }
+  for (int lp = t; lp < slice; lp += CLT) {
+    const bool v = has_cbam && lp < np;
+    const int64_t o = (int64_t)n * HW + p_lo + lp;
+    s_gs[lp] = v ? d.gs[o] : 0.f;
+    s_cidx[lp] = v ? d.cidx[o] : -1;
+    s_dq[lp] = 0.f; s_dmean[lp] = 0.f; s_dmax[lp] = 0.f;
+  }
+  if (t < 32) { s_w[t] = (has_cbam && t < 18) ? d.wsp[t] : 0.f; s_dw[t] = 0.f; }
+  __syncthreads();
+
+  if (has_cbam) {
+    // ---- phase 1: dgs[p] = sum_c ds*u*gc (complete inside the CTA) ; dgc[c] += sum_p ds*u*gs (partial)
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int pb = 0; pb < np; pb += PL) {
+      const int lp = pb + pl, p = p_lo + lp;
+      float dgs = 0.f;
+      if (lp < np) {
+        float uh[8], o[8], dd[8];
+        unpack8(ldg8(uhat + ubase + (int64_t)p * C + c0), uh);
+        unpack8(ldg8(out + obase + (int64_t)p * d.out_pitch + c0), o);
+        unpack8(ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0), dd);
+        const float g = s_gs[lp];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          const float tt = ds * (s_g[c0 + i] * uh[i] + s_b[c0 + i]);
+          dgs += tt * s_gc[c0 + i];
+          acc[i] += tt * g;
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (lp < np && (t & (G - 1)) == 0) atomicAdd(&s_dq[lp], dgs);
+    }
+    for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (lane < G)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&s_dgc[c0 + i], acc[i]);
+    __syncthreads();
+    // dq for this slice -> global (the transpose conv below needs the neighbouring slices' values)
+    for (int lp = t; lp < np; lp += CLT) {
+      const float g = s_gs[lp];
+      px_n[(int64_t)(p_lo + lp) * BP_W + BP_DQ] = s_dq[lp] * g * (1.f - g);
+    }
+    if (CLn > 1) cl.sync(); else __syncthreads();
+    // ---- phase 2: 3x3 transpose conv of dq and the attention-conv weight gradient
+    float part[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) part[i] = 0.f;
+    const float* sa_n = d.sa + (int64_t)n * HW * 2;
+    for (int lp = t; lp < np; lp += CLT) {
+      const int p = p_lo + lp, py = p / W, px = p % W;
+      const float dq = px_n[(int64_t)p * BP_W + BP_DQ];
+      float dmean = 0.f, dmax = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py - (ky - 1), xx = px - (kx - 1);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float dqq = px_n[((int64_t)yy * W + xx) * BP_W + BP_DQ];
+            dmean += s_w[ky * 3 + kx] * dqq;
+            dmax += s_w[9 + ky * 3 + kx] * dqq;
+          }
+          const int y2 = py + ky - 1, x2 = px + kx - 1;
+          if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            const float2 v = *reinterpret_cast<const float2*>(sa_n + ((int64_t)y2 * W + x2) * 2);
+            part[ky * 3 + kx] += dq * v.x;
+            part[9 + ky * 3 + kx] += dq * v.y;
+          }
+        }
+      s_dmean[lp] = dmean / (float)C;
+      s_dmax[lp] = dmax;
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float v = warp_sum(part[i]);
+      if (lane == 0 && v != 0.f) atomicAdd(&s_dw[i], v);
+    }
+    __syncthreads();
+    if (t < 18) atomicAdd(d.dwsp + t, s_dw[t]);
+  }
+
+  // ---- phase 3: S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u (partials over this slice) ; dres
+  {
+    float a1[8], a2[8], a3[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a1[i] = 0.f; a2[i] = 0.f; a3[i] = 0.f; }
+    for (int lb = pl; lb < np; lb += 2 * PL) {
+      bf16x8 ru[2], ro[2], rd[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int lp = lb + u * PL;
+        if (lp < np) {
+          const int p = p_lo + lp;
+          ru[u] = ldg8(uhat + ubase + (int64_t)p * C + c0);
+          ro[u] = ldg8(out + obase + (int64_t)p * d.out_pitch + c0);
+          rd[u] = ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int lp = lb + u * PL;
+        if (lp >= np) break;
+        const int p = p_lo + lp;
+        float uh[8], o[8], dd[8], du[8], dsv[8], dspu[8];
+        unpack8(ru[u], uh); unpack8(ro[u], o); unpack8(rd[u], dd);
+        nb_du8<true>(uh, o, dd, c0, s_g + c0, s_b + c0, s_gc + c0, has_cbam, res_mode, slope, s_gs[lp], s_dmean[lp],
+                     s_dmax[lp], s_cidx[lp], du, dsv, dspu);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { a1[i] += du[i]; a2[i] += du[i] * uh[i]; a3[i] += dspu[i]; }
+        if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * d.dres_pitch + c0, pack8(dsv));
+      }
+    }
+    for (int o = G; o < 32; o <<= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a1[i] += __shfl_xor_sync(0xffffffffu, a1[i], o);
+        a2[i] += __shfl_xor_sync(0xffffffffu, a2[i], o);
+        a3[i] += __shfl_xor_sync(0xffffffffu, a3[i], o);
+      }
+    if (lane < G)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_S1[c0 + i], a1[i]);
+        atomicAdd(&s_S2[c0 + i], a2[i]);
+        if (has_cbam) atomicAdd(&s_dgc[c0 + i], a3[i]);
+      }
+  }
+  if (CLn > 1) cl.sync(); else __syncthreads();
+
+  // ---- phase 4: cluster all-reduce of (dgc, S1, S2); channel-MLP backward; dgamma / dbeta; InstanceNorm means
+  for (int c = t; c < C; c += CLT) {
+    const float gc = s_gc[c];
+    const float dgc = CLn > 1 ? cl_sum(cl, s_dgc, c, CLn) : s_dgc[c];
+    s_dv[c] = has_cbam ? dgc * gc * (1.f - gc) : 0.f;
+    s_m1[c] = CLn > 1 ? cl_sum(cl, s_S1, c, CLn) : s_S1[c];       // totals, turned into the means below
+    s_m2[c] = CLn > 1 ? cl_sum(cl, s_S2, c, CLn) : s_S2[c];
+    s_dmx[c] = q0[c * NC_W + NC_EXTU];                             // staging: max-pooled u for the hidden layer
+  }
+  if (t < 64) s_dh[t] = 0.f;
+  if (CLn > 1) cl.sync(); else __syncthreads();                    // remote reads done; partial arrays may be reused
+  if (has_cbam) {
+    mlp_hidden(d.w1, C, Cr, s_b, s_dmx, s_ha, s_hm);
+    mlp_cols_dot(d.w2, C, Cr, s_dv, s_dh);
+    __syncthreads();
+    if (rank == 0)
+      for (int j = t; j < Cr; j += CLT) {
+        float* hq = d.bwd_h + (int64_t)n * 192;
+        hq[j] = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[j], 0.f);
+        hq[64 + j] = s_ha[j] > 0.f ? s_dh[j] : 0.f;
+        hq[128 + j] = s_hm[j] > 0.f ? s_dh[j] : 0.f;
+      }
+  }
+  const float inv = 1.f / (float)HW;
+  for (int c = t; c < C; c += CLT) {
+    float d_avg = 0.f, d_mx = 0.f;
+    if (has_cbam) {
+#pragma unroll 8
+      for (int j = 0; j < Cr; ++j) {
+        const float w = __ldg(d.w1 + (int64_t)j * C + c);
+        if (s_ha[j] > 0.f) d_avg += w * s_dh[j];
+        if (s_hm[j] > 0.f) d_mx += w * s_dh[j];
+      }
+      if (rank == 0) d.bwd_nc[((int64_t)n * C + c) * BN_W + BN_DGC] = s_dv[c];      // consumed by nb_bwd_w_kernel
+    }
+    const float ext_uhat = q0[c * NC_W + NC_EXTUHAT];
+    const float S1 = s_m1[c] + d_mx;
+    const float S2 = s_m2[c] + d_mx * ext_uhat;
+    if (rank == 0) {
+      atomicAdd(d.dbeta + c, S1 + d_avg);
+      atomicAdd(d.dgamma + c, S2);
+    }
+    const float a = s_a[c];
+    s_dmx[c] = a * d_mx; s_m1[c] = a * S1 * inv; s_m2[c] = a * S2 * inv;
+  }
+  __syncthreads();
+
+  // ---- phase 5: dy = a*du + [p == argmax] a*d_mx - a*m1 - uhat*(a*m2)
+  for (int lb = pl; lb < np; lb += 2 * PL) {
+    bf16x8 ru[2], ro[2], rd[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int lp = lb + u * PL;
+      if (lp < np) {
+        const int p = p_lo + lp;
+        ru[u] = ldg8(uhat + ubase + (int64_t)p * C + c0);
+        ro[u] = ldg8(out + obase + (int64_t)p * d.out_pitch + c0);
+        rd[u] = ldg8(dout + dbase + (int64_t)p * d.dout_pitch + c0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int lp = lb + u * PL;
+      if (lp >= np) break;
+      const int p = p_lo + lp;
+      float uh[8], o[8], dd[8], du[8], dsv[8], dspu[8], r[8];
+      unpack8(ru[u], uh); unpack8(ro[u], o); unpack8(rd[u], dd);
+      nb_du8<false>(uh, o, dd, c0, s_gc + c0, s_gc + c0, s_gc + c0, has_cbam, res_mode, slope, s_gs[lp], s_dmean[lp],
+                    s_dmax[lp], s_cidx[lp], du, dsv, dspu);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float extra = (p == s_idx[c0 + i]) ? s_dmx[c0 + i] : 0.f;
+        r[i] = s_a[c0 + i] * du[i] + extra - s_m1[c0 + i] - uh[i] * s_m2[c0 + i];
+      }
+      stg8(dy + ybase + (int64_t)p * d.dy_pitch + c0, pack8(r));
+    }
+  }
+}
+
+static void nb_cl_geometry(const bvae_nb_desc* d, int* CLn, int* slice) {
+  const int HW = d->H * d->W;
+  const int cl = HW <= 128 ? 1 : (HW <= 1440 ? 4 : (HW <= 2880 ? 8 : 16));
+  *CLn = cl;
+  *slice = ceil_div(HW, cl);
+}
+static size_t nb_cl_fwd_smem(int C, int slice) { return (size_t)(8 * C) * 4 + (size_t)2 * C * 8 + (64 + 64 + 32) * 4 + (size_t)slice * (8 + 4 + 4) + 64; }
+static size_t nb_cl_bwd_smem(int C, int slice) { return (size_t)(12 * C) * 4 + (3 * 64 + 32 + 32) * 4 + (size_t)slice * 5 * 4 + 64; }
+
+template <typename K>
+static int nb_cl_launch(K kernel, const bvae_nb_desc* d, size_t smem, cudaStream_t st, const char* what) {
+  int CLn, slice;
+  nb_cl_geometry(d, &CLn, &slice);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(d->N * CLn));
+  cfg.blockDim = dim3(CLT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLn; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, *d, CLn, slice);
+  if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return BVAE_ERR_CUDA; }
+  return check_launch(what);
+}
+
+// BVAE_NB_MODE: 0 (default) = cluster kernel for maps <= 128 pixels (one CTA per sample), tiled kernels otherwise;
+//               1 = cluster kernels everywhere (4..16 CTAs per sample; halves HBM traffic but is latency bound:
+//                   measured 1.2-1.5x slower than the tiled kernels on the 96x60 maps);  2 = tiled / nb_small only.
+static int nb_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_NB_MODE"); v = e ? atoi(e) : 0; }
+  return v;
+}
+static bool use_nb_cluster(const bvae_nb_desc* d) {
+  const int m = nb_mode();
+  return m == 1 || (m == 0 && d->H * d->W <= 128);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int pick_ppc(int HW, int N, int G) {
@@ -1232,6 +1760,21 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   int rc = validate(d, "nb_forward");
   if (rc) return rc;
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  if (use_nb_cluster(d)) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(nb_cl_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(nb_cl_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(nb_cl_fwd_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaFuncSetAttribute(nb_cl_fwd_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      attr = true;
+    }
+    int CLn, slice;
+    nb_cl_geometry(d, &CLn, &slice);
+    const size_t smem = nb_cl_fwd_smem(C, slice);
+    if (d->y_f32) return nb_cl_launch(nb_cl_fwd_kernel<true>, d, smem, st, "nb_cl_fwd");
+    return nb_cl_launch(nb_cl_fwd_kernel<false>, d, smem, st, "nb_cl_fwd");
+  }
   if (nb_small_ok(d)) {
     static bool attr = false;
     if (!attr) {
@@ -1310,6 +1853,28 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   if (rc) return rc;
   BVAE_REQUIRE(d->dout_pitch % 8 == 0 && d->dy_pitch % 8 == 0, BVAE_ERR_ALIGN, "nb_backward: pitches % 8 != 0");
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  if (use_nb_cluster(d)) {
+    static bool attr = false;
+    if (!attr) {
+      cudaFuncSetAttribute(nb_cl_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      cudaFuncSetAttribute(nb_cl_bwd_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      attr = true;
+    }
+    int CLn, slice;
+    nb_cl_geometry(d, &CLn, &slice);
+    if ((rc = nb_cl_launch(nb_cl_bwd_kernel, d, nb_cl_bwd_smem(C, slice), st, "nb_cl_bwd"))) return rc;
+    if (d->has_cbam) {
+      int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
+      if (nsplit > N) nsplit = N;
+      if (nsplit > 32) nsplit = 32;
+      if (nsplit < 1) nsplit = 1;
+      const int npb = ceil_div(N, nsplit);
+      dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
+      nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
+      if ((rc = check_launch("nb_bwd_w"))) return rc;
+    }
+    return BVAE_OK;
+  }
   if (nb_small_ok(d)) {
     static bool attr = false;
     if (!attr) {
