@@ -68,6 +68,10 @@ typedef struct bvae_conv_desc {
   const float* bias; /* [Cout] or NULL */
   const void* addend; /* same geometry/dtype as y (pitch add_pitch) or NULL: out += addend */
   const void* mask;  /* bf16, same geometry as y (pitch mask_pitch) or NULL: out *= (mask > 0 ? 1 : mask_slope) */
+  void* stats;       /* optional, 24*N*Cout bytes, zero before the first phase: the epilogue accumulates the
+                        InstanceNorm statistics of the output -- double sum[N*Cout], double sumsq[N*Cout],
+                        uint32 max key[N*Cout], uint32 min key[N*Cout] (order-preserving float keys) -- so that
+                        bvae_nb_forward (stats_fused = 1) needs no statistics pass; see bvae_conv_stats_ok */
   int32_t N, H, W, C, x_pitch;
   int32_t Cout, w_pitch;
   int32_t ntaps;
@@ -83,6 +87,9 @@ typedef struct bvae_conv_desc {
 } bvae_conv_desc;
 
 int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream);
+/* 1 if bvae_conv_gemm(d, BVAE_IMPL_AUTO) can fuse the statistics (tcgen05 path, fp32 output, every M tile inside one
+ * sample) */
+int bvae_conv_stats_ok(const bvae_conv_desc* d);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Weight gradient of the same contractions:
@@ -131,6 +138,7 @@ typedef struct bvae_nb_desc {
   int32_t y_pitch, out_pitch, res_pitch, dout_pitch, dy_pitch, dres_pitch;
   int32_t has_cbam, Cr, res_mode; /* res_mode: 0 u | 1 u + cbam(u) | 2 res + cbam(u) | 3 cbam(u) */
   int32_t y_f32;        /* raw conv output dtype: 1 = fp32 (default: survives |mean| >> std), 0 = bf16 */
+  int32_t stats_fused;  /* 1: `stats` was filled by bvae_conv_gemm's epilogue (see bvae_conv_desc.stats) */
   float slope, eps;
   const void* y;        /* raw conv output [N,H,W,C] (forward only; not needed by backward) */
   void* uhat;           /* bf16 [N,H,W,C] dense: normalised activations, saved for backward */

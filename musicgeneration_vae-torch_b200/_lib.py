@@ -21,6 +21,7 @@ c_i32, c_f32, c_vp, c_i64 = C.c_int32, C.c_float, C.c_void_p, C.c_int64
 class ConvDesc(C.Structure):
     """struct bvae_conv_desc (include/barvae.h)."""
     _fields_ = [("x", c_vp), ("w", c_vp), ("y", c_vp), ("bias", c_vp), ("addend", c_vp), ("mask", c_vp),
+                ("stats", c_vp),
                 ("N", c_i32), ("H", c_i32), ("W", c_i32), ("C", c_i32), ("x_pitch", c_i32),
                 ("Cout", c_i32), ("w_pitch", c_i32), ("ntaps", c_i32),
                 ("dy", c_i32 * MAX_TAPS), ("dx", c_i32 * MAX_TAPS),
@@ -46,7 +47,7 @@ class NbDesc(C.Structure):
                 ("y_pitch", c_i32), ("out_pitch", c_i32), ("res_pitch", c_i32), ("dout_pitch", c_i32),
                 ("dy_pitch", c_i32), ("dres_pitch", c_i32),
                 ("has_cbam", c_i32), ("Cr", c_i32), ("res_mode", c_i32), ("y_f32", c_i32),
-                ("slope", c_f32), ("eps", c_f32),
+                ("stats_fused", c_i32), ("slope", c_f32), ("eps", c_f32),
                 ("y", c_vp), ("uhat", c_vp), ("out", c_vp), ("stats", c_vp), ("res", c_vp),
                 ("gamma", c_vp), ("beta", c_vp), ("w1", c_vp), ("w2", c_vp), ("wsp", c_vp),
                 ("nc", c_vp), ("nc_idx", c_vp), ("sa", c_vp), ("cidx", c_vp), ("gs", c_vp),
@@ -66,6 +67,7 @@ SYMBOLS = [
     ("bvae_launch_count_reset", None, []),
     ("bvae_device_ok", C.c_int, []),
     ("bvae_conv_gemm", C.c_int, [C.POINTER(ConvDesc), C.c_int, c_vp]),
+    ("bvae_conv_stats_ok", C.c_int, [C.POINTER(ConvDesc)]),
     ("bvae_wgrad_gemm", C.c_int, [C.POINTER(WgradDesc), C.c_int, c_vp]),
     ("bvae_pack_weight", C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.POINTER(c_i32), C.c_int,
                                    c_vp]),

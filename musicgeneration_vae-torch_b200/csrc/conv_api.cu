@@ -6,6 +6,7 @@ int conv_simt_launch(const bvae_conv_desc* d, cudaStream_t stream);
 int wgrad_simt_launch(const bvae_wgrad_desc* d, cudaStream_t stream);
 int conv_tc_eligible(const bvae_conv_desc* d);
 int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream);
+int conv_tc_stats_ok(const bvae_conv_desc* d);
 int wgrad_tc_eligible(const bvae_wgrad_desc* d);
 int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream);
 int stem_fwd_eligible(const bvae_conv_desc* d);
@@ -24,6 +25,8 @@ extern "C" int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream) {
   BVAE_REQUIRE((d->QH - 1) * d->osy + d->ooy < d->OH && (d->QW - 1) * d->osx + d->oox < d->OW, BVAE_ERR_SHAPE,
                "conv_gemm: phase grid exceeds the output tensor");
   BVAE_REQUIRE(d->w_pitch >= d->ntaps * d->C, BVAE_ERR_SHAPE, "conv_gemm: w_pitch too small");
+  BVAE_REQUIRE(!d->stats || (impl != BVAE_IMPL_SIMT && conv_tc_stats_ok(d)), BVAE_ERR_UNSUPPORTED,
+               "conv_gemm: statistics fusion is not available for this problem (check bvae_conv_stats_ok)");
   if (impl == BVAE_IMPL_SIMT) return conv_simt_launch(d, (cudaStream_t)stream);
   if (impl == BVAE_IMPL_AUTO && stem_fwd_eligible(d)) return stem_fwd_launch(d, (cudaStream_t)stream);
   const int ok = conv_tc_eligible(d);
@@ -33,6 +36,8 @@ extern "C" int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream) {
   }
   return ok ? conv_tc_launch(d, (cudaStream_t)stream) : conv_simt_launch(d, (cudaStream_t)stream);
 }
+
+extern "C" int bvae_conv_stats_ok(const bvae_conv_desc* d) { return d && conv_tc_stats_ok(d); }
 
 extern "C" int bvae_wgrad_gemm(const bvae_wgrad_desc* d, int impl, void* stream) {
   BVAE_REQUIRE(d && d->a && d->s && d->dw, BVAE_ERR_SHAPE, "wgrad_gemm: null pointer");

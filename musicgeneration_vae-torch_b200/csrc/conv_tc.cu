@@ -133,9 +133,28 @@ struct alignas(64) ConvTcParams {
   const float* bias;
   const void* addend;
   const void* mask;
+  void* stats;                      // fused InstanceNorm statistics (see bvae_conv_desc.stats) or null
   int OH, OW, y_pitch, osy, osx, ooy, oox, add_pitch, mask_pitch, act, out_f32;
   float slope, mask_slope;
 };
+
+// Column reduction over the 32 rows a warp holds (one row per lane, 32 columns per lane): butterfly in which every
+// step halves the number of columns a lane is responsible for; after 5 steps lane l holds the result of column l.
+template <typename Op>
+__device__ __forceinline__ float warp_col_reduce(float (&v)[32], Op op) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float mine = up ? v[i + s] : v[i];
+      const float other = up ? v[i] : v[i + s];
+      v[i] = op(mine, __shfl_xor_sync(0xffffffffu, other, s));
+    }
+  }
+  return v[0];
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // forward / dgrad kernel.  128 threads: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
@@ -399,6 +418,46 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);
+        if (p.stats) {
+          // raw fp32 output in front of an InstanceNorm: store it and reduce this warp's 32 rows per column
+          // (sum, sum of squares, max, min) -> one double / key atomic per column; the tile lies inside sample tn
+          float f[32], g[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+          }
+          if (valid) {
+            float* yp = (float*)p.y + opix * p.y_pitch + col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(yp + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = valid ? f[i] : 0.f;
+          const float s1 = warp_col_reduce(g, [](float a, float b) { return a + b; });
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = valid ? f[i] * f[i] : 0.f;
+          const float s2 = warp_col_reduce(g, [](float a, float b) { return a + b; });
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = valid ? f[i] : -INFINITY;
+          const float mx = warp_col_reduce(g, [](float a, float b) { return fmaxf(a, b); });
+#pragma unroll
+          for (int i = 0; i < 32; ++i) g[i] = valid ? -f[i] : -INFINITY;
+          const float mn = warp_col_reduce(g, [](float a, float b) { return fmaxf(a, b); });     // max of -x
+          const long long NC = (long long)p.N * p.Cout;
+          const long long o = (long long)tn * p.Cout + col0 + c0 + lane;
+          double* sd = (double*)p.stats;
+          atomicAdd(sd + o, (double)s1);
+          atomicAdd(sd + NC + o, (double)s2);
+          uint32_t* kk = (uint32_t*)(sd + 2 * NC);
+          atomicMax(kk + o, f2ord(mx));
+          atomicMax(kk + NC + o, f2ord(mn));
+          continue;
+        }
         if (!valid) continue;
         float f[32];
 #pragma unroll
@@ -683,6 +742,12 @@ static int make_w_map(CUtensorMap* m, const void* base, int K, int rows, int pit
   return BVAE_OK;
 }
 
+static bool use_conv_v1_flag() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // choose the pixel box (bn, bh, bw) with bn*bh*bw <= cap that needs the fewest boxes to cover [N, QH, QW]
@@ -709,7 +774,8 @@ static void pick_box(int N, int QH, int QW, int cap, int* bw_, int* bh_, int* bn
       if (bn < 1) continue;
       long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, bn);
       if (cap == 64) tiles *= ceil_div(bw * bh * bn, 16);      // weight-gradient K chunks cost one MMA per 16 pixel rows
-      if (best < 0 || tiles < best || (tiles == best && bw > bbw)) { best = tiles; bbw = bw; bbh = bh; bbn = bn; }
+      // ties: wider rows first, then boxes that stay inside one sample (needed by the fused statistics)
+      if (best < 0 || tiles < best || (tiles == best && (bw > bbw || (bw == bbw && bn < bbn)))) { best = tiles; bbw = bw; bbh = bh; bbn = bn; }
     }
   }
   *bw_ = bbw; *bh_ = bbh; *bn_ = bbn;
@@ -758,6 +824,13 @@ int conv_tc_eligible(const bvae_conv_desc* d) {
   ViewPlan vp;
   if (!plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp)) return 0;
   return pick_bn(d->Cout) != 0;
+}
+
+int conv_tc_stats_ok(const bvae_conv_desc* d) {
+  if (use_conv_v1_flag() || !conv_tc_eligible(d) || !d->out_f32 || d->act || d->addend || d->mask) return 0;
+  int bw, bh, bn;
+  pick_box(d->N, d->QH, d->QW, 128, &bw, &bh, &bn);
+  return bn == 1;
 }
 
 template <int KB, int BN, int STAGES>
@@ -824,7 +897,7 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   P.tiles_w = ceil_div(d->QW, P.bw); P.tiles_h = ceil_div(d->QH, P.bh); P.tiles_n = ceil_div(d->N, P.bn);
   P.n_tiles = d->Cout / BN;
   P.N = d->N; P.QH = d->QH; P.QW = d->QW; P.Cout = d->Cout;
-  P.y = d->y; P.bias = d->bias; P.addend = d->addend; P.mask = d->mask;
+  P.y = d->y; P.bias = d->bias; P.addend = d->addend; P.mask = d->mask; P.stats = d->stats;
   P.OH = d->OH; P.OW = d->OW; P.y_pitch = d->y_pitch; P.osy = d->osy; P.osx = d->osx; P.ooy = d->ooy; P.oox = d->oox;
   P.add_pitch = d->add_pitch; P.mask_pitch = d->mask_pitch; P.act = d->act; P.out_f32 = d->out_f32;
   P.slope = d->slope; P.mask_slope = d->mask_slope;

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y
                                                       const float* __restrict__ beta, float eps, int has_cbam,
                                                       int Cr, const float* __restrict__ w1,
                                                       const float* __restrict__ w2, float* __restrict__ nc,
-                                                      int32_t* __restrict__ nc_idx) {
+                                                      int32_t* __restrict__ nc_idx, int fused, int N) {
   extern __shared__ float sm[];
   float* s_avg = sm;          // [C]
   float* s_mx = sm + C;       // [C]
@@ -181,22 +181,36 @@ __global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y
   const float inv = 1.f / (float)HW;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int64_t o = (int64_t)n * C + c;
-    const float shift = F32 ? ((const float*)y)[base + c] : bf2f(((const bf16*)y)[base + c]);
-    const float2 s = ss[o];
-    const float md = s.x * inv;
-    const float mean = shift + md;
-    const float var = fmaxf(s.y * inv - md * md, 0.f);
-    const float rstd = rsqrtf(var + eps);
+    float mean, rstd, yext;
+    uint32_t idx;
     const float g = gamma[c], b0 = beta[c];
+    if (fused) {
+      // statistics accumulated by the convolution epilogue: double sum / sumsq, order-preserving max / min keys
+      const int64_t NCt = (int64_t)N * C;
+      const double* sd = (const double*)ss;
+      const double m = sd[o] * (double)inv;
+      const double var = fmax(sd[NCt + o] * (double)inv - m * m, 0.0);
+      mean = (float)m;
+      rstd = rsqrtf((float)var + eps);
+      const uint32_t* kk = (const uint32_t*)(sd + 2 * NCt);
+      yext = (g * rstd >= 0.f) ? ord2f(kk[o]) : -ord2f(kk[NCt + o]);
+      idx = 0x7fffffffu;            // recovered by nb_pool (first pixel whose value equals yext)
+    } else {
+      const float shift = F32 ? ((const float*)y)[base + c] : bf2f(((const bf16*)y)[base + c]);
+      const float2 s = ss[o];
+      const float md = s.x * inv;
+      mean = shift + md;
+      const float var = fmaxf(s.y * inv - md * md, 0.f);
+      rstd = rsqrtf(var + eps);
+      if (g * rstd >= 0.f) { const u64 k = kmax[o]; yext = key_val(k); idx = key_idx(k); }
+      else { const u64 k = kmin[o]; yext = -key_val(k); idx = key_idx(k); }
+    }
     const float a = g * rstd, b = b0 - mean * a;
-    float yext; uint32_t idx;
-    if (a >= 0.f) { const u64 k = kmax[o]; yext = key_val(k); idx = key_idx(k); }
-    else { const u64 k = kmin[o]; yext = -key_val(k); idx = key_idx(k); }
     const float ext_uhat = (yext - mean) * rstd;
     const float ext_u = g * ext_uhat + b0;
     float* q = nc + o * NC_W;
     q[NC_MEAN] = mean; q[NC_RSTD] = rstd; q[NC_A] = a; q[NC_B] = b;
-    q[NC_EXTU] = ext_u; q[NC_EXTUHAT] = ext_uhat; q[NC_GC] = 1.f; q[NC_SPARE] = 0.f;
+    q[NC_EXTU] = ext_u; q[NC_EXTUHAT] = ext_uhat; q[NC_GC] = 1.f; q[NC_SPARE] = yext;
     nc_idx[o] = (int32_t)idx;
     s_avg[c] = b0;      // mean over H*W of an instance-normalised map is exactly beta
     s_mx[c] = ext_u;
@@ -223,13 +237,16 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
                                                       const float* __restrict__ nc, int has_cbam, float slope,
                                                       bf16* __restrict__ uhat, bf16* __restrict__ out,
                                                       int out_pitch, float* __restrict__ sa,
-                                                      int32_t* __restrict__ cidx, int ppc) {
+                                                      int32_t* __restrict__ cidx, int ppc, int fused,
+                                                      int32_t* __restrict__ nc_idx) {
   extern __shared__ float sm[];
   float* s_mean = sm; float* s_rstd = sm + C; float* s_a = sm + 2 * C; float* s_b = sm + 3 * C; float* s_gc = sm + 4 * C;
+  float* s_yext = sm + 5 * C;      // raw value of the max-pooled element (fused statistics: its pixel index is found here)
   const int n = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* q = nc + ((int64_t)n * C + c) * NC_W;
     s_mean[c] = q[NC_MEAN]; s_rstd[c] = q[NC_RSTD]; s_a[c] = q[NC_A]; s_b[c] = q[NC_B]; s_gc[c] = q[NC_GC];
+    s_yext[c] = q[NC_SPARE];
   }
   __syncthreads();
   const int G = min(32, C / 8);
@@ -272,6 +289,12 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
         for (int i = 0; i < 8; ++i) uh[i] = (v[i] - p_mean[i]) * p_rstd[i];
         stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
         if (has_cbam) {
+          if (fused) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (v[i] == s_yext[c + i] && p < nc_idx[(int64_t)n * C + c + i])            // (a stale read only costs an atomic)
+                atomicMin(&nc_idx[(int64_t)n * C + c + i], p);                              // first index wins
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float u1 = (p_a[i] * v[i] + p_b[i]) * p_gc[i];
@@ -1760,6 +1783,8 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   int rc = validate(d, "nb_forward");
   if (rc) return rc;
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  BVAE_REQUIRE(!d->stats_fused || !(use_nb_cluster(d) || nb_small_ok(d)), BVAE_ERR_UNSUPPORTED,
+               "nb_forward: fused statistics are only consumed by the tiled path (H*W > 128)");
   if (use_nb_cluster(d)) {
     static bool attr = false;
     if (!attr) {
@@ -1787,45 +1812,50 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
     return check_launch("nb_small_fwd");
   }
   const int64_t NC = (int64_t)N * C;
-  // scratch layout inside d->stats: [NC] float2 | [NC] u64 max keys | [NC] u64 min keys
+  // scratch layout inside d->stats: [NC] float2 | [NC] u64 max keys | [NC] u64 min keys   (own statistics pass), or
+  //                                 [NC] double sum | [NC] double sumsq | [NC] u32 max | [NC] u32 min  (stats_fused)
   float2* ss = (float2*)d->stats;
   u64* kmax = (u64*)(ss + NC);
   u64* kmin = kmax + NC;
-  const int cchunks = ceil_div(C, 256);
-  // enough CTAs for ~8 per SM; every CTA should still stream >= 256 pixels
-  int psplit = ceil_div(148 * 8, N * cchunks);
-  const int maxsplit = HW / 256 > 0 ? HW / 256 : 1;
-  if (psplit > maxsplit) psplit = maxsplit;
-  if (psplit < 1) psplit = 1;
-  if (psplit > 1) {
-    if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
+  if (!d->stats_fused) {
+    const int cchunks = ceil_div(C, 256);
+    // enough CTAs for ~8 per SM; every CTA should still stream >= 256 pixels
+    int psplit = ceil_div(148 * 8, N * cchunks);
+    const int maxsplit = HW / 256 > 0 ? HW / 256 : 1;
+    if (psplit > maxsplit) psplit = maxsplit;
+    if (psplit < 1) psplit = 1;
+    if (psplit > 1) {
+      if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
+    }
+    dim3 g1(cchunks, psplit, N);
+    if (d->y_f32) nb_stats_kernel<true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+    else nb_stats_kernel<false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+    if ((rc = check_launch("nb_stats"))) return rc;
   }
-  dim3 g1(cchunks, psplit, N);
-  if (d->y_f32) nb_stats_kernel<true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
-  else nb_stats_kernel<false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
-  if ((rc = check_launch("nb_stats"))) return rc;
 
   const size_t sm2 = (2 * C + 128) * sizeof(float);
   if (d->y_f32)
     nb_coef_kernel<true><<<N, 256, sm2, st>>>(d->y, d->y_pitch, HW, C, ss, kmax, kmin, d->gamma, d->beta, d->eps,
-                                              d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx);
+                                              d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx, d->stats_fused, N);
   else
     nb_coef_kernel<false><<<N, 256, sm2, st>>>(d->y, d->y_pitch, HW, C, ss, kmax, kmin, d->gamma, d->beta, d->eps,
-                                               d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx);
+                                               d->has_cbam, d->Cr, d->w1, d->w2, d->nc, d->nc_idx, d->stats_fused, N);
   if ((rc = check_launch("nb_coef"))) return rc;
 
   const int G = C / 8 < 32 ? C / 8 : 32;
   const int iters = C / (8 * G);
   const int ppc = pick_ppc(HW, N, G);
   dim3 g3(ceil_div(HW, ppc), N);
-  const size_t sm3 = 5 * C * sizeof(float);
+  const size_t sm3 = 6 * C * sizeof(float);
   DISPATCH_ITERS(iters, {
     if (d->y_f32)
       nb_pool_kernel<true, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
-                                                      (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);
+                                                      (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
+                                                      d->stats_fused, d->nc_idx);
     else
       nb_pool_kernel<false, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
-                                                       (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);
+                                                       (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
+                                                       d->stats_fused, d->nc_idx);
   });
   if ((rc = check_launch("nb_pool"))) return rc;
   if (!d->has_cbam) return BVAE_OK;

@@ -24,6 +24,9 @@ BF16 = torch.bfloat16
 _PARAM_EPOCH = [0]          # bumped whenever libbarvae itself rewrites parameters (fused Adam)
 _IMPL = [_lib.IMPL_AUTO]    # contraction implementation selector (tests flip it to compare SIMT vs tcgen05)
 _RAW_F32 = [True]           # dtype of raw conv outputs feeding an InstanceNorm (see DESIGN.md "Parity tolerances")
+_FUSE_STATS = [False]       # opt-in: let the conv epilogue accumulate the InstanceNorm statistics of its output
+                            # (measured: the extra epilogue work costs the small-channel layers what the saved
+                            # statistics pass gains -- 56.6 vs 54.4 ms/step -- so it is off by default)
 
 
 def set_impl(impl: int):
@@ -40,6 +43,10 @@ def set_raw_f32(flag: bool):
 
 def raw_dtype():
     return torch.float32 if _RAW_F32[0] else BF16
+
+
+def set_fuse_stats(flag: bool):
+    _FUSE_STATS[0] = bool(flag)
 
 
 def bump_param_epoch():
@@ -254,11 +261,17 @@ class GemmLayer:
 
     # ---- launches -------------------------------------------------------------------------------------
     def _run_phases(self, phases, wpk: torch.Tensor, x: Act, y: Act, cout: int, grid_of, bias, act, slope,
-                    addend: Optional[Act], mask: Optional[Act], mask_slope: float, tag: str):
+                    addend: Optional[Act], mask: Optional[Act], mask_slope: float, tag: str, want_stats: bool = False):
+        """returns the fused-statistics buffer (zeroed, then filled by the epilogues of all phases) or None"""
         lib = _lib.lib()
         st = _lib.stream_ptr()
         key = (tag, x.N, x.H, x.W, x.pitch, y.H, y.W, y.pitch, y.f32, act, slope, addend is not None and addend.pitch,
                mask is not None and mask.pitch, mask_slope, bias is not None)
+        stats = None
+        if want_stats:
+            ok = self._cache.get(("stats_ok",) + key)
+            if ok is None or ok:
+                stats = torch.zeros(y.N * cout * 6, dtype=torch.float32, device=y.t.device)
         descs = self._cache.get(key)
         if descs is None:
             descs = []
@@ -281,26 +294,41 @@ class GemmLayer:
                 d.act, d.out_f32, d.slope, d.mask_slope = int(act), int(y.f32), float(slope), float(mask_slope)
                 descs.append((d, ph.k_off * x.C * 2))
             self._cache[key] = descs
+        if stats is not None and ("stats_ok",) + key not in self._cache:
+            # every phase must be able to fuse (tcgen05 path, fp32 output, each M tile inside one sample)
+            ok = _IMPL[0] != _lib.IMPL_SIMT
+            for d, woff in descs:
+                d.x, d.w, d.y = x.ptr, wpk.data_ptr() + woff, y.ptr
+                ok = ok and bool(lib.bvae_conv_stats_ok(C.byref(d)))
+            self._cache[("stats_ok",) + key] = ok
+            if not ok:
+                stats = None
         xp, yp, wp = x.ptr, y.ptr, wpk.data_ptr()
+        sp = stats.data_ptr() if stats is not None else None
         bp = bias.data_ptr() if bias is not None else None
         ap = addend.ptr if addend is not None else None
         mp = mask.ptr if mask is not None else None
         for d, woff in descs:
-            d.x, d.w, d.y, d.bias, d.addend, d.mask = xp, wp + woff, yp, bp, ap, mp
+            d.x, d.w, d.y, d.bias, d.addend, d.mask, d.stats = xp, wp + woff, yp, bp, ap, mp, sp
             _lib.check(_timed("conv_gemm", lib.bvae_conv_gemm, C.byref(d), _IMPL[0], st,
                               detail="%s %s %d->%d k%dx%d s%dx%d in%dx%d" % (tag, self.kind, self.Cin, self.Cout, self.kh,
                                                                              self.kw, self.sy, self.sx, x.H, x.W)),
                        "conv_gemm[%s]" % tag)
+        return stats
 
-    def forward(self, x: Act, y: Act, act: bool = False, slope: float = 0.0, use_bias: bool = True):
-        """y = epi(conv(x)); y geometry must be out_hw(x) with C == Cout."""
+    def forward(self, x: Act, y: Act, act: bool = False, slope: float = 0.0, use_bias: bool = True,
+                want_stats: bool = False):
+        """y = epi(conv(x)); y geometry must be out_hw(x) with C == Cout.  With want_stats the InstanceNorm statistics
+        of y are accumulated by the epilogue when possible; returns that buffer (for NormBlock.forward) or None."""
         assert x.C == self.Cin and y.C == self.Cout, (x.C, self.Cin, y.C, self.Cout)
         if self.kind == "convT":
             grid_of = lambda ph: (-(-(y.H - ph.ooy) // ph.osy), -(-(y.W - ph.oox) // ph.osx))
         else:
             grid_of = lambda ph: (y.H, y.W)
         bias = self.bias.detach() if (self.bias is not None and use_bias) else None
-        self._run_phases(self.f_phases, self.w_fwd(), x, y, self.Cout, grid_of, bias, act, slope, None, None, 0.0, "f")
+        fuse = want_stats and _FUSE_STATS[0] and y.f32 and not act and y.H * y.W > 128
+        return self._run_phases(self.f_phases, self.w_fwd(), x, y, self.Cout, grid_of, bias, act, slope, None, None, 0.0,
+                                "f", fuse)
 
     def dgrad(self, dy: Act, dx: Act, addend: Optional[Act] = None, mask: Optional[Act] = None,
               mask_slope: float = 0.0):
@@ -370,15 +398,18 @@ class NormBlock:
             d.w1, d.w2, d.wsp = (p.data_ptr() for p in self.cbam)
         return d
 
-    def forward(self, y: Act, out: Act, res: Optional[Act] = None) -> dict:
+    def forward(self, y: Act, out: Act, res: Optional[Act] = None, stats: Optional[torch.Tensor] = None) -> dict:
         N, H, W, Cc = y.N, y.H, y.W, self.C
         dev = y.t.device
         ctx = {"N": N, "H": H, "W": W, "out": out,
                "uhat": torch.empty((N, H, W, Cc), dtype=BF16, device=dev),
                "nc": torch.empty((N, Cc, 8), dtype=torch.float32, device=dev),
                "nc_idx": torch.empty((N, Cc), dtype=torch.int32, device=dev)}
-        stats = torch.empty((N * Cc * 6,), dtype=torch.float32, device=dev)
+        fused = stats is not None
+        if stats is None:
+            stats = torch.empty((N * Cc * 6,), dtype=torch.float32, device=dev)
         d = self._desc(y.pitch, y.f32, out, N, H, W)
+        d.stats_fused = int(fused)
         d.y, d.uhat, d.out, d.stats = y.ptr, ctx["uhat"].data_ptr(), out.ptr, stats.data_ptr()
         d.nc, d.nc_idx = ctx["nc"].data_ptr(), ctx["nc_idx"].data_ptr()
         if self.cbam is not None:

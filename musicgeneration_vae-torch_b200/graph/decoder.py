@@ -34,9 +34,9 @@ class _HeadModule(nn.Module):
         t1 = Act.empty(x.N, h1, w1, 1024)
         g1.forward(x, t1, act=True, slope=0.0)
         y = Act.empty(x.N, out.H, out.W, 1024, dtype=raw_dtype())
-        g2.forward(t1, y)
+        st = g2.forward(t1, y, want_stats=True)
         nb = norm_block(self.bn, self.cbam, 1, 0.0)
-        return (x, t1, nb, nb.forward(y, out))
+        return (x, t1, nb, nb.forward(y, out, stats=st))
 
     def bwd(self, ctx, dout: Act, dx: Act, accumulate: bool):
         x, t1, nb, nctx = ctx
@@ -83,14 +83,14 @@ class _UpBlock(nn.Module):
         for i, (deconv, bn, cbam, mode) in enumerate(self._branches()):
             g = gemm_of(deconv)
             y = Act.empty(out.N, out.H, out.W, Cc, dtype=raw_dtype())
-            g.forward(x, y)
+            st = g.forward(x, y, want_stats=True)
             nb = norm_block(bn, cbam, mode, 0.0)
-            bctx.append((g, nb, nb.forward(y, cat.slice(i * Cc, Cc))))
+            bctx.append((g, nb, nb.forward(y, cat.slice(i * Cc, Cc), stats=st)))
         g3 = gemm_of(self.conv)
         y3 = Act.empty(out.N, out.H, out.W, Cc, dtype=raw_dtype())
-        g3.forward(cat, y3)
+        st3 = g3.forward(cat, y3, want_stats=True)
         nb3 = norm_block(self.bn3, self._last_cbam(), 1, 0.0)
-        return (x, cat, bctx, g3, nb3, nb3.forward(y3, out))
+        return (x, cat, bctx, g3, nb3, nb3.forward(y3, out, stats=st3))
 
     def bwd(self, ctx, dout: Act) -> Act:
         x, cat, bctx, g3, nb3, n3ctx = ctx
@@ -217,10 +217,10 @@ class Decoder(nn.Module):
         c_t = self.time.fwd(x, hcat.slice(1024, 1024))
         g1 = gemm_of(self.fit1)
         y = Act.empty(B, 6, 3, 1024, dtype=raw_dtype())
-        g1.forward(hcat, y)
+        st1 = g1.forward(hcat, y, want_stats=True)
         nb = norm_block(self.bn, self.cbam, 1, 0.0)
         h = Act.empty(B, 6, 3, 1024)
-        c_f = nb.forward(y, h)
+        c_f = nb.forward(y, h, stats=st1)
         ctxs = []
         for layer in self.layers:
             oh, ow, oc = layer.out_shape(h.H, h.W)

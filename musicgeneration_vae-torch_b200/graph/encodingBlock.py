@@ -51,9 +51,9 @@ class _StemModule(nn.Module):
         g1.forward(x, t1, act=True, slope=self.SLOPE)
         h2, w2 = g2.out_hw(h1, w1)
         y = Act.empty(x.N, h2, w2, 32, dtype=raw_dtype())
-        g2.forward(t1, y)
+        st = g2.forward(t1, y, want_stats=True)
         nb = norm_block(self.bn, self.cbam, 1, self.SLOPE)
-        return (x, t1, nb, nb.forward(y, out))
+        return (x, t1, nb, nb.forward(y, out, stats=st))
 
     def bwd(self, ctx, dout: Act):
         x, t1, nb, nctx = ctx
@@ -101,9 +101,9 @@ class ResidualModule(nn.Module):
         c1 = Act.empty(x.N, x.H, x.W, x.C)
         g1.forward(x, c1, act=True, slope=0.0)
         y = Act.empty(x.N, x.H, x.W, x.C, dtype=raw_dtype())
-        g2.forward(c1, y)
+        st = g2.forward(c1, y, want_stats=True)
         nb = norm_block(self.bn, self.cbam, 2, 0.0)
-        return (x, c1, nb, nb.forward(y, out, res=x))
+        return (x, c1, nb, nb.forward(y, out, res=x, stats=st))
 
     def bwd(self, ctx, dout: Act) -> Act:
         x, c1, nb, nctx = ctx
@@ -136,9 +136,9 @@ class PoolingModule(nn.Module):
     def fwd(self, x: Act, out: Act):
         g = gemm_of(self.conv)
         y = Act.empty(out.N, out.H, out.W, out.C, dtype=raw_dtype())
-        g.forward(x, y)
+        st = g.forward(x, y, want_stats=True)
         nb = norm_block(self.bn, self.cbam, 1, 0.0)
-        return (x, nb, nb.forward(y, out))
+        return (x, nb, nb.forward(y, out, stats=st))
 
     def bwd(self, ctx, dout: Act) -> Act:
         x, nb, nctx = ctx
