@@ -33,6 +33,7 @@ extern "C" {
 #define BVAE_ERR_UNSUPPORTED 5
 
 #define BVAE_MAX_TAPS 16
+#define BVAE_MAX_PHASES 6
 
 /* implementation selector for the contraction kernels */
 #define BVAE_IMPL_AUTO 0  /* tcgen05 when the shape allows, else SIMT */
@@ -84,6 +85,14 @@ typedef struct bvae_conv_desc {
   int32_t act;       /* 0 none, 1 leaky-relu with `slope` (0 = ReLU) applied after bias */
   int32_t out_f32;
   float slope, mask_slope;
+  /* Several phases in ONE call (all sub-pixel phases of a strided transposed convolution / of a strided
+   * convolution's data gradient): nphase > 0, taps listed phase-major in dy/dx (ntaps = total), phase i uses
+   * ph_ntaps[i] taps and weight columns starting at (taps before it)*C, writes at offset (ph_ooy[i], ph_oox[i]) on the
+   * grid ph_QH[i] x ph_QW[i].  QH/QW/ooy/oox above are ignored then.  Tiles of the same input patch run back to back,
+   * so the patch is read from HBM once for all phases.  nphase == 0: the single phase described above. */
+  int32_t nphase;
+  int32_t ph_ntaps[BVAE_MAX_PHASES], ph_ooy[BVAE_MAX_PHASES], ph_oox[BVAE_MAX_PHASES];
+  int32_t ph_QH[BVAE_MAX_PHASES], ph_QW[BVAE_MAX_PHASES];
 } bvae_conv_desc;
 
 int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream);

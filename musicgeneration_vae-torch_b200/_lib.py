@@ -13,6 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbarvae.so")
 MAX_TAPS = 16
+MAX_PHASES = 6
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 
 c_i32, c_f32, c_vp, c_i64 = C.c_int32, C.c_float, C.c_void_p, C.c_int64
@@ -29,7 +30,9 @@ class ConvDesc(C.Structure):
                 ("OH", c_i32), ("OW", c_i32), ("y_pitch", c_i32),
                 ("osy", c_i32), ("osx", c_i32), ("ooy", c_i32), ("oox", c_i32),
                 ("add_pitch", c_i32), ("mask_pitch", c_i32), ("act", c_i32), ("out_f32", c_i32),
-                ("slope", c_f32), ("mask_slope", c_f32)]
+                ("slope", c_f32), ("mask_slope", c_f32),
+                ("nphase", c_i32), ("ph_ntaps", c_i32 * MAX_PHASES), ("ph_ooy", c_i32 * MAX_PHASES),
+                ("ph_oox", c_i32 * MAX_PHASES), ("ph_QH", c_i32 * MAX_PHASES), ("ph_QW", c_i32 * MAX_PHASES)]
 
 
 class WgradDesc(C.Structure):

@@ -129,6 +129,9 @@ struct alignas(64) ConvTcParams {
   int ntaps, kchunks, C;
   int bw, bh, bn, tiles_w, tiles_h, tiles_n, n_tiles;
   int N, QH, QW, Cout;
+  int nphase;                                   // >= 1 (conv_tc2 only; conv_tc_kernel handles exactly one phase)
+  int ph_tap0[BVAE_MAX_PHASES], ph_ntaps[BVAE_MAX_PHASES], ph_ooy[BVAE_MAX_PHASES], ph_oox[BVAE_MAX_PHASES];
+  int ph_QH[BVAE_MAX_PHASES], ph_QW[BVAE_MAX_PHASES];
   void* y;
   const float* bias;
   const void* addend;
@@ -330,9 +333,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
   uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int KT = p.ntaps * p.kchunks;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total = m_tiles * p.n_tiles;
+  const int total = m_tiles * p.nphase * p.n_tiles;     // tile order: N tile fastest, then phase, then the pixel box
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
@@ -354,16 +356,18 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
+      int ph = m_tile % p.nphase; m_tile /= p.nphase;
+      ph = (ph + m_tile) % p.nphase;      // rotate: a static round-robin must not pin a CTA to one phase (unequal tap counts)
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int tn = m_tile / p.tiles_h;
-      for (int t = 0; t < p.ntaps; ++t) {
+      for (int t = p.ph_tap0[ph]; t < p.ph_tap0[ph] + p.ph_ntaps[ph]; ++t) {
         const CUtensorMap* am = &p.amap[p.tap_view[t]];
         const int cw = tw * p.bw + p.tap_ex[t], ch = th * p.bh + p.tap_ey[t], cn = tn * p.bn;
         for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
           const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(empty_bar + s, ph ^ 1u);
+          const uint32_t par = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + s, par ^ 1u);
           mbar_expect_tx(full_bar + s, tx);
           uint8_t* sa = smem + s * STAGE_BYTES;
           tma_load_4d(sa, am, full_bar + s, kc * KB, cw, ch, cn);
@@ -379,6 +383,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       mbar_wait(tempty + ab, aph ^ 1u);            // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tacc = tmem_base + ab * ACC_COLS;
+      const int rest = tile / p.n_tiles;
+      const int KT = p.ph_ntaps[(rest % p.nphase + rest / p.nphase) % p.nphase] * p.kchunks;
       for (int kb = 0; kb < KT; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -404,12 +410,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
+      int ph = m_tile % p.nphase; m_tile /= p.nphase;
+      ph = (ph + m_tile) % p.nphase;      // rotate: a static round-robin must not pin a CTA to one phase (unequal tap counts)
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int tn = m_tile / p.tiles_h;
       const int n = tn * p.bn + nn, qy = th * p.bh + hh, qx = tw * p.bw + ww;
-      const bool valid = r < rows_box && n < p.N && qy < p.QH && qx < p.QW;
-      const int64_t opix = ((int64_t)n * p.OH + (qy * p.osy + p.ooy)) * p.OW + (qx * p.osx + p.oox);
+      const bool valid = r < rows_box && n < p.N && qy < p.ph_QH[ph] && qx < p.ph_QW[ph];
+      const int64_t opix = ((int64_t)n * p.OH + (qy * p.osy + p.ph_ooy[ph])) * p.OW + (qx * p.osx + p.ph_oox[ph]);
       const int col0 = n_tile * BN;
       mbar_wait(tfull + ab, aph);
       tc_fence_after();
@@ -826,10 +834,18 @@ int conv_tc_eligible(const bvae_conv_desc* d) {
   return pick_bn(d->Cout) != 0;
 }
 
+int conv_tc_multi_ok(const bvae_conv_desc* d) { return !use_conv_v1_flag() && conv_tc_eligible(d); }
+
 int conv_tc_stats_ok(const bvae_conv_desc* d) {
   if (use_conv_v1_flag() || !conv_tc_eligible(d) || !d->out_f32 || d->act || d->addend || d->mask) return 0;
+  int QHm = d->QH, QWm = d->QW;
+  for (int i = 0; i < d->nphase; ++i) {
+    if (i == 0) QHm = QWm = 0;
+    if (d->ph_QH[i] > QHm) QHm = d->ph_QH[i];
+    if (d->ph_QW[i] > QWm) QWm = d->ph_QW[i];
+  }
   int bw, bh, bn;
-  pick_box(d->N, d->QH, d->QW, 128, &bw, &bh, &bn);
+  pick_box(d->N, QHm, QWm, 128, &bw, &bh, &bn);
   return bn == 1;
 }
 
@@ -881,7 +897,25 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   const int BN = pick_bn(d->Cout);
   ViewPlan vp;
   BVAE_REQUIRE(plan_views(d->ntaps, d->dy, d->dx, d->sy, d->sx, &vp), BVAE_ERR_UNSUPPORTED, "conv_tc: too many views");
-  pick_box(d->N, d->QH, d->QW, 128, &P.bw, &P.bh, &P.bn);
+  int QHm = d->QH, QWm = d->QW;
+  if (d->nphase > 0) {
+    QHm = QWm = 0;
+    int t0 = 0;
+    P.nphase = d->nphase;
+    for (int i = 0; i < d->nphase; ++i) {
+      P.ph_tap0[i] = t0; P.ph_ntaps[i] = d->ph_ntaps[i]; P.ph_ooy[i] = d->ph_ooy[i]; P.ph_oox[i] = d->ph_oox[i];
+      P.ph_QH[i] = d->ph_QH[i]; P.ph_QW[i] = d->ph_QW[i];
+      t0 += d->ph_ntaps[i];
+      if (d->ph_QH[i] > QHm) QHm = d->ph_QH[i];
+      if (d->ph_QW[i] > QWm) QWm = d->ph_QW[i];
+    }
+    BVAE_REQUIRE(t0 == d->ntaps, BVAE_ERR_SHAPE, "conv_tc: phase tap counts do not add up to ntaps");
+  } else {
+    P.nphase = 1;
+    P.ph_tap0[0] = 0; P.ph_ntaps[0] = d->ntaps; P.ph_ooy[0] = d->ooy; P.ph_oox[0] = d->oox;
+    P.ph_QH[0] = d->QH; P.ph_QW[0] = d->QW;
+  }
+  pick_box(d->N, QHm, QWm, 128, &P.bw, &P.bh, &P.bn);
   for (int v = 0; v < vp.nviews; ++v) {
     const int Hv = ceil_div(d->H - vp.fy[v], d->sy), Wv = ceil_div(d->W - vp.fx[v], d->sx);
     BVAE_REQUIRE(Hv > 0 && Wv > 0, BVAE_ERR_SHAPE, "conv_tc: empty view");
@@ -894,15 +928,16 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   if (rc) return rc;
   for (int t = 0; t < d->ntaps; ++t) { P.tap_view[t] = vp.tap_view[t]; P.tap_ex[t] = vp.tap_ex[t]; P.tap_ey[t] = vp.tap_ey[t]; }
   P.ntaps = d->ntaps; P.kchunks = d->C / KB; P.C = d->C;
-  P.tiles_w = ceil_div(d->QW, P.bw); P.tiles_h = ceil_div(d->QH, P.bh); P.tiles_n = ceil_div(d->N, P.bn);
+  P.tiles_w = ceil_div(QWm, P.bw); P.tiles_h = ceil_div(QHm, P.bh); P.tiles_n = ceil_div(d->N, P.bn);
   P.n_tiles = d->Cout / BN;
-  P.N = d->N; P.QH = d->QH; P.QW = d->QW; P.Cout = d->Cout;
+  P.N = d->N; P.QH = QHm; P.QW = QWm; P.Cout = d->Cout;
   P.y = d->y; P.bias = d->bias; P.addend = d->addend; P.mask = d->mask; P.stats = d->stats;
   P.OH = d->OH; P.OW = d->OW; P.y_pitch = d->y_pitch; P.osy = d->osy; P.osx = d->osx; P.ooy = d->ooy; P.oox = d->oox;
   P.add_pitch = d->add_pitch; P.mask_pitch = d->mask_pitch; P.act = d->act; P.out_f32 = d->out_f32;
   P.slope = d->slope; P.mask_slope = d->mask_slope;
-  const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles;
+  const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles * P.nphase;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "conv_tc: grid too large");
+  BVAE_REQUIRE(P.nphase == 1 || !use_conv_v1(), BVAE_ERR_UNSUPPORTED, "conv_tc: multi-phase needs the persistent kernel");
   if (!use_conv_v1()) {
 #define CONV2_CASE(kb, bn) if (KB == kb && BN == bn) return launch_conv2<kb, bn>(P, grid, stream)
     CONV2_CASE(64, 256); CONV2_CASE(64, 192); CONV2_CASE(64, 128); CONV2_CASE(64, 64); CONV2_CASE(64, 32);

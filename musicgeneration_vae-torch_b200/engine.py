@@ -275,24 +275,49 @@ class GemmLayer:
         descs = self._cache.get(key)
         if descs is None:
             descs = []
+            live = []
             for ph in phases:
                 if not ph.taps:
                     raise RuntimeError("phase without taps (kernel smaller than stride) is not supported")
                 QH, QW = grid_of(ph)
-                if QH <= 0 or QW <= 0:
-                    continue
+                if QH > 0 and QW > 0:
+                    live.append((ph, QH, QW))
+
+            def base_desc(ph):
                 d = ConvDesc()
                 d.N, d.H, d.W, d.C, d.x_pitch = x.N, x.H, x.W, x.C, x.pitch
-                d.Cout, d.w_pitch, d.ntaps = cout, wpk.shape[1], len(ph.taps)
-                for i in range(len(ph.taps)):
-                    d.dy[i], d.dx[i] = ph.dy[i], ph.dx[i]
-                d.sy, d.sx, d.QH, d.QW = ph.sy, ph.sx, QH, QW
+                d.Cout, d.w_pitch = cout, wpk.shape[1]
+                d.sy, d.sx = ph.sy, ph.sx
                 d.OH, d.OW, d.y_pitch = y.H, y.W, y.pitch
-                d.osy, d.osx, d.ooy, d.oox = ph.osy, ph.osx, ph.ooy, ph.oox
+                d.osy, d.osx = ph.osy, ph.osx
                 d.add_pitch = addend.pitch if addend is not None else 0
                 d.mask_pitch = mask.pitch if mask is not None else 0
                 d.act, d.out_f32, d.slope, d.mask_slope = int(act), int(y.f32), float(slope), float(mask_slope)
-                descs.append((d, ph.k_off * x.C * 2))
+                return d
+
+            ntot = sum(len(ph.taps) for ph, _, _ in live)
+            contiguous = all(live[i][0].k_off + len(live[i][0].taps) == live[i + 1][0].k_off for i in range(len(live) - 1))
+            if len(live) > 1 and len(live) <= _lib.MAX_PHASES and ntot <= _lib.MAX_TAPS and contiguous:
+                # all sub-pixel phases in ONE launch: tiles of the same input patch run back to back (L2 reuse)
+                d = base_desc(live[0][0])
+                d.nphase, d.ntaps = len(live), ntot
+                t = 0
+                for i, (ph, QH, QW) in enumerate(live):
+                    d.ph_ntaps[i], d.ph_ooy[i], d.ph_oox[i], d.ph_QH[i], d.ph_QW[i] = len(ph.taps), ph.ooy, ph.oox, QH, QW
+                    for j in range(len(ph.taps)):
+                        d.dy[t], d.dx[t] = ph.dy[j], ph.dx[j]
+                        t += 1
+                d.QH, d.QW = max(q[1] for q in live), max(q[2] for q in live)
+                descs.append((d, live[0][0].k_off * x.C * 2))
+            else:
+                for ph, QH, QW in live:
+                    d = base_desc(ph)
+                    d.ntaps = len(ph.taps)
+                    for i in range(len(ph.taps)):
+                        d.dy[i], d.dx[i] = ph.dy[i], ph.dx[i]
+                    d.QH, d.QW = QH, QW
+                    d.ooy, d.oox = ph.ooy, ph.oox
+                    descs.append((d, ph.k_off * x.C * 2))
             self._cache[key] = descs
         if stats is not None and ("stats_ok",) + key not in self._cache:
             # every phase must be able to fuse (tcgen05 path, fp32 output, each M tile inside one sample)

@@ -180,3 +180,24 @@ def test_state_dict_roundtrip_and_freeze(oracle):
         p.requires_grad = True
     out = model(note, pre_note, phrase, position)[0]
     assert out.requires_grad
+
+
+def test_fused_statistics_path_matches(oracle):
+    """opt-in fusion of the InstanceNorm statistics into the convolution epilogue (bvae_conv_desc.stats): same encoder
+    output as the separate statistics pass (both fp32 statistics of the same fp32 values: 1e-3 on z)."""
+    O = oracle
+    eng = pkg("engine")
+    Model = pkg("graph.model").Model
+    sd = O.make_state_dict(O.generator_spec(), 11, "lively")
+    model = _load(Model(), sd).eval()
+    note = O.make_inputs(3, 5)[0].cuda()
+    with torch.no_grad():
+        z0 = model.encoder(note)
+        eng.set_fuse_stats(True)
+        try:
+            z1 = model.encoder(note)
+        finally:
+            eng.set_fuse_stats(False)
+    e = rel_fro(z1, z0)
+    report(test="fused_stats", z_rel=e)
+    assert e < 1e-3, e
