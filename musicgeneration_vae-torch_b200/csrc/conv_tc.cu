@@ -313,11 +313,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int KB, int BN, int STAGES>
+// BRES: the whole weight operand (all taps x K chunks of the single N tile) is loaded ONCE per CTA and stays resident in
+// shared memory; the pipeline then streams activation tiles only (small-channel layers are L2-bandwidth bound and the
+// weights were a third of their traffic).
+template <int KB, int BN, int STAGES, bool BRES>
 __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
   constexpr int A_BYTES = 128 * KB * 2;
   constexpr int B_BYTES = BN * KB * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
   constexpr int ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
   constexpr int TMEM_COLS = 2 * ACC_COLS;
   constexpr uint32_t LAYOUT = KB == 64 ? 2u : 4u;
@@ -325,12 +328,15 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
   constexpr uint32_t IDESC = make_idesc(128, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_al = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* bres = smem_al;                                       // [ntaps * kchunks][BN x KB] resident weights (BRES)
+  uint8_t* smem = smem_al + (BRES ? p.ntaps * p.kchunks * B_BYTES : 0);
   uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull = empty_bar + STAGES;       // [2]
   uint64_t* tempty = tfull + 2;               // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+  uint64_t* bres_bar = tempty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -339,6 +345,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 128); }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.bmap);
     tma_prefetch_desc(&p.amap[0]);
@@ -351,7 +358,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    const uint32_t tx = (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + B_BYTES);
+    const uint32_t tx = (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + (BRES ? 0 : B_BYTES));
+    if (BRES) {
+      mbar_expect_tx(bres_bar, (uint32_t)(p.ntaps * p.kchunks * B_BYTES));
+      for (int t = 0; t < p.ntaps; ++t)
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_2d(bres + (t * p.kchunks + kc) * B_BYTES, &p.bmap, bres_bar, t * p.C + kc * KB, 0);
+    }
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
@@ -371,20 +384,23 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
           mbar_expect_tx(full_bar + s, tx);
           uint8_t* sa = smem + s * STAGE_BYTES;
           tma_load_4d(sa, am, full_bar + s, kc * KB, cw, ch, cn);
-          tma_load_2d(sa + A_BYTES, &p.bmap, full_bar + s, t * p.C + kc * KB, n_tile * BN);
+          if (!BRES) tma_load_2d(sa + A_BYTES, &p.bmap, full_bar + s, t * p.C + kc * KB, n_tile * BN);
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     uint32_t it = 0, ti = 0;
+    if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
       mbar_wait(tempty + ab, aph ^ 1u);            // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tacc = tmem_base + ab * ACC_COLS;
       const int rest = tile / p.n_tiles;
-      const int KT = p.ph_ntaps[(rest % p.nphase + rest / p.nphase) % p.nphase] * p.kchunks;
+      const int phase = (rest % p.nphase + rest / p.nphase) % p.nphase;
+      const int KT = p.ph_ntaps[phase] * p.kchunks;
+      const uint32_t bres0 = smem_u32(bres) + (uint32_t)(p.ph_tap0[phase] * p.kchunks) * B_BYTES;
       for (int kb = 0; kb < KT; ++kb, ++it) {
         const uint32_t s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1u;
@@ -392,7 +408,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
         const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
-        const uint64_t bdesc = make_sdesc(sa + A_BYTES, 16, SBO, LAYOUT);
+        const uint64_t bdesc = make_sdesc(BRES ? bres0 + (uint32_t)kb * B_BYTES : sa + A_BYTES, 16, SBO, LAYOUT);
 #pragma unroll
         for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kb | j) ? 1u : 0u);
         umma_commit(empty_bar + s);
@@ -862,25 +878,34 @@ static int launch_conv(const ConvTcParams& P, int grid, cudaStream_t stream) {
   return check_launch("conv_tc");
 }
 
-template <int KB, int BN>
-static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) {
-  constexpr int STAGE = 128 * KB * 2 + BN * KB * 2;
-  constexpr int ST_RAW = (200 * 1024) / STAGE;
+template <int KB, int BN, bool BRES>
+static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t stream) {
+  constexpr int B_BYTES = BN * KB * 2;
+  constexpr int STAGE = BRES ? 128 * KB * 2 : 128 * KB * 2 + B_BYTES;
+  constexpr int BUDGET = BRES ? 100 * 1024 : 200 * 1024;        // resident weights take up to 96 KB of their own
+  constexpr int ST_RAW = BUDGET / STAGE;
   constexpr int STAGES = ST_RAW > 8 ? 8 : ST_RAW;
-  constexpr int smem = 1024 + STAGES * STAGE + (2 * STAGES + 4) * 8 + 16;
-  static bool attr_done = false;
+  const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 16;
+  static int attr_smem = 0;
   static int num_sms = 148;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<KB, BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<KB, BN, STAGES, BRES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "conv_tc2: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    attr_done = true;
+    attr_smem = smem;
   }
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  conv_tc2_kernel<KB, BN, STAGES><<<grid, 256, smem, stream>>>(P);
+  conv_tc2_kernel<KB, BN, STAGES, BRES><<<grid, 256, smem, stream>>>(P);
   return check_launch("conv_tc2");
+}
+
+template <int KB, int BN>
+static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) {
+  // weights resident in shared memory when one N tile covers Cout and all taps fit in 96 KB
+  const bool bres = P.n_tiles == 1 && (long)P.ntaps * P.kchunks * (BN * KB * 2) <= 96 * 1024 && tiles >= 2 * 148;
+  return bres ? launch_conv2_impl<KB, BN, true>(P, tiles, stream) : launch_conv2_impl<KB, BN, false>(P, tiles, stream);
 }
 
 static bool use_conv_v1() {
