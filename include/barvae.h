@@ -128,6 +128,21 @@ int bvae_wgrad_gemm(const bvae_wgrad_desc* d, int impl, void* stream);
 int bvae_pack_weight(const float* src, void* dst, int R, int T, int Cc, int64_t sr, int64_t sc,
                      const int32_t* perm /* host array [T] */, int dst_pitch, void* stream);
 
+/* The same repack for MANY parameters in one launch (all contraction weights of the model after each optimiser step;
+ * replaces ~100 bvae_pack_weight launches).  Jobs are copied to the device when the plan is created; the plan keeps
+ * the src/dst pointers, so it is valid while those buffers live.  `perm` must hold T entries. */
+typedef struct bvae_pack_job {
+  const float* src;
+  void* dst;                        /* bf16 */
+  int32_t R, T, Cc, dst_pitch;
+  int64_t sr, sc;
+  int32_t perm[BVAE_MAX_TAPS];
+} bvae_pack_job;
+typedef struct bvae_pack_plan bvae_pack_plan;
+int bvae_pack_plan_create(const bvae_pack_job* jobs /* host */, int njobs, bvae_pack_plan** out);
+int bvae_pack_plan_run(const bvae_pack_plan* plan, void* stream);
+void bvae_pack_plan_destroy(bvae_pack_plan* plan);
+
 /* column sums: out[c] += sum over rows of x[row*pitch + c]  (bias gradients; x bf16 or fp32) */
 int bvae_colsum(const void* x, int x_f32, int64_t rows, int C, int pitch, float* out, void* stream);
 

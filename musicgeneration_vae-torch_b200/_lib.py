@@ -59,6 +59,12 @@ class NbDesc(C.Structure):
                 ("bwd_nc", c_vp), ("bwd_px", c_vp), ("bwd_h", c_vp)]
 
 
+class PackJob(C.Structure):
+    """mirror of bvae_pack_job (include/barvae.h)"""
+    _fields_ = [("src", c_vp), ("dst", c_vp), ("R", c_i32), ("T", c_i32), ("Cc", c_i32), ("dst_pitch", c_i32),
+                ("sr", c_i64), ("sc", c_i64), ("perm", c_i32 * MAX_TAPS)]
+
+
 _lib = None
 _dev_checked = False
 
@@ -74,6 +80,9 @@ SYMBOLS = [
     ("bvae_wgrad_gemm", C.c_int, [C.POINTER(WgradDesc), C.c_int, c_vp]),
     ("bvae_pack_weight", C.c_int, [c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_i64, c_i64, C.POINTER(c_i32), C.c_int,
                                    c_vp]),
+    ("bvae_pack_plan_create", C.c_int, [C.POINTER(PackJob), C.c_int, C.POINTER(c_vp)]),
+    ("bvae_pack_plan_run", C.c_int, [c_vp, c_vp]),
+    ("bvae_pack_plan_destroy", None, [c_vp]),
     ("bvae_colsum", C.c_int, [c_vp, C.c_int, c_i64, C.c_int, C.c_int, c_vp, c_vp]),
     ("bvae_nb_forward", C.c_int, [C.POINTER(NbDesc), c_vp]),
     ("bvae_nb_backward", C.c_int, [C.POINTER(NbDesc), c_vp]),

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <atomic>
 #include "common.cuh"
+#include <vector>
 
 namespace bvae {
 
@@ -42,6 +43,68 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     const int tp = (int)((i / Cc) % T);
     const int r = (int)(i / ((int64_t)Cc * T));
     dst[(int64_t)r * dst_pitch + (int64_t)tp * Cc + c] = f2bf(src[r * sr + c * sc + perm.p[tp]]);
+  }
+}
+
+// Batched repack: one CTA per (8 rows x 64 columns x all taps) tile of one job.  The tile is read in the order that is
+// contiguous in the SOURCE (taps fastest, then whichever of r / c has the smaller stride), staged in shared memory
+// and written as 128-byte destination rows.
+struct PackJobDev {
+  const float* src;
+  bf16* dst;
+  int R, T, Cc, dst_pitch;
+  long long sr, sc;
+  int perm[BVAE_MAX_TAPS];
+  int block0, ctiles;
+};
+
+__global__ void __launch_bounds__(256) pack_batch_kernel(const PackJobDev* __restrict__ jobs, int njobs) {
+  constexpr int RT = 8, CT = 64, LD = CT + 2;
+  __shared__ PackJobDev j;
+  __shared__ __align__(16) bf16 tile[RT * BVAE_MAX_TAPS * LD];
+  __shared__ int jsel;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    jsel = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x < sizeof(PackJobDev) / 4)
+    reinterpret_cast<int*>(&j)[threadIdx.x] = reinterpret_cast<const int*>(jobs + jsel)[threadIdx.x];
+  __syncthreads();
+  const int local = blockIdx.x - j.block0;
+  const int r0 = (local / j.ctiles) * RT, c0 = (local % j.ctiles) * CT;
+  const int nr = min(RT, j.R - r0), nc = min(CT, j.Cc - c0), T = j.T;
+  const float* src = j.src + r0 * j.sr + c0 * j.sc;
+  const int total = nr * nc * T;
+  if (j.sr <= j.sc) {
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int tp = e % T, r = (e / T) % nr, c = e / (T * nr);
+      tile[(r * T + tp) * LD + c] = f2bf(src[r * j.sr + c * j.sc + j.perm[tp]]);
+    }
+  } else {
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int tp = e % T, c = (e / T) % nc, r = e / (T * nc);
+      tile[(r * T + tp) * LD + c] = f2bf(src[r * j.sr + c * j.sc + j.perm[tp]]);
+    }
+  }
+  __syncthreads();
+  if (nc == CT && (j.Cc & 1) == 0 && (j.dst_pitch & 1) == 0) {
+    for (int e = threadIdx.x; e < nr * T * (CT / 2); e += 256) {
+      const int c2 = e % (CT / 2), row = e / (CT / 2);
+      const int tp = row % T, r = row / T;
+      *reinterpret_cast<uint32_t*>(j.dst + (int64_t)(r0 + r) * j.dst_pitch + (int64_t)tp * j.Cc + c0 + 2 * c2) =
+          *reinterpret_cast<const uint32_t*>(tile + row * LD + 2 * c2);
+    }
+  } else {
+    for (int e = threadIdx.x; e < nr * T * nc; e += 256) {
+      const int c = e % nc, row = e / nc;
+      const int tp = row % T, r = row / T;
+      j.dst[(int64_t)(r0 + r) * j.dst_pitch + (int64_t)tp * j.Cc + c0 + c] = tile[row * LD + c];
+    }
   }
 }
 
@@ -323,6 +386,54 @@ int bvae_pack_weight(const float* src, void* dst, int R, int T, int Cc, int64_t 
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, R, T, Cc, sr, sc, pp,
                                                                               dst_pitch);
   return check_launch("pack_weight");
+}
+
+struct bvae_pack_plan {
+  bvae::PackJobDev* jobs;
+  int njobs, nblocks;
+};
+
+int bvae_pack_plan_create(const bvae_pack_job* jobs, int njobs, bvae_pack_plan** out) {
+  BVAE_REQUIRE(jobs && out && njobs > 0, BVAE_ERR_SHAPE, "pack_plan: no jobs");
+  std::vector<bvae::PackJobDev> host((size_t)njobs);
+  long long blocks = 0;
+  for (int i = 0; i < njobs; ++i) {
+    const bvae_pack_job& a = jobs[i];
+    BVAE_REQUIRE(a.T >= 1 && a.T <= BVAE_MAX_TAPS, BVAE_ERR_SHAPE, "pack_plan: job %d: T=%d out of range", i, a.T);
+    BVAE_REQUIRE(a.R > 0 && a.Cc > 0 && a.dst_pitch >= a.T * a.Cc, BVAE_ERR_SHAPE, "pack_plan: job %d: bad shape", i);
+    BVAE_REQUIRE(a.src && a.dst, BVAE_ERR_SHAPE, "pack_plan: job %d: null pointer", i);
+    bvae::PackJobDev& d = host[(size_t)i];
+    d.src = a.src; d.dst = (bf16*)a.dst;
+    d.R = a.R; d.T = a.T; d.Cc = a.Cc; d.dst_pitch = a.dst_pitch; d.sr = a.sr; d.sc = a.sc;
+    for (int t = 0; t < BVAE_MAX_TAPS; ++t) d.perm[t] = t < a.T ? a.perm[t] : 0;
+    d.block0 = (int)blocks;
+    d.ctiles = ceil_div(a.Cc, 64);
+    blocks += (long long)ceil_div(a.R, 8) * d.ctiles;
+    BVAE_REQUIRE(blocks < (1ll << 31), BVAE_ERR_SHAPE, "pack_plan: too many tiles");
+  }
+  bvae_pack_plan* pl = new bvae_pack_plan;
+  pl->njobs = njobs; pl->nblocks = (int)blocks; pl->jobs = nullptr;
+  cudaError_t e = cudaMalloc(&pl->jobs, sizeof(bvae::PackJobDev) * (size_t)njobs);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->jobs, host.data(), sizeof(bvae::PackJobDev) * (size_t)njobs, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (pl->jobs) cudaFree(pl->jobs);
+    delete pl;
+    BVAE_REQUIRE(false, BVAE_ERR_CUDA, "pack_plan: %s", cudaGetErrorString(e));
+  }
+  *out = pl;
+  return 0;
+}
+
+int bvae_pack_plan_run(const bvae_pack_plan* plan, void* stream) {
+  BVAE_REQUIRE(plan && plan->jobs, BVAE_ERR_SHAPE, "pack_plan_run: null plan");
+  bvae::pack_batch_kernel<<<plan->nblocks, 256, 0, (cudaStream_t)stream>>>(plan->jobs, plan->njobs);
+  return check_launch("pack_batch");
+}
+
+void bvae_pack_plan_destroy(bvae_pack_plan* plan) {
+  if (!plan) return;
+  if (plan->jobs) cudaFree(plan->jobs);
+  delete plan;
 }
 
 int bvae_colsum(const void* x, int x_f32, int64_t rows, int C, int pitch, float* out, void* stream) {

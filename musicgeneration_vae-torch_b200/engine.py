@@ -218,6 +218,7 @@ class GemmLayer:
             # W[co][ci][t]
             self.f_src = (Cin * T, T)
             self.d_src = (T, Cin * T)
+        weight._bvae_layer = self   # lets FlatParams find every contraction weight for the batched repack
         self._wf = self._wd = None
         self._wscratch = None       # zero-in / zero-out fp32 scratch for the packed weight-gradient reduction
         self._wf_key = self._wd_key = None
@@ -533,6 +534,63 @@ def flatten(module: torch.nn.Module) -> FlatParams:
     return flat
 
 
+class PackPlan:
+    """One-launch repack of every bf16 contraction operand that the model has used so far (bvae_pack_plan_*).
+
+    Built after the first optimiser step from the operands the layers packed lazily during that step; it takes over
+    those buffers and rewrites them in place after every later step."""
+
+    def __init__(self, flat: FlatParams):
+        self.handle = None
+        self.items = []          # (layer, which, tensor, weight data_ptr)
+        jobs = []
+        for p in flat.params:
+            layer = getattr(p, "_bvae_layer", None)
+            if layer is None or layer.weight is not p:
+                continue
+            for which, buf, rows, cc, src, perm in (("f", layer._wf, layer.Cout, layer.Cin, layer.f_src, layer.f_perm),
+                                                    ("d", layer._wd, layer.Cin, layer.Cout, layer.d_src, layer.d_perm)):
+                if buf is None:
+                    continue
+                j = _lib.PackJob()
+                j.src, j.dst = p.data_ptr(), buf.data_ptr()
+                j.R, j.T, j.Cc, j.dst_pitch = rows, len(perm), cc, buf.shape[1]
+                j.sr, j.sc = src
+                for i, t in enumerate(perm):
+                    j.perm[i] = t
+                jobs.append(j)
+                self.items.append((layer, which, buf, p.data_ptr()))
+        if jobs:
+            arr = (_lib.PackJob * len(jobs))(*jobs)
+            h = _lib.c_vp()
+            _lib.check(_lib.lib().bvae_pack_plan_create(arr, len(jobs), C.byref(h)), "pack_plan_create")
+            self.handle = h
+
+    def valid(self) -> bool:
+        for layer, which, buf, ptr in self.items:
+            if layer.weight.data_ptr() != ptr or (layer._wf if which == "f" else layer._wd) is not buf:
+                return False
+        return True
+
+    def run(self):
+        if self.handle is None:
+            return
+        _lib.check(_lib.lib().bvae_pack_plan_run(self.handle, _lib.stream_ptr()), "pack_plan_run")
+        for layer, which, _, _ in self.items:
+            if which == "f":
+                layer._wf_key = layer._key()
+            else:
+                layer._wd_key = layer._key()
+
+    def __del__(self):
+        if self.handle is not None:
+            try:
+                _lib.load().bvae_pack_plan_destroy(self.handle)
+            except Exception:
+                pass
+            self.handle = None
+
+
 def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
     """torch.optim.Adam semantics (agent/barGen.py:61-62) on the flat bucket, one kernel."""
     if flat.exp_avg is None:
@@ -542,3 +600,8 @@ def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: f
                                          flat.exp_avg_sq.data_ptr(), flat.numel, lr, betas[0], betas[1], eps, step,
                                          grad_scale, _lib.stream_ptr()), "adam")
     bump_param_epoch()
+    # refresh the bf16 operands of all contraction weights in one launch
+    plan = getattr(flat, "pack_plan", None)
+    if plan is None or not plan.valid():
+        plan = flat.pack_plan = PackPlan(flat)
+    plan.run()

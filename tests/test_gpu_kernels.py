@@ -296,3 +296,41 @@ def test_flat_adam():
         eng.adam_step(flat, 0.002, step)
         for a, b in zip(net.parameters(), ref.parameters()):
             assert rel_fro(a, b) < 1e-6
+
+
+def test_pack_plan_matches_single_packs():
+    """bvae_pack_plan_run (one launch for every contraction weight) must write bit-identical bf16 operands to the
+    per-layer bvae_pack_weight launches, for conv / transposed conv / linear layouts and ragged sizes."""
+    eng = pkg("engine")
+    torch.manual_seed(11)
+    mods = nn.ModuleList([nn.Conv2d(64, 128, 3), nn.ConvTranspose2d(128, 64, 4, 2, 1), nn.Linear(200, 72, bias=False),
+                          nn.Conv2d(8, 24, (1, 4)), nn.ConvTranspose2d(96, 40, (6, 1), (6, 1)),
+                          nn.Conv2d(1, 32, (4, 1))]).cuda()
+    layers = [eng.GemmLayer("conv", mods[0].weight, None, (3, 3), (1, 1), (1, 1)),
+              eng.GemmLayer("convT", mods[1].weight, None, (4, 4), (2, 2), (1, 1)),
+              eng.GemmLayer("linear", mods[2].weight),
+              eng.GemmLayer("conv", mods[3].weight, None, (1, 4), (1, 2), (0, 1)),
+              eng.GemmLayer("convT", mods[4].weight, None, (6, 1), (6, 1), (0, 0)),
+              eng.GemmLayer("conv", mods[5].weight, None, (4, 1), (2, 1), (1, 0))]
+    flat = eng.flatten(mods)
+    want = [(l.w_fwd().clone(), l.w_dgrad().clone()) for l in layers]
+    plan = eng.PackPlan(flat)
+    assert len(plan.items) == 2 * len(layers) and plan.valid()
+    for l in layers:
+        l._wf.zero_()
+        l._wd.zero_()
+    plan.run()
+    torch.cuda.synchronize()
+    for l, (wf, wd) in zip(layers, want):
+        assert torch.equal(l._wf, wf) and torch.equal(l._wd, wd)
+        assert l._wf_key == l._key() and l._wd_key == l._key()
+    # after an optimiser step the plan refreshes the same buffers in place
+    flat.attach_grads()
+    flat.grad.normal_()
+    bufs = [(l._wf, l._wd) for l in layers]
+    eng.adam_step(flat, 0.01, 1)
+    for l, (bf, bd) in zip(layers, bufs):
+        assert l.w_fwd() is bf and l.w_dgrad() is bd
+        ref_f = l._pack(l.Cout, l.Cin, l.f_src, l.f_perm)
+        ref_d = l._pack(l.Cin, l.Cout, l.d_src, l.d_perm)
+        assert torch.equal(bf, ref_f) and torch.equal(bd, ref_d)

@@ -1,4 +1,9 @@
-"""Turn an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-kernel share table (markdown)."""
+"""Turn an `ncu --metrics gpu__time_duration.sum --csv` launch list into a per-kernel share table (markdown).
+
+usage: summarize_launches.py launches.csv out.md [title [delimiter-kernel k]]
+With a delimiter (e.g. `adam_kernel 4`) only the launches after its (k-1)-th and up to its k-th occurrence are kept: one
+whole step of a multi-step capture.
+"""
 import collections
 import csv
 import re
@@ -10,7 +15,12 @@ lines = [l for l in open(src) if not l.startswith("==")]
 agg = collections.defaultdict(lambda: [0.0, 0])
 tot = 0.0
 n = 0
-for row in csv.DictReader(lines):
+rows = list(csv.DictReader(lines))
+if len(sys.argv) > 5:
+    delim, k = sys.argv[4], int(sys.argv[5])
+    hits = [i for i, r in enumerate(rows) if delim in r.get("Kernel Name", "")]
+    rows = rows[hits[k - 2] + 1:hits[k - 1] + 1]
+for row in rows:
     try:
         t = float(row["Metric Value"].replace(",", ""))
     except (ValueError, KeyError):
