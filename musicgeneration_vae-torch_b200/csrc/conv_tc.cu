@@ -139,6 +139,10 @@ struct alignas(64) ConvTcParams {
   void* stats;                      // fused InstanceNorm statistics (see bvae_conv_desc.stats) or null
   int OH, OW, y_pitch, osy, osx, ooy, oox, add_pitch, mask_pitch, act, out_f32;
   float slope, mask_slope;
+  // halo mode (stride-1 multi-tap layers with resident weights): ONE activation tile with its halo is loaded per
+  // (output tile, K chunk) and every tap reads it through a row-shifted shared-memory descriptor
+  int halo, halo_x0, halo_y0, halo_rows, halo_stage, halo_stages;
+  int halo_shift[BVAE_MAX_TAPS];
 };
 
 // Column reduction over the 32 rows a warp holds (one row per lane, 32 columns per lane): butterfly in which every
@@ -337,6 +341,9 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
   uint64_t* tempty = tfull + 2;               // [2]
   uint64_t* bres_bar = tempty + 2;
   uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
+  const bool halo = BRES && KB == 64 && p.halo;
+  const uint32_t nst = halo ? (uint32_t)p.halo_stages : (uint32_t)STAGES;      // ring depth / stage size in use
+  const uint32_t stage_bytes = halo ? (uint32_t)p.halo_stage : (uint32_t)STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -358,14 +365,14 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
-    const uint32_t tx = (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + (BRES ? 0 : B_BYTES));
+    const uint32_t tx = halo ? (uint32_t)(p.halo_rows * KB * 2) : (uint32_t)(p.bn * p.bh * p.bw * KB * 2 + (BRES ? 0 : B_BYTES));
     if (BRES) {
       mbar_expect_tx(bres_bar, (uint32_t)(p.ntaps * p.kchunks * B_BYTES));
       for (int t = 0; t < p.ntaps; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_2d(bres + (t * p.kchunks + kc) * B_BYTES, &p.bmap, bres_bar, t * p.C + kc * KB, 0);
     }
-    uint32_t it = 0;
+    uint32_t s = 0, par = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
@@ -374,23 +381,31 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       const int tw = m_tile % p.tiles_w; m_tile /= p.tiles_w;
       const int th = m_tile % p.tiles_h;
       const int tn = m_tile / p.tiles_h;
+      if (halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(empty_bar + s, par ^ 1u);
+          mbar_expect_tx(full_bar + s, tx);
+          tma_load_4d(smem + s * stage_bytes, &p.amap[0], full_bar + s, kc * KB, p.halo_x0, th * p.bh + p.halo_y0, tn);
+          if (++s == nst) { s = 0; par ^= 1u; }
+        }
+        continue;
+      }
       for (int t = p.ph_tap0[ph]; t < p.ph_tap0[ph] + p.ph_ntaps[ph]; ++t) {
         const CUtensorMap* am = &p.amap[p.tap_view[t]];
         const int cw = tw * p.bw + p.tap_ex[t], ch = th * p.bh + p.tap_ey[t], cn = tn * p.bn;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t par = (it / STAGES) & 1u;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
           mbar_wait(empty_bar + s, par ^ 1u);
           mbar_expect_tx(full_bar + s, tx);
-          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sa = smem + s * stage_bytes;
           tma_load_4d(sa, am, full_bar + s, kc * KB, cw, ch, cn);
           if (!BRES) tma_load_2d(sa + A_BYTES, &p.bmap, full_bar + s, t * p.C + kc * KB, n_tile * BN);
+          if (++s == nst) { s = 0; par ^= 1u; }
         }
       }
     }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
-    uint32_t it = 0, ti = 0;
+    uint32_t s = 0, par = 0, ti = 0;
     if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
@@ -401,17 +416,37 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       const int phase = (rest % p.nphase + rest / p.nphase) % p.nphase;
       const int KT = p.ph_ntaps[phase] * p.kchunks;
       const uint32_t bres0 = smem_u32(bres) + (uint32_t)(p.ph_tap0[phase] * p.kchunks) * B_BYTES;
-      for (int kb = 0; kb < KT; ++kb, ++it) {
-        const uint32_t s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1u;
-        mbar_wait(full_bar + s, ph);
+      if (halo) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(full_bar + s, par);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          for (int t = 0; t < p.ntaps; ++t) {
+            // tap t = the same tile, p.halo_shift[t] pixel rows (128 B each) further on.  Measured on B200: the 128B
+            // swizzle XOR is taken from the absolute shared-memory address bits [7,10) - exactly how TMA wrote the
+            // tile - so a start address that is not 1024-byte aligned needs NO descriptor base offset (setting
+            // (addr >> 7) & 7 there gives wrong results).
+            const uint64_t adesc = make_sdesc(sa + (uint32_t)p.halo_shift[t] * 128u, 16, SBO, LAYOUT);
+            const uint64_t bdesc = make_sdesc(bres0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, SBO, LAYOUT);
+#pragma unroll
+            for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kc | t | j) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);
+          if (++s == nst) { s = 0; par ^= 1u; }
+        }
+        umma_commit(tfull + ab);
+        continue;
+      }
+      for (int kb = 0; kb < KT; ++kb) {
+        mbar_wait(full_bar + s, par);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t sa = smem_u32(smem + s * stage_bytes);
         const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
         const uint64_t bdesc = make_sdesc(BRES ? bres0 + (uint32_t)kb * B_BYTES : sa + A_BYTES, 16, SBO, LAYOUT);
 #pragma unroll
         for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kb | j) ? 1u : 0u);
         umma_commit(empty_bar + s);
+        if (++s == nst) { s = 0; par ^= 1u; }
       }
       umma_commit(tfull + ab);
     }
@@ -882,9 +917,10 @@ template <int KB, int BN, bool BRES>
 static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t stream) {
   constexpr int B_BYTES = BN * KB * 2;
   constexpr int STAGE = BRES ? 128 * KB * 2 : 128 * KB * 2 + B_BYTES;
-  constexpr int BUDGET = BRES ? 100 * 1024 : 200 * 1024;        // resident weights take up to 96 KB of their own
+  constexpr int BUDGET = BRES ? 128 * 1024 : 200 * 1024;        // resident weights take up to 72 KB of their own
   constexpr int ST_RAW = BUDGET / STAGE;
-  constexpr int STAGES = ST_RAW > 8 ? 8 : ST_RAW;
+  // small-channel layers are bound by the bytes in flight per SM (8 KB stages): give them a deep ring
+  constexpr int STAGES = ST_RAW > 16 ? 16 : ST_RAW;
   const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 16;
   static int attr_smem = 0;
   static int num_sms = 148;
@@ -904,8 +940,52 @@ static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t str
 template <int KB, int BN>
 static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) {
   // weights resident in shared memory when one N tile covers Cout and all taps fit in 96 KB
-  const bool bres = P.n_tiles == 1 && (long)P.ntaps * P.kchunks * (BN * KB * 2) <= 96 * 1024 && tiles >= 2 * 148;
+  const bool bres = P.n_tiles == 1 && (long)P.ntaps * P.kchunks * (BN * KB * 2) <= 72 * 1024 && tiles >= 2 * 148;
   return bres ? launch_conv2_impl<KB, BN, true>(P, tiles, stream) : launch_conv2_impl<KB, BN, false>(P, tiles, stream);
+}
+
+// BVAE_CONV_HALO: 0 = off, 1 = on (default)
+static int conv_halo_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_CONV_HALO"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+// Halo mode applies to single-phase stride-1 layers whose weights stay resident (see launch_conv2): the output tile is
+// RH image rows of the PADDED width PW = QW + (dx_max - dx_min), flattened, so that tap (dy, dx) is the same smem tile
+// shifted by (dy - dy_min) * PW + (dx - dx_min) rows.  Output rows that fall on padding columns are discarded.
+static int plan_halo(const bvae_conv_desc* d, ConvTcParams* P, int KB, int BN) {
+  const int mode = conv_halo_mode();
+  if (mode == 0 || use_conv_v1_flag() || KB != 64 || P->nphase != 1 || d->sy != 1 || d->sx != 1 || d->osy != 1 || d->osx != 1 ||
+      P->n_tiles != 1 || d->ntaps < 4 || d->stats)
+    return BVAE_OK;
+  if ((long)d->ntaps * P->kchunks * (BN * KB * 2) > 72 * 1024) return BVAE_OK;
+  int dy0 = d->dy[0], dy1 = d->dy[0], dx0 = d->dx[0], dx1 = d->dx[0];
+  for (int t = 1; t < d->ntaps; ++t) {
+    dy0 = d->dy[t] < dy0 ? d->dy[t] : dy0; dy1 = d->dy[t] > dy1 ? d->dy[t] : dy1;
+    dx0 = d->dx[t] < dx0 ? d->dx[t] : dx0; dx1 = d->dx[t] > dx1 ? d->dx[t] : dx1;
+  }
+  const int QH = P->ph_QH[0], QW = P->ph_QW[0];
+  const int PW = QW + (dx1 - dx0);
+  if (PW > 128) return BVAE_OK;
+  int RH = 128 / PW;
+  if (RH > QH) RH = QH;
+  const int rows = (RH + dy1 - dy0) * PW;
+  int reach = 128 + (dy1 - dy0) * PW + (dx1 - dx0);          // rows the shifted descriptors can touch
+  if (reach < rows) reach = rows;
+  const int stage = ((reach * 128 + 1023) / 1024) * 1024;
+  const long tiles = (long)d->N * ceil_div(QH, RH);
+  if (RH + dy1 - dy0 > 256 || QW * RH * 10 < 128 * 8 || stage > 64 * 1024 || tiles < 2 * 148) return BVAE_OK;
+  int rc = make_view_map(&P->amap[0], d->x, d->C, d->W, d->H, d->N, d->x_pitch, (int64_t)d->W * d->x_pitch,
+                         (int64_t)d->H * d->W * d->x_pitch, KB, PW, RH + dy1 - dy0, 1, true);
+  if (rc) return rc;
+  P->halo = 1;
+  P->halo_x0 = dx0; P->halo_y0 = dy0; P->halo_rows = rows; P->halo_stage = stage;
+  P->halo_stages = (128 * 1024) / stage;                     // the BRES ring region (see launch_conv2_impl)
+  for (int t = 0; t < d->ntaps; ++t) P->halo_shift[t] = (d->dy[t] - dy0) * PW + (d->dx[t] - dx0);
+  P->bw = PW; P->bh = RH; P->bn = 1;
+  P->tiles_w = 1; P->tiles_h = ceil_div(QH, RH); P->tiles_n = d->N;
+  return BVAE_OK;
 }
 
 static bool use_conv_v1() {
@@ -960,6 +1040,8 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   P.OH = d->OH; P.OW = d->OW; P.y_pitch = d->y_pitch; P.osy = d->osy; P.osx = d->osx; P.ooy = d->ooy; P.oox = d->oox;
   P.add_pitch = d->add_pitch; P.mask_pitch = d->mask_pitch; P.act = d->act; P.out_f32 = d->out_f32;
   P.slope = d->slope; P.mask_slope = d->mask_slope;
+  rc = plan_halo(d, &P, KB, BN);
+  if (rc) return rc;
   const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles * P.nphase;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "conv_tc: grid too large");
   BVAE_REQUIRE(P.nphase == 1 || !use_conv_v1(), BVAE_ERR_UNSUPPORTED, "conv_tc: multi-phase needs the persistent kernel");

@@ -64,6 +64,11 @@ BIG_LAYERS = [
     ("convT", 128, 64, (3, 3), (2, 2), (1, 1), (1, 1), 48, 30, 2),           # decoder.layers.3.deConv2
     ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 48, 30, 4),             # encoder.layers.0
     ("conv", 32, 32, (1, 4), (1, 2), (0, 1), (0, 0), 192, 60, 2),            # phrase stem (KB = 32, SWIZZLE_64B)
+    # halo mode (one shared-memory tile per output tile, taps = row-shifted descriptors; needs >= 296 tiles)
+    ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 48, 30, 26),            # padded width 32, 4 rows per tile
+    ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 20, 60, 30),            # padded width 62, 2 rows per tile
+    ("conv", 64, 64, (3, 3), (1, 1), (1, 1), (0, 0), 21, 13, 100),           # ragged: width 15, 8 rows, H % 8 != 0
+    ("conv", 64, 64, (1, 4), (1, 1), (0, 1), (0, 0), 40, 30, 30),            # asymmetric taps, output narrower than input
 ]
 
 
