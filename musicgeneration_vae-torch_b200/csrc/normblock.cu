@@ -52,16 +52,26 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
   load8<F32>(y, base + c0, shift);
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
-  for (int p = p_begin + warp * gpw + grp; p < p_end; p += 8 * gpw) {
-    float v[8];
-    load8<F32>(y, base + (int64_t)p * pitch + c0, v);
+  constexpr int U = 2;                           // pixels per trip: their loads are issued before the first use
+  for (int pb = p_begin + warp * gpw + grp; pb < p_end; pb += 8 * gpw * U) {
+    float v[U][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float dlt = v[i] - shift[i];
-      sum[i] += dlt;
-      sq[i] += dlt * dlt;
-      if (v[i] > vmx[i]) { vmx[i] = v[i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
-      if (v[i] < vmn[i]) { vmn[i] = v[i]; imn[i] = p; }
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * 8 * gpw;
+      if (p < p_end) load8<F32>(y, base + (int64_t)p * pitch + c0, v[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + u * 8 * gpw;
+      if (p >= p_end) break;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dlt = v[u][i] - shift[i];
+        sum[i] += dlt;
+        sq[i] += dlt * dlt;
+        if (v[u][i] > vmx[i]) { vmx[i] = v[u][i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
+        if (v[u][i] < vmn[i]) { vmn[i] = v[u][i]; imn[i] = p; }
+      }
     }
   }
 #pragma unroll
@@ -269,58 +279,71 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
   }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ybase = (int64_t)n * HW * y_pitch, ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch;
-  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
-    const int p = pb + grp;
-    const bool valid = p < p_end;
-    float sum = 0.f, mx = -INFINITY;
-    int mxc = 0;
-    if (valid) {
+  constexpr int U = ITERS == 1 ? 2 : 1;          // pixels per lane group and trip (loads first, then math)
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw * U) {
+    float vv[U][ITERS][8];
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int c = (it * G + sub) * 8;
-        const float* p_mean = (ITERS == 1) ? h_mean : (s_mean + c);
-        const float* p_rstd = (ITERS == 1) ? h_rstd : (s_rstd + c);
-        const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
-        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
-        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
-        float v[8], uh[8];
-        load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + grp + u * 8 * gpw;
+      if (p < p_end) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) uh[i] = (v[i] - p_mean[i]) * p_rstd[i];
-        stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
-        if (has_cbam) {
-          if (fused) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (v[i] == s_yext[c + i] && p < nc_idx[(int64_t)n * C + c + i])            // (a stale read only costs an atomic)
-                atomicMin(&nc_idx[(int64_t)n * C + c + i], p);                              // first index wins
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float u1 = (p_a[i] * v[i] + p_b[i]) * p_gc[i];
-            sum += u1;
-            if (u1 > mx) { mx = u1; mxc = c + i; }
-          }
-        } else {
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = act_fwd(p_a[i] * v[i] + p_b[i], slope);
-          stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
-        }
+        for (int it = 0; it < ITERS; ++it) load8<F32>(y, ybase + (int64_t)p * y_pitch + (it * G + sub) * 8, vv[u][it]);
       }
     }
-    if (has_cbam) {
-      for (int o = G >> 1; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
-        const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
-        if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + grp + u * 8 * gpw;
+      const bool valid = p < p_end;
+      float sum = 0.f, mx = -INFINITY;
+      int mxc = 0;
+      if (valid) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          const float* p_mean = (ITERS == 1) ? h_mean : (s_mean + c);
+          const float* p_rstd = (ITERS == 1) ? h_rstd : (s_rstd + c);
+          const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
+          const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+          const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
+          const float* v = vv[u][it];
+          float uh[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) uh[i] = (v[i] - p_mean[i]) * p_rstd[i];
+          stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
+          if (has_cbam) {
+            if (fused) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (v[i] == s_yext[c + i] && p < nc_idx[(int64_t)n * C + c + i])            // (a stale read only costs an atomic)
+                  atomicMin(&nc_idx[(int64_t)n * C + c + i], p);                              // first index wins
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float u1 = (p_a[i] * v[i] + p_b[i]) * p_gc[i];
+              sum += u1;
+              if (u1 > mx) { mx = u1; mxc = c + i; }
+            }
+          } else {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = act_fwd(p_a[i] * v[i] + p_b[i], slope);
+            stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
+          }
+        }
       }
-      if (valid && sub == 0) {
-        const int64_t o = (int64_t)n * HW + p;
-        sa[o * 2] = sum / (float)C;
-        sa[o * 2 + 1] = mx;
-        cidx[o] = mxc;
+      if (has_cbam) {
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+          const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+          if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+        }
+        if (valid && sub == 0) {
+          const int64_t o = (int64_t)n * HW + p;
+          sa[o * 2] = sum / (float)C;
+          sa[o * 2 + 1] = mx;
+          cidx[o] = mxc;
+        }
       }
     }
   }
@@ -393,27 +416,47 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ 
   }
   const int p0 = blockIdx.x * ppc, p_end = min(HW, p0 + ppc);
   const int64_t ybase = (int64_t)n * HW * y_pitch, obase = (int64_t)n * HW * out_pitch, rbase = (int64_t)n * HW * res_pitch;
-  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
-    const int p = pb + grp;
-    if (p >= p_end) continue;
-    const float g = gs[(int64_t)n * HW + p];
+  constexpr int U = ITERS == 1 ? 2 : 1;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw * U) {
+    float vv[U][ITERS][8], gq[U];
+    bf16x8 rr8[U][ITERS];
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int c = (it * G + sub) * 8;
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + grp + u * 8 * gpw;
+      gq[u] = 0.f;
+      if (p < p_end) {
+        gq[u] = gs[(int64_t)n * HW + p];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          load8<F32>(y, ybase + (int64_t)p * y_pitch + c, vv[u][it]);
+          if (res_mode == 2) rr8[u][it] = ldg8(res + rbase + (int64_t)p * res_pitch + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pb + grp + u * 8 * gpw;
+      if (p >= p_end) continue;
+      const float g = gq[u];
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = (it * G + sub) * 8;
         const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
         const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
         const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
-      float v[8], r[8], o[8];
-      load8<F32>(y, ybase + (int64_t)p * y_pitch + c, v);
-      if (res_mode == 2) unpack8(ldg8(res + rbase + (int64_t)p * res_pitch + c), r);
+        const float* v = vv[u][it];
+        float r[8], o[8];
+        if (res_mode == 2) unpack8(rr8[u][it], r);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float u = p_a[i] * v[i] + p_b[i];
-        const float cb = u * p_gc[i] * g;
-        const float rr = res_mode == 1 ? u : (res_mode == 2 ? r[i] : 0.f);
-        o[i] = act_fwd(rr + cb, slope);
+        for (int i = 0; i < 8; ++i) {
+          const float uu = p_a[i] * v[i] + p_b[i];
+          const float cb = uu * p_gc[i] * g;
+          const float rr = res_mode == 1 ? uu : (res_mode == 2 ? r[i] : 0.f);
+          o[i] = act_fwd(rr + cb, slope);
+        }
+        stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
       }
-      stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
     }
   }
 }
@@ -481,33 +524,57 @@ __global__ void __launch_bounds__(256) nb_bwd1_kernel(const bf16* __restrict__ d
   for (int it = 0; it < ITERS; ++it)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[it][i] = 0.f;
-  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
-    const int p = pb + grp;
-    const bool valid = p < p_end;
-    float dgs = 0.f, g = 0.f;
-    if (valid) {
-      g = gs[(int64_t)n * HW + p];
+  // U pixels per lane group and trip: all their 16-byte loads are issued before the first use (bytes in flight)
+  constexpr int U = ITERS == 1 ? 2 : 1;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw * U) {
+    int pp[U];
+    bool valid[U];
+    float gq[U];
+    bf16x8 ru[U][ITERS], ro[U][ITERS], rd[U][ITERS];
 #pragma unroll
-      for (int it = 0; it < ITERS; ++it) {
-        const int c = (it * G + sub) * 8;
-        const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
-        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
-        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
-        float uh[8], o[8], d[8];
-        unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
-        unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
-        unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
+    for (int u = 0; u < U; ++u) {
+      pp[u] = pb + grp + u * 8 * gpw;
+      valid[u] = pp[u] < p_end;
+      gq[u] = 0.f;
+      if (valid[u]) {
+        gq[u] = gs[(int64_t)n * HW + pp[u]];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
-          const float t = ds * (p_g[i] * uh[i] + p_b[i]);
-          dgs += t * p_gc[i];
-          acc[it][i] += t * g;
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          ru[u][it] = ldg8(uhat + ubase + (int64_t)pp[u] * C + c);
+          ro[u][it] = ldg8(out + obase + (int64_t)pp[u] * out_pitch + c);
+          rd[u][it] = ldg8(dout + dbase + (int64_t)pp[u] * dout_pitch + c);
         }
       }
     }
-    for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
-    if (valid && sub == 0) bwd_px[((int64_t)n * HW + p) * BP_W + BP_DQ] = dgs * g * (1.f - g);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = pp[u];
+      const float g = gq[u];
+      float dgs = 0.f;
+      if (valid[u]) {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
+          const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+          const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
+          float uh[8], o[8], d[8];
+          unpack8(ru[u][it], uh);
+          unpack8(ro[u][it], o);
+          unpack8(rd[u][it], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float ds = d[i] * (o[i] > 0.f ? 1.f : slope);
+            const float t = ds * (p_g[i] * uh[i] + p_b[i]);
+            dgs += t * p_gc[i];
+            acc[it][i] += t * g;
+          }
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (valid[u] && sub == 0) bwd_px[((int64_t)n * HW + p) * BP_W + BP_DQ] = dgs * g * (1.f - g);
+    }
   }
   flush_nc<ITERS>(acc, G, sub, grp, C, s_buf, bwd_nc + (int64_t)n * C * BN_W, BN_DGC);
 }
@@ -627,36 +694,57 @@ __global__ void __launch_bounds__(256, ITERS == 1 ? 2 : 1) nb_bwd2_kernel(const 
   for (int it = 0; it < ITERS; ++it)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a1[it][i] = 0.f; a2[it][i] = 0.f; a3[it][i] = 0.f; }
-  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
-    const int p = pb + grp;
-    if (p >= p_end) continue;
-    float g = 0.f, dmean = 0.f, dmax = 0.f;
-    int ci = -1;
-    if (has_cbam) {
-      const int64_t o = (int64_t)n * HW + p;
-      g = gs[o];
-      dmean = bwd_px[o * BP_W + BP_DMEAN] * invC;
-      dmax = bwd_px[o * BP_W + BP_DMAX];
-      ci = cidx[o];
+  constexpr int U = ITERS == 1 ? 2 : 1;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw * U) {
+    int pp[U], ciq[U];
+    bool valid[U];
+    float gq[U], dmeanq[U], dmaxq[U];
+    bf16x8 ru[U][ITERS], ro[U][ITERS], rd[U][ITERS];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pp[u] = pb + grp + u * 8 * gpw;
+      valid[u] = pp[u] < p_end;
+      gq[u] = 0.f; dmeanq[u] = 0.f; dmaxq[u] = 0.f; ciq[u] = -1;
+      if (valid[u]) {
+        if (has_cbam) {
+          const int64_t o = (int64_t)n * HW + pp[u];
+          gq[u] = gs[o];
+          dmeanq[u] = bwd_px[o * BP_W + BP_DMEAN] * invC;
+          dmaxq[u] = bwd_px[o * BP_W + BP_DMAX];
+          ciq[u] = cidx[o];
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          ru[u][it] = ldg8(uhat + ubase + (int64_t)pp[u] * C + c);
+          ro[u][it] = ldg8(out + obase + (int64_t)pp[u] * out_pitch + c);
+          rd[u][it] = ldg8(dout + dbase + (int64_t)pp[u] * dout_pitch + c);
+        }
+      }
     }
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int c = (it * G + sub) * 8;
-      const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
-      const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
-      const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
-      float uh[8], o[8], d[8], du[8], dsv[8], dspu[8];
-      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
-      unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
-      unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8<true>(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+    for (int u = 0; u < U; ++u) {
+      if (!valid[u]) continue;
+      const int p = pp[u];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        a1[it][i] += du[i];
-        a2[it][i] += du[i] * uh[i];
-        a3[it][i] += dspu[i];
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = (it * G + sub) * 8;
+        const float* p_g = (ITERS == 1) ? h_g : (s_g + c);
+        const float* p_b = (ITERS == 1) ? h_b : (s_b + c);
+        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
+        float uh[8], o[8], d[8], du[8], dsv[8], dspu[8];
+        unpack8(ru[u][it], uh);
+        unpack8(ro[u][it], o);
+        unpack8(rd[u][it], d);
+        nb_du8<true>(uh, o, d, c, p_g, p_b, p_gc, has_cbam, res_mode, slope, gq[u], dmeanq[u], dmaxq[u], ciq[u], du, dsv, dspu);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a1[it][i] += du[i];
+          a2[it][i] += du[i] * uh[i];
+          a3[it][i] += dspu[i];
+        }
+        if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * dres_pitch + c, pack8(dsv));
       }
-      if (res_mode == 2 && dres) stg8(dres + rbase + (int64_t)p * dres_pitch + c, pack8(dsv));
     }
   }
   float* dst = bwd_nc + (int64_t)n * C * BN_W;
@@ -803,38 +891,59 @@ __global__ void __launch_bounds__(256, ITERS == 1 ? 3 : 1) nb_bwd3_kernel(const 
   const int64_t ubase = (int64_t)n * HW * C, obase = (int64_t)n * HW * out_pitch, dbase = (int64_t)n * HW * dout_pitch;
   const int64_t ybase = (int64_t)n * HW * dy_pitch;
   const float invC = 1.f / (float)C;
-  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw) {
-    const int p = pb + grp;
-    if (p >= p_end) continue;
-    float g = 0.f, dmean = 0.f, dmax = 0.f;
-    int ci = -1;
-    if (has_cbam) {
-      const int64_t o = (int64_t)n * HW + p;
-      g = gs[o];
-      dmean = bwd_px[o * BP_W + BP_DMEAN] * invC;
-      dmax = bwd_px[o * BP_W + BP_DMAX];
-      ci = cidx[o];
+  constexpr int U = ITERS == 1 ? 2 : 1;
+  for (int pb = p0 + warp * gpw; pb < p_end; pb += 8 * gpw * U) {
+    int pp[U], ciq[U];
+    bool valid[U];
+    float gq[U], dmeanq[U], dmaxq[U];
+    bf16x8 ru[U][ITERS], ro[U][ITERS], rd[U][ITERS];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pp[u] = pb + grp + u * 8 * gpw;
+      valid[u] = pp[u] < p_end;
+      gq[u] = 0.f; dmeanq[u] = 0.f; dmaxq[u] = 0.f; ciq[u] = -1;
+      if (valid[u]) {
+        if (has_cbam) {
+          const int64_t o = (int64_t)n * HW + pp[u];
+          gq[u] = gs[o];
+          dmeanq[u] = bwd_px[o * BP_W + BP_DMEAN] * invC;
+          dmaxq[u] = bwd_px[o * BP_W + BP_DMAX];
+          ciq[u] = cidx[o];
+        }
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int c = (it * G + sub) * 8;
+          ru[u][it] = ldg8(uhat + ubase + (int64_t)pp[u] * C + c);
+          ro[u][it] = ldg8(out + obase + (int64_t)pp[u] * out_pitch + c);
+          rd[u][it] = ldg8(dout + dbase + (int64_t)pp[u] * dout_pitch + c);
+        }
+      }
     }
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-      const int c = (it * G + sub) * 8;
-      const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
-      const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
-      const float* p_m1 = (ITERS == 1) ? h_m1 : (s_m1 + c);
-      const float* p_m2 = (ITERS == 1) ? h_m2 : (s_m2 + c);
-      const float* p_dmx = (ITERS == 1) ? h_dmx : (s_dmx + c);
-      const int* p_idx = (ITERS == 1) ? h_idx : (s_idx + c);
-      float uh[8], o[8], d[8], du[8], dsv[8], dspu[8], r[8];
-      unpack8(ldg8(uhat + ubase + (int64_t)p * C + c), uh);
-      unpack8(ldg8(out + obase + (int64_t)p * out_pitch + c), o);
-      unpack8(ldg8(dout + dbase + (int64_t)p * dout_pitch + c), d);
-      nb_du8<false>(uh, o, d, c, p_gc, p_gc, p_gc, has_cbam, res_mode, slope, g, dmean, dmax, ci, du, dsv, dspu);
+    for (int u = 0; u < U; ++u) {
+      if (!valid[u]) continue;
+      const int p = pp[u];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float extra = (p == p_idx[i]) ? p_dmx[i] : 0.f;
-        r[i] = p_a[i] * du[i] + extra - p_m1[i] - uh[i] * p_m2[i];
+      for (int it = 0; it < ITERS; ++it) {
+        const int c = (it * G + sub) * 8;
+        const float* p_gc = (ITERS == 1) ? h_gc : (s_gc + c);
+        const float* p_a = (ITERS == 1) ? h_a : (s_a + c);
+        const float* p_m1 = (ITERS == 1) ? h_m1 : (s_m1 + c);
+        const float* p_m2 = (ITERS == 1) ? h_m2 : (s_m2 + c);
+        const float* p_dmx = (ITERS == 1) ? h_dmx : (s_dmx + c);
+        const int* p_idx = (ITERS == 1) ? h_idx : (s_idx + c);
+        float uh[8], o[8], d[8], du[8], dsv[8], dspu[8], r[8];
+        unpack8(ru[u][it], uh);
+        unpack8(ro[u][it], o);
+        unpack8(rd[u][it], d);
+        nb_du8<false>(uh, o, d, c, p_gc, p_gc, p_gc, has_cbam, res_mode, slope, gq[u], dmeanq[u], dmaxq[u], ciq[u], du, dsv, dspu);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float extra = (p == p_idx[i]) ? p_dmx[i] : 0.f;
+          r[i] = p_a[i] * du[i] + extra - p_m1[i] - uh[i] * p_m2[i];
+        }
+        stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
       }
-      stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
     }
   }
 }
