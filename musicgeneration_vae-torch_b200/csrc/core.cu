@@ -79,31 +79,30 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const PackJobDev* __res
   const int r0 = (local / j.ctiles) * RT, c0 = (local % j.ctiles) * CT;
   const int nr = min(RT, j.R - r0), nc = min(CT, j.Cc - c0), T = j.T;
   const float* src = j.src + r0 * j.sr + c0 * j.sc;
-  const int total = nr * nc * T;
-  if (j.sr <= j.sc) {
-    for (int e = threadIdx.x; e < total; e += 256) {
-      const int tp = e % T, r = (e / T) % nr, c = e / (T * nr);
-      tile[(r * T + tp) * LD + c] = f2bf(src[r * j.sr + c * j.sc + j.perm[tp]]);
-    }
-  } else {
-    for (int e = threadIdx.x; e < total; e += 256) {
-      const int tp = e % T, c = (e / T) % nc, r = e / (T * nc);
-      tile[(r * T + tp) * LD + c] = f2bf(src[r * j.sr + c * j.sc + j.perm[tp]]);
+  // every thread owns (row, column) pairs and walks their T taps (T consecutive floats): no integer divisions, and a
+  // warp covers a contiguous run of the source in whichever of r / c is the faster source dimension
+#pragma unroll
+  for (int k = 0; k < RT * CT / 256; ++k) {
+    const int e = threadIdx.x + 256 * k;
+    const int r = (j.sr <= j.sc) ? (e & (RT - 1)) : (e / CT);
+    const int c = (j.sr <= j.sc) ? (e / RT) : (e & (CT - 1));
+    if (r < nr && c < nc) {
+      const float* sp = src + r * j.sr + c * j.sc;
+      bf16* tp_ = tile + (r * T) * LD + c;
+      for (int tp = 0; tp < T; ++tp) tp_[tp * LD] = f2bf(sp[j.perm[tp]]);
     }
   }
   __syncthreads();
-  if (nc == CT && (j.Cc & 1) == 0 && (j.dst_pitch & 1) == 0) {
-    for (int e = threadIdx.x; e < nr * T * (CT / 2); e += 256) {
-      const int c2 = e % (CT / 2), row = e / (CT / 2);
-      const int tp = row % T, r = row / T;
-      *reinterpret_cast<uint32_t*>(j.dst + (int64_t)(r0 + r) * j.dst_pitch + (int64_t)tp * j.Cc + c0 + 2 * c2) =
-          *reinterpret_cast<const uint32_t*>(tile + row * LD + 2 * c2);
-    }
-  } else {
-    for (int e = threadIdx.x; e < nr * T * nc; e += 256) {
-      const int c = e % nc, row = e / nc;
-      const int tp = row % T, r = row / T;
-      j.dst[(int64_t)(r0 + r) * j.dst_pitch + (int64_t)tp * j.Cc + c0 + c] = tile[row * LD + c];
+  const int rr = threadIdx.x >> 5, c2 = threadIdx.x & 31;        // warp = tile row r, lane = channel pair
+  if (rr < nr) {
+    bf16* drow = j.dst + (int64_t)(r0 + rr) * j.dst_pitch + c0;
+    if (nc == CT && (j.Cc & 1) == 0 && (j.dst_pitch & 1) == 0) {
+      for (int tp = 0; tp < T; ++tp)
+        *reinterpret_cast<uint32_t*>(drow + (int64_t)tp * j.Cc + 2 * c2) =
+            *reinterpret_cast<const uint32_t*>(tile + (rr * T + tp) * LD + 2 * c2);
+    } else {
+      for (int tp = 0; tp < T; ++tp)
+        for (int c = c2; c < nc; c += 32) drow[(int64_t)tp * j.Cc + c] = tile[(rr * T + tp) * LD + c];
     }
   }
 }

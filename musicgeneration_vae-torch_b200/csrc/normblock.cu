@@ -53,16 +53,18 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
   constexpr int U = 2;                           // pixels per trip: their loads are issued before the first use
-  for (int pb = p_begin + warp * gpw + grp; pb < p_end; pb += 8 * gpw * U) {
+  const int step = 8 * gpw;
+  const int64_t sy = (int64_t)step * pitch;
+  int64_t off = base + (int64_t)(p_begin + warp * gpw + grp) * pitch + c0;
+  for (int pb = p_begin + warp * gpw + grp; pb < p_end; pb += step * U, off += sy * U) {
     float v[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int p = pb + u * 8 * gpw;
-      if (p < p_end) load8<F32>(y, base + (int64_t)p * pitch + c0, v[u]);
+      if (pb + u * step < p_end) load8<F32>(y, off + u * sy, v[u]);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int p = pb + u * 8 * gpw;
+      const int p = pb + u * step;
       if (p >= p_end) break;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -458,6 +460,138 @@ __global__ void __launch_bounds__(256) nb_apply_kernel(const void* __restrict__ 
         stg8(out + obase + (int64_t)p * out_pitch + c, pack8(o));
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast forward sweeps for C <= 256 (same restructuring as the nbf_bwd* kernels below: template variants, pointer
+// strides, folded per-channel constants).  uhat = v*rstd - mean*rstd, u*gc = v*(a*gc) + b*gc.
+// ---------------------------------------------------------------------------------------------------
+template <bool F32, bool CBAM>
+__global__ void __launch_bounds__(256, 3) nbf_pool_kernel(const void* __restrict__ y, int y_pitch, int HW, int C,
+                                                          const float* __restrict__ nc, float slope,
+                                                          bf16* __restrict__ uhat, bf16* __restrict__ out, int out_pitch,
+                                                          float* __restrict__ sa, int32_t* __restrict__ cidx, int ppc) {
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_r[8], h_nm[8], h_a[8], h_b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4* q = reinterpret_cast<const float4*>(nc + ((int64_t)n * C + c + i) * NC_W);
+    const float4 lo = __ldg(q);                      // {mean, rstd, a, b}
+    const float gc = CBAM ? __ldg(q + 1).x : 1.f;    // {gc, ...}
+    h_r[i] = lo.y; h_nm[i] = -lo.x * lo.y;
+    h_a[i] = lo.z * gc; h_b[i] = lo.w * gc;
+  }
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  int64_t yo = q0 * y_pitch + c;
+  bf16* pu = uhat + q0 * C + c;
+  bf16* po = CBAM ? nullptr : out + q0 * out_pitch + c;
+  float2* psa = reinterpret_cast<float2*>(sa) + q0;
+  int32_t* pci = cidx + q0;
+  const int64_t sy = (int64_t)step * y_pitch, su = (int64_t)step * C, so = (int64_t)step * out_pitch;
+  const float invC = 1.f / (float)C;
+  for (; p < p_end + grp; p += 2 * step) {            // "+ grp": all lanes of a warp run the same trips (shuffles)
+    const bool vld[2] = {p < p_end, p + step < p_end};
+    float v[2][8];
+    if (vld[0]) load8<F32>(y, yo, v[0]);
+    if (vld[1]) load8<F32>(y, yo + sy, v[1]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float sum = 0.f, mx = -INFINITY;
+      int mxc = 0;
+      if (vld[u]) {
+        float uh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uh[i] = fmaf(v[u][i], h_r[i], h_nm[i]);
+        stg8(pu + u * su, pack8(uh));
+        if (CBAM) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float u1 = fmaf(h_a[i], v[u][i], h_b[i]);
+            sum += u1;
+            if (u1 > mx) { mx = u1; mxc = c + i; }
+          }
+        } else {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = act_fwd(fmaf(h_a[i], v[u][i], h_b[i]), slope);
+          stg8(po + u * so, pack8(o));
+        }
+      }
+      if (CBAM) {
+        for (int o = G >> 1; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+          const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+          if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+        }
+        if (vld[u] && sub == 0) {
+          psa[u * step] = make_float2(sum * invC, mx);
+          pci[u * step] = mxc;
+        }
+      }
+    }
+    yo += 2 * sy; pu += 2 * su; psa += 2 * step; pci += 2 * step;
+    if (!CBAM) po += 2 * so;
+  }
+}
+
+// out = act(r + u*gc*gs),  r = u (MODE 1) | res (MODE 2) | 0 (MODE 3)
+template <bool F32, int MODE>
+__global__ void __launch_bounds__(256, 3) nbf_apply_kernel(const void* __restrict__ y, int y_pitch, int HW, int C,
+                                                           const float* __restrict__ nc, const bf16* __restrict__ res,
+                                                           int res_pitch, float slope, bf16* __restrict__ out,
+                                                           int out_pitch, const float* __restrict__ gs, int ppc) {
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_a[8], h_b[8], h_gc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4* q = reinterpret_cast<const float4*>(nc + ((int64_t)n * C + c + i) * NC_W);
+    const float4 lo = __ldg(q);                      // {mean, rstd, a, b}
+    h_a[i] = lo.z; h_b[i] = lo.w; h_gc[i] = __ldg(q + 1).x;
+  }
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  int64_t yo = q0 * y_pitch + c;
+  bf16* po = out + q0 * out_pitch + c;
+  const bf16* pr = MODE == 2 ? res + q0 * res_pitch + c : nullptr;
+  const float* pg = gs + q0;
+  const int64_t sy = (int64_t)step * y_pitch, so = (int64_t)step * out_pitch, sr = (int64_t)step * res_pitch;
+  for (; p < p_end; p += 2 * step) {
+    const bool v1 = p + step < p_end;
+    float v[2][8], g[2];
+    bf16x8 rr[2];
+    load8<F32>(y, yo, v[0]);
+    g[0] = pg[0];
+    if (MODE == 2) rr[0] = ldg8(pr);
+    if (v1) {
+      load8<F32>(y, yo + sy, v[1]);
+      g[1] = pg[step];
+      if (MODE == 2) rr[1] = ldg8(pr + sr);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u && !v1) break;
+      float r[8], o[8];
+      if (MODE == 2) unpack8(rr[u], r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float uu = fmaf(h_a[i], v[u][i], h_b[i]);
+        const float k = h_gc[i] * g[u];
+        const float t = MODE == 1 ? fmaf(uu, k, uu) : (MODE == 2 ? fmaf(uu, k, r[i]) : uu * k);
+        o[i] = act_fwd(t, slope);
+      }
+      stg8(po + u * so, pack8(o));
+    }
+    yo += 2 * sy; po += 2 * so; pg += 2 * step;
+    if (MODE == 2) pr += 2 * sr;
   }
 }
 
@@ -945,6 +1079,276 @@ __global__ void __launch_bounds__(256, ITERS == 1 ? 3 : 1) nb_bwd3_kernel(const 
         stg8(dy + ybase + (int64_t)p * dy_pitch + c, pack8(r));
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast tiled backward kernels for C <= 256 (one 8-channel vector per lane, G = C/8 lanes per pixel).  Same
+// mathematics as nb_bwd1/2/3_kernel, restructured for instruction count: the variant (MODE = 0 plain, else the
+// CBAM residual mode 1..3) is a template parameter, every stream is a pointer advanced by a constant stride, the
+// per-channel constants are folded (a*gc, a*m1, a*m2, ...) so the dense part is 2-4 FMAs per element, and the two
+// sparse terms (arg-max channel of a pixel, arg-max pixel of a channel) stay out of the dense expression.
+// ---------------------------------------------------------------------------------------------------
+// ds = dout * act'(out): the sign of `out` is read from the raw bf16 bits (positive, non-zero <=> the word > 0)
+__device__ __forceinline__ void nbf_ds8(const bf16x8& rd, const bf16x8& ro, float slope, float* ds) {
+  const uint32_t dw[4] = {rd.x, rd.y, rd.z, rd.w};
+  const uint32_t ow[4] = {ro.x, ro.y, ro.z, ro.w};
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float dlo = __uint_as_float(dw[w] << 16), dhi = __uint_as_float(dw[w] & 0xffff0000u);
+    ds[2 * w] = ((int)(ow[w] << 16) > 0) ? dlo : dlo * slope;
+    ds[2 * w + 1] = ((int)ow[w] > 0xffff) ? dhi : dhi * slope;
+  }
+}
+
+struct NbfPix {
+  float g, dmean, dmx;        // spatial gate, d/d(mean_c) / C, dmean + d/d(max_c)
+  int k;                      // arg-max channel of this pixel minus the lane's first channel (matches i in [0, 8) or not)
+};
+
+template <int MODE>
+__device__ __forceinline__ NbfPix nbf_pix(const float* __restrict__ gs, const float4* __restrict__ px,
+                                          const int32_t* __restrict__ cidx, int64_t q, float invC, int c) {
+  NbfPix r;
+  r.g = 0.f; r.dmean = 0.f; r.dmx = 0.f; r.k = -1;
+  if (MODE) {
+    r.g = gs[q];
+    const float4 v = px[q];               // {dq, dmean, dmax, -}
+    r.dmean = v.y * invC;
+    r.dmx = r.dmean + v.z;
+    r.k = cidx[q] - c;
+  }
+  return r;
+}
+
+// backward 1 (CBAM only): dgs[p] = sum_c ds*u*gc -> dq ; dgc[n,c] += sum_p ds*u*gs
+__global__ void __launch_bounds__(256, 3) nbf_bwd1_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                          const bf16* __restrict__ out, int out_pitch,
+                                                          const bf16* __restrict__ uhat, int HW, int C,
+                                                          const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ gs,
+                                                          float slope, float* __restrict__ bwd_nc,
+                                                          float* __restrict__ bwd_px, int ppc) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_g[8], h_b[8], h_gc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h_g[i] = __ldg(gamma + c + i);
+    h_b[i] = __ldg(beta + c + i);
+    h_gc[i] = __ldg(nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
+  }
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  const bf16* pu = uhat + q0 * C + c;
+  const bf16* po = out + q0 * out_pitch + c;
+  const bf16* pd = dout + q0 * dout_pitch + c;
+  const float* pg = gs + q0;
+  float* pq = bwd_px + q0 * BP_W + BP_DQ;
+  const int64_t su = (int64_t)step * C, so = (int64_t)step * out_pitch, sd = (int64_t)step * dout_pitch;
+  float acc[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = 0.f;
+  for (; p < p_end + grp; p += 2 * step) {           // "+ grp": every lane of the warp runs the same trips (shuffles)
+    const bool v0 = p < p_end, v1 = p + step < p_end;
+    bf16x8 ru[2], ro[2], rd[2];
+    float g[2] = {0.f, 0.f};
+    if (v0) { ru[0] = ldg8(pu); ro[0] = ldg8(po); rd[0] = ldg8(pd); g[0] = pg[0]; }
+    if (v1) { ru[1] = ldg8(pu + su); ro[1] = ldg8(po + so); rd[1] = ldg8(pd + sd); g[1] = pg[step]; }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool v = u ? v1 : v0;
+      float dgs = 0.f;
+      if (v) {
+        float uh[8], ds[8];
+        unpack8(ru[u], uh);
+        nbf_ds8(rd[u], ro[u], slope, ds);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float t = ds[i] * fmaf(h_g[i], uh[i], h_b[i]);
+          dgs = fmaf(t, h_gc[i], dgs);
+          acc[0][i] = fmaf(t, g[u], acc[0][i]);
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (v && sub == 0) pq[(int64_t)u * step * BP_W] = dgs * g[u] * (1.f - g[u]);
+    }
+    pu += 2 * su; po += 2 * so; pd += 2 * sd; pg += 2 * step; pq += (int64_t)2 * step * BP_W;
+  }
+  flush_nc<1>(acc, G, sub, grp, C, sm, bwd_nc + (int64_t)n * C * BN_W, BN_DGC);
+}
+
+// backward 2: per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u ; writes dres (MODE 2)
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) nbf_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                          const bf16* __restrict__ out, int out_pitch,
+                                                          const bf16* __restrict__ uhat, int HW, int C,
+                                                          const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ gs,
+                                                          const int32_t* __restrict__ cidx,
+                                                          const float* __restrict__ bwd_px, float slope,
+                                                          bf16* __restrict__ dres, int dres_pitch,
+                                                          float* __restrict__ bwd_nc, int ppc) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_g[8], h_b[8], h_gc[8];
+  if (MODE) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h_g[i] = __ldg(gamma + c + i);
+      h_b[i] = __ldg(beta + c + i);
+      h_gc[i] = __ldg(nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
+    }
+  }
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  const bf16* pu = uhat + q0 * C + c;
+  const bf16* po = out + q0 * out_pitch + c;
+  const bf16* pd = dout + q0 * dout_pitch + c;
+  bf16* pr = (MODE == 2 && dres) ? dres + q0 * dres_pitch + c : nullptr;
+  const float4* px4 = reinterpret_cast<const float4*>(bwd_px);
+  const int64_t su = (int64_t)step * C, so = (int64_t)step * out_pitch, sd = (int64_t)step * dout_pitch;
+  const int64_t sr = (int64_t)step * dres_pitch;
+  const float invC = 1.f / (float)C;
+  float a1[1][8], a2[1][8], a3[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a1[0][i] = 0.f; a2[0][i] = 0.f; a3[0][i] = 0.f; }
+  int64_t q = q0;
+  for (; p < p_end; p += 2 * step, q += 2 * step) {
+    const bool v1 = p + step < p_end;
+    bf16x8 ru[2], ro[2], rd[2];
+    NbfPix px[2];
+    ru[0] = ldg8(pu); ro[0] = ldg8(po); rd[0] = ldg8(pd);
+    px[0] = nbf_pix<MODE>(gs, px4, cidx, q, invC, c);
+    if (v1) {
+      ru[1] = ldg8(pu + su); ro[1] = ldg8(po + so); rd[1] = ldg8(pd + sd);
+      px[1] = nbf_pix<MODE>(gs, px4, cidx, q + step, invC, c);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u && !v1) break;
+      float uh[8], ds[8];
+      unpack8(ru[u], uh);
+      nbf_ds8(rd[u], ro[u], slope, ds);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a1[0][i] += ds[i];
+          a2[0][i] = fmaf(ds[i], uh[i], a2[0][i]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // du = ds*([direct] + gc*g) + gc*dsp ,  dsp = dmean (+ dmax on the pixel's arg-max channel)
+          const float dsp = (i == px[u].k) ? px[u].dmx : px[u].dmean;
+          const float k1 = MODE == 1 ? fmaf(h_gc[i], px[u].g, 1.f) : h_gc[i] * px[u].g;
+          const float du = fmaf(ds[i], k1, h_gc[i] * dsp);
+          a1[0][i] += du;
+          a2[0][i] = fmaf(du, uh[i], a2[0][i]);
+          a3[0][i] = fmaf(dsp, fmaf(h_g[i], uh[i], h_b[i]), a3[0][i]);
+        }
+        if (MODE == 2 && pr) stg8(pr + (int64_t)u * sr, pack8(ds));
+      }
+    }
+    pu += 2 * su; po += 2 * so; pd += 2 * sd;
+    if (MODE == 2 && pr) pr += 2 * sr;
+  }
+  float* dst = bwd_nc + (int64_t)n * C * BN_W;
+  flush_nc<1>(a1, G, sub, grp, C, sm, dst, BN_S1);
+  flush_nc<1>(a2, G, sub, grp, C, sm, dst, BN_S2);
+  if (MODE) flush_nc<1>(a3, G, sub, grp, C, sm, dst, BN_DGC);
+}
+
+// backward 4: dy = a*du + [p == argmax_p(c)] a*d_mx - a*m1 - uhat*a*m2
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) nbf_bwd3_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                          const bf16* __restrict__ out, int out_pitch,
+                                                          const bf16* __restrict__ uhat, int HW, int C,
+                                                          const float* __restrict__ nc,
+                                                          const int32_t* __restrict__ nc_idx,
+                                                          const float* __restrict__ gs, const int32_t* __restrict__ cidx,
+                                                          const float* __restrict__ bwd_px,
+                                                          const float* __restrict__ bwd_nc, float slope,
+                                                          bf16* __restrict__ dy, int dy_pitch, int ppc) {
+  extern __shared__ float sm[];
+  float* s_admx = sm;                     // a * d_mx per channel
+  int* s_idx = (int*)(sm + C);            // arg-max pixel per channel
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_a[8], h_ag[8], h_am1[8], h_am2[8];
+  int imin = 0x7fffffff, imax = -1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t o = (int64_t)n * C + c + i;
+    const float a = __ldg(nc + o * NC_W + NC_A);
+    const float4 bn = __ldg(reinterpret_cast<const float4*>(bwd_nc + o * BN_W));     // {-, S1 -> m1, S2 -> m2, d_mx}
+    h_a[i] = a;
+    h_ag[i] = MODE ? a * __ldg(nc + o * NC_W + NC_GC) : 0.f;
+    h_am1[i] = a * bn.y;
+    h_am2[i] = a * bn.z;
+    if (MODE) {
+      const int ix = __ldg(nc_idx + o);
+      imin = min(imin, ix); imax = max(imax, ix);
+      if (grp == 0 && warp == 0) { s_admx[c + i] = a * bn.w; s_idx[c + i] = ix; }
+    }
+  }
+  if (MODE) __syncthreads();
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  const bf16* pu = uhat + q0 * C + c;
+  const bf16* po = out + q0 * out_pitch + c;
+  const bf16* pd = dout + q0 * dout_pitch + c;
+  bf16* py = dy + q0 * dy_pitch + c;
+  const float4* px4 = reinterpret_cast<const float4*>(bwd_px);
+  const int64_t su = (int64_t)step * C, so = (int64_t)step * out_pitch, sd = (int64_t)step * dout_pitch;
+  const int64_t sy = (int64_t)step * dy_pitch;
+  const float invC = 1.f / (float)C;
+  int64_t q = q0;
+  for (; p < p_end; p += 2 * step, q += 2 * step) {
+    const bool v1 = p + step < p_end;
+    bf16x8 ru[2], ro[2], rd[2];
+    NbfPix px[2];
+    ru[0] = ldg8(pu); ro[0] = ldg8(po); rd[0] = ldg8(pd);
+    px[0] = nbf_pix<MODE>(gs, px4, cidx, q, invC, c);
+    if (v1) {
+      ru[1] = ldg8(pu + su); ro[1] = ldg8(po + so); rd[1] = ldg8(pd + sd);
+      px[1] = nbf_pix<MODE>(gs, px4, cidx, q + step, invC, c);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u && !v1) break;
+      float uh[8], ds[8], r[8];
+      unpack8(ru[u], uh);
+      nbf_ds8(rd[u], ro[u], slope, ds);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = fmaf(-uh[i], h_am2[i], fmaf(ds[i], h_a[i], -h_am1[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // a*du = ds*(a*[direct] + a*gc*g) + a*gc*dsp
+          const float dsp = (i == px[u].k) ? px[u].dmx : px[u].dmean;
+          const float k1 = MODE == 1 ? fmaf(h_ag[i], px[u].g, h_a[i]) : h_ag[i] * px[u].g;
+          r[i] = fmaf(-uh[i], h_am2[i], fmaf(ds[i], k1, fmaf(h_ag[i], dsp, -h_am1[i])));
+        }
+        const int pp = p + u * step;
+        if (pp >= imin && pp <= imax) {            // rare: this pixel is the arg-max of one of the lane's channels
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (pp == s_idx[c + i]) r[i] += s_admx[c + i];
+        }
+      }
+      stg8(py + (int64_t)u * sy, pack8(r));
+    }
+    pu += 2 * su; po += 2 * so; pd += 2 * sd; py += 2 * sy;
   }
 }
 
@@ -1866,6 +2270,13 @@ static int pick_ppc(int HW, int N, int G) {
   return ppc;
 }
 
+// BVAE_NB_FAST=0 selects the generic tiled backward kernels (kept as the reference implementation of the fast ones)
+static bool nb_fast_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_NB_FAST"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 static int validate(const bvae_nb_desc* d, const char* who) {
   BVAE_REQUIRE(d->C >= 32 && d->C <= 1024 && (d->C & (d->C - 1)) == 0, BVAE_ERR_SHAPE,
                "%s: C=%d must be a power of two in [32,1024]", who, d->C);
@@ -1956,16 +2367,28 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   const int ppc = pick_ppc(HW, N, G);
   dim3 g3(ceil_div(HW, ppc), N);
   const size_t sm3 = 6 * C * sizeof(float);
-  DISPATCH_ITERS(iters, {
-    if (d->y_f32)
-      nb_pool_kernel<true, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
-                                                      (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
-                                                      d->stats_fused, d->nc_idx);
-    else
-      nb_pool_kernel<false, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
-                                                       (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
-                                                       d->stats_fused, d->nc_idx);
-  });
+  const bool fast = iters == 1 && !d->stats_fused && nb_fast_enabled();
+#define NBF_POOL(F) do {                                                                                                  \
+    if (d->has_cbam) nbf_pool_kernel<F, true><<<g3, 256, 0, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->slope, (bf16*)d->uhat, \
+                                                                  (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);      \
+    else nbf_pool_kernel<F, false><<<g3, 256, 0, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->slope, (bf16*)d->uhat,           \
+                                                       (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc);                 \
+  } while (0)
+  if (fast) {
+    if (d->y_f32) NBF_POOL(true); else NBF_POOL(false);
+  } else {
+    DISPATCH_ITERS(iters, {
+      if (d->y_f32)
+        nb_pool_kernel<true, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
+                                                        (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
+                                                        d->stats_fused, d->nc_idx);
+      else
+        nb_pool_kernel<false, IT><<<g3, 256, sm3, st>>>(d->y, d->y_pitch, HW, C, d->nc, d->has_cbam, d->slope,
+                                                         (bf16*)d->uhat, (bf16*)d->out, d->out_pitch, d->sa, d->cidx, ppc,
+                                                         d->stats_fused, d->nc_idx);
+    });
+  }
+#undef NBF_POOL
   if ((rc = check_launch("nb_pool"))) return rc;
   if (!d->has_cbam) return BVAE_OK;
 
@@ -1973,6 +2396,18 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   dim3 gg(ceil_div(HW, 256), N);
   nb_gate_kernel<<<gg, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->gs);
   if ((rc = check_launch("nb_gate"))) return rc;
+  BVAE_REQUIRE(d->res_mode >= 1 && d->res_mode <= 3, BVAE_ERR_SHAPE, "nb_forward: CBAM needs res_mode 1..3");
+#define NBF_APPLY(F, M) nbf_apply_kernel<F, M><<<g3, 256, 0, st>>>(d->y, d->y_pitch, HW, C, d->nc, (const bf16*)d->res, \
+                                                                   d->res_pitch, d->slope, (bf16*)d->out, d->out_pitch, d->gs, ppc)
+  if (fast) {
+    if (d->y_f32) {
+      if (d->res_mode == 1) NBF_APPLY(true, 1); else if (d->res_mode == 2) NBF_APPLY(true, 2); else NBF_APPLY(true, 3);
+    } else {
+      if (d->res_mode == 1) NBF_APPLY(false, 1); else if (d->res_mode == 2) NBF_APPLY(false, 2); else NBF_APPLY(false, 3);
+    }
+    return check_launch("nb_apply");
+  }
+#undef NBF_APPLY
   DISPATCH_ITERS(iters, {
     if (d->y_f32)
       nb_apply_kernel<true, IT><<<g3, 256, sm4, st>>>(d->y, d->y_pitch, d->H, d->W, C, d->nc, d->res_mode,
@@ -2043,23 +2478,48 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     return BVAE_ERR_CUDA;
   }
   const size_t smb = 4 * C * sizeof(float);
+  const bool fast = iters == 1 && nb_fast_enabled();        // C <= 256: the restructured kernels
+  const int mode = d->has_cbam ? d->res_mode : 0;
+  BVAE_REQUIRE(!d->has_cbam || (mode >= 1 && mode <= 3), BVAE_ERR_SHAPE, "nb_backward: CBAM needs res_mode 1..3");
+#define NBF_MODES(...)                                          \
+  switch (mode) {                                               \
+    case 0: { constexpr int MD = 0; __VA_ARGS__; } break;       \
+    case 1: { constexpr int MD = 1; __VA_ARGS__; } break;       \
+    case 2: { constexpr int MD = 2; __VA_ARGS__; } break;       \
+    default: { constexpr int MD = 3; __VA_ARGS__; } break;      \
+  }
   if (d->has_cbam) {
-    DISPATCH_ITERS(iters, {
-      nb_bwd1_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
-                                                (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->slope,
-                                                d->bwd_nc, d->bwd_px, ppc);
-    });
+    if (fast) {
+      nbf_bwd1_kernel<<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
+                                                          d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
+                                                          d->beta, d->gs, d->slope, d->bwd_nc, d->bwd_px, ppc);
+    } else {
+      DISPATCH_ITERS(iters, {
+        nb_bwd1_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
+                                                  (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->slope,
+                                                  d->bwd_nc, d->bwd_px, ppc);
+      });
+    }
     if ((rc = check_launch("nb_bwd1"))) return rc;
     dim3 gs(ceil_div(HW, 256 * 8), N);          // up to 8 pixels per thread, one block reduction of dwsp
     nb_bwd_sp_kernel<<<gs, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->bwd_px, d->dwsp);
     if ((rc = check_launch("nb_bwd_sp"))) return rc;
   }
-  DISPATCH_ITERS(iters, {
-    nb_bwd2_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
-                                              (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->cidx,
-                                              d->bwd_px, d->has_cbam, d->res_mode, d->slope, (bf16*)d->dy, d->dy_pitch,
-                                              (bf16*)d->dres, d->dres_pitch, d->bwd_nc, ppc);
-  });
+  if (fast) {
+    NBF_MODES({
+      nbf_bwd2_kernel<MD><<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
+                                                              d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
+                                                              d->beta, d->gs, d->cidx, d->bwd_px, d->slope, (bf16*)d->dres,
+                                                              d->dres_pitch, d->bwd_nc, ppc);
+    });
+  } else {
+    DISPATCH_ITERS(iters, {
+      nb_bwd2_kernel<IT><<<gp, 256, smb, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
+                                                (const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->gs, d->cidx,
+                                                d->bwd_px, d->has_cbam, d->res_mode, d->slope, (bf16*)d->dy, d->dy_pitch,
+                                                (bf16*)d->dres, d->dres_pitch, d->bwd_nc, ppc);
+    });
+  }
   if ((rc = check_launch("nb_bwd2"))) return rc;
   const size_t smc = (3 * C + 192) * sizeof(float);
   nb_bwd_coef_kernel<<<N, 256, smc, st>>>(HW, C, d->has_cbam, d->Cr, d->nc, d->beta, d->w1, d->w2, d->bwd_nc, d->dgamma,
@@ -2076,6 +2536,16 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     if ((rc = check_launch("nb_bwd_w"))) return rc;
   }
   const size_t sm5 = 6 * C * sizeof(float);
+  if (fast) {
+    NBF_MODES({
+      nbf_bwd3_kernel<MD><<<gp, 256, 2 * C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
+                                                                  d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->nc_idx,
+                                                                  d->gs, d->cidx, d->bwd_px, d->bwd_nc, d->slope,
+                                                                  (bf16*)d->dy, d->dy_pitch, ppc);
+    });
+    return check_launch("nb_bwd3");
+  }
+#undef NBF_MODES
   DISPATCH_ITERS(iters, {
     nb_bwd3_kernel<IT><<<gp, 256, sm5, st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch,
                                               (const bf16*)d->uhat, HW, C, d->nc, d->nc_idx, d->gamma, d->beta, d->gs,

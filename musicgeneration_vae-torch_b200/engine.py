@@ -591,8 +591,17 @@ class PackPlan:
             self.handle = None
 
 
-def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0):
-    """torch.optim.Adam semantics (agent/barGen.py:61-62) on the flat bucket, one kernel."""
+def repack_weights(flat: FlatParams):
+    """Refresh the bf16 operands of all contraction weights in one launch (after anything rewrote flat.data)."""
+    plan = getattr(flat, "pack_plan", None)
+    if plan is None or not plan.valid():
+        plan = flat.pack_plan = PackPlan(flat)
+    plan.run()
+
+
+def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0,
+              repack: bool = True):
+    """torch.optim.Adam semantics (agent/barGen.py:61-62) on the flat bucket, one kernel (+ one repack launch)."""
     if flat.exp_avg is None:
         flat.exp_avg = torch.zeros_like(flat.data)
         flat.exp_avg_sq = torch.zeros_like(flat.data)
@@ -600,8 +609,5 @@ def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: f
                                          flat.exp_avg_sq.data_ptr(), flat.numel, lr, betas[0], betas[1], eps, step,
                                          grad_scale, _lib.stream_ptr()), "adam")
     bump_param_epoch()
-    # refresh the bf16 operands of all contraction weights in one launch
-    plan = getattr(flat, "pack_plan", None)
-    if plan is None or not plan.valid():
-        plan = flat.pack_plan = PackPlan(flat)
-    plan.run()
+    if repack:
+        repack_weights(flat)
