@@ -598,6 +598,9 @@ struct alignas(64) WgradTcParams {
   float* dw;                        // destination of the reduction (parameter gradient or packed scratch)
   long long s_ra, s_t;              // element strides of the anchor channel / the tap; the shifted channel stride is
   int s_rs;                         // 1 (vector reductions) or T (scalar reductions straight into [ra][rs][tap])
+  // halo variant (wgrad_halo_kernel): one shifted-tensor tile with its halo per chunk, taps = row-shifted descriptors
+  int h_PW, h_RH, h_rows_a, h_rows_s, h_stage, h_stages, h_x0, h_y0, h_tiles_h;
+  int h_shift[BVAE_MAX_TAPS];
 };
 
 // CB = channels per swizzle atom (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NS = shifted-channel tile (multiple of
@@ -722,6 +725,114 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
 #pragma unroll
         for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)i * p.T, __uint_as_float(v[i]));
       }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// Halo variant for 64 -> 64 channel stride-1 layers.  The generic kernel wastes half of every MMA there (M = 128 rows
+// for 64 anchor channels) and re-loads the shifted tensor once per tap; this one
+//   * flattens a chunk to RH image rows of the PADDED width PW = AW + (dx_max - dx_min): the anchor tile is loaded
+//     with its padding columns out of bounds (= zero, so they contribute nothing) and the shifted tensor is loaded ONCE
+//     per chunk as (RH + dy_max - dy_min) padded rows; tap (dy, dx) is that tile (dy - dy_min) * PW + (dx - dx_min)
+//     pixel rows further on, i.e. a start-address shift of the MN-major descriptor (the 128B swizzle is a function of
+//     the absolute shared-memory address, see conv_tc2_kernel);
+//   * makes the SHIFTED tensor the M operand and stacks TWO taps in it: the two 64-channel blocks of the M = 128
+//     operand are the same tile at two row shifts, expressed through the descriptor's leading-dimension byte offset.
+//     D[(tap of the pair, shifted channel)][anchor channel] fills all 128 lanes, N = 64 anchor channels.
+__global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__ WgradTcParams p) {
+  constexpr int ROW = 128;                              // bytes per pixel row (64 bf16 channels)
+  constexpr int ATOM_BYTES = 64 * ROW;                  // anchor: [64 pixel rows][64 channels]
+  constexpr uint32_t SBO = 8 * ROW;
+  constexpr uint32_t KSTEP = (16 * ROW) >> 4;
+  constexpr uint32_t IDESC = make_idesc(128, 64, 1, 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int STAGES = p.h_stages, STAGE_BYTES = p.h_stage;
+  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int npairs = (p.ntaps + 1) >> 1;
+  const int ck0 = split * p.chunks_per_split;
+  const int ck1 = min(p.nchunks, ck0 + p.chunks_per_split);
+
+  // zero the pipeline buffer once: anchor rows a box never writes must be 0, and whatever a shifted descriptor reads
+  // past the loaded tile must at least be finite
+  for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&p.amap);
+    tma_prefetch_desc(&p.smap[0]);
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    const uint32_t tx = (uint32_t)((p.h_rows_a + p.h_rows_s) * ROW);
+    int s = 0; uint32_t par = 0;
+    for (int ck = ck0; ck < ck1; ++ck) {
+      const int th = ck % p.h_tiles_h, n = ck / p.h_tiles_h;
+      mbar_wait(empty_bar + s, par ^ 1u);
+      mbar_expect_tx(full_bar + s, tx);
+      uint8_t* st = smem + s * STAGE_BYTES;
+      tma_load_4d(st, &p.amap, full_bar + s, 0, 0, th * p.h_RH, n);
+      tma_load_4d(st + ATOM_BYTES, &p.smap[0], full_bar + s, 0, p.h_x0, th * p.h_RH + p.h_y0, n);
+      if (++s == STAGES) { s = 0; par ^= 1u; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    const int ksteps = (p.h_rows_a + 15) / 16;
+    int s = 0; uint32_t par = 0;
+    for (int ck = ck0; ck < ck1; ++ck) {
+      mbar_wait(full_bar + s, par);
+      tc_fence_after();
+      const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+      const uint64_t bdesc = make_sdesc(st, ATOM_BYTES, SBO, 2u);                 // anchor: N = 64 channels, one block
+      for (int pi = 0; pi < npairs; ++pi) {
+        const int s0 = p.h_shift[2 * pi];
+        const int s1 = 2 * pi + 1 < p.ntaps ? p.h_shift[2 * pi + 1] : s0 + 1;     // an odd tap out pairs with a dummy block
+        const uint64_t adesc = make_sdesc(st + ATOM_BYTES + (uint32_t)s0 * ROW, (uint32_t)(s1 - s0) * ROW, SBO, 2u);
+        for (int j = 0; j < ksteps; ++j)
+          umma_f16(tmem_base + (uint32_t)(pi * 64), adesc + KSTEP * j, bdesc + KSTEP * j, IDESC, (ck > ck0 || j) ? 1u : 0u);
+      }
+      umma_commit(empty_bar + s);
+      if (++s == STAGES) { s = 0; par ^= 1u; }
+    }
+    umma_commit(tmem_full);
+  }
+  __syncwarp();
+  mbar_wait(tmem_full, 0);
+  tc_fence_after();
+
+  // epilogue: lane = (tap of the pair, shifted channel), columns = anchor channels
+  const int m = threadIdx.x >> 6, rs = threadIdx.x & 63;
+  for (int pi = 0; pi < npairs; ++pi) {
+    const int t = 2 * pi + m;
+    const bool valid = t < p.ntaps && ck1 > ck0;
+    const int tix = valid ? p.tap_idx[t] : 0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pi * 64 + c0), v);
+      if (!valid) continue;
+      // consecutive lanes = consecutive shifted channels: every atomic instruction covers 128 contiguous bytes when
+      // the shifted-channel stride is 1 (packed scratch)
+      float* dst = p.s_rs == 1 ? p.dw + (int64_t)c0 * p.s_ra + (int64_t)tix * p.s_t + rs
+                               : p.dw + ((int64_t)c0 * p.Cs + rs) * p.T + tix;
+      const int64_t stride = p.s_rs == 1 ? p.s_ra : (int64_t)p.Cs * p.T;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) atomicAdd(dst + (int64_t)i * stride, __uint_as_float(v[i]));
     }
   }
   tc_fence_before();
@@ -1081,6 +1192,117 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
   return check_launch("wgrad_tc");
 }
 
+// BVAE_WGRAD_HALO: 0 = off, 1 = on (default)
+static int wgrad_halo_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_WGRAD_HALO"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_tiles, bool* packed_) {
+  // pixel splits: aim at ~2 waves of 148 CTAs and pick the candidate that fills its last wave best
+  const int max_splits = ceil_div(P->nchunks, 8);
+  int splits = 1;
+  const int centre = ceil_div(148 * 2, out_tiles);
+  double best_fill = -1.0;
+  for (int sp = (centre > 3 ? centre - 2 : 1); sp <= centre + 2; ++sp) {
+    if (sp > max_splits) break;
+    const long ctas = (long)out_tiles * sp;
+    const long waves = (ctas + 147) / 148;
+    const double fill = (double)ctas / (double)(waves * 148);
+    if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
+  }
+  P->chunks_per_split = ceil_div(P->nchunks, splits);
+  P->splits = ceil_div(P->nchunks, P->chunks_per_split);
+  // Reduction target.  Many pixel splits over a small weight (encoder front, decoder back): vector atomics into the
+  // packed scratch, then one unpack pass.  Few splits over a large weight: scalar atomics straight into dw are cheaper
+  // than an extra pass over the weight.
+  const bool packed = d->T > 1 && d->scratch != nullptr && P->splits >= 3;
+  if (d->T == 1) { P->dw = d->dw; P->s_ra = d->Cs; P->s_t = 0; P->s_rs = 1; }
+  else if (packed) { P->dw = d->scratch; P->s_ra = (long long)d->T * d->Cs; P->s_t = d->Cs; P->s_rs = 1; }
+  else { P->dw = d->dw; P->s_ra = 0; P->s_t = 0; P->s_rs = d->T; }
+  *packed_ = packed;
+}
+
+static int wgrad_unpack(const bvae_wgrad_desc* d, cudaStream_t stream) {
+  if (d->Cs % 128 == 0) {
+    dim3 ug(d->Cs / 128, d->Ca);
+    wgrad_unpack_kernel<128><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+  } else {
+    dim3 ug(d->Cs / 32, d->Ca);
+    wgrad_unpack_kernel<32><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+  }
+  return check_launch("wgrad_unpack");
+}
+
+static int wgrad_halo_try(const bvae_wgrad_desc* d, const ViewPlan* vp, cudaStream_t stream, int* done) {
+  *done = 0;
+  const int mode = wgrad_halo_mode();
+  if (mode == 0 || d->Ca != 64 || d->Cs != 64 || d->sy != 1 || d->sx != 1 || d->ntaps < 4 || d->ntaps > 16 || vp->nviews != 1)
+    return BVAE_OK;
+  int dy0 = d->dy[0], dy1 = d->dy[0], dx0 = d->dx[0], dx1 = d->dx[0];
+  for (int t = 1; t < d->ntaps; ++t) {
+    dy0 = d->dy[t] < dy0 ? d->dy[t] : dy0; dy1 = d->dy[t] > dy1 ? d->dy[t] : dy1;
+    dx0 = d->dx[t] < dx0 ? d->dx[t] : dx0; dx1 = d->dx[t] > dx1 ? d->dx[t] : dx1;
+  }
+  const int PW = d->AW + (dx1 - dx0);
+  if (PW > 64) return BVAE_OK;
+  int RH = 64 / PW;
+  if (RH > d->AH) RH = d->AH;
+  if (d->AW * RH * 4 < 64 * 3) return BVAE_OK;                  // < 75 % of the contraction rows would be real pixels
+  WgradTcParams P;
+  memset(&P, 0, sizeof(P));
+  P.h_PW = PW; P.h_RH = RH; P.h_rows_a = RH * PW; P.h_rows_s = (RH + dy1 - dy0) * PW;
+  P.h_x0 = dx0; P.h_y0 = dy0;
+  int reach = 64 + (dy1 - dy0) * PW + (dx1 - dx0) + 1;          // rows the shifted descriptors can touch
+  if (reach < P.h_rows_s) reach = P.h_rows_s;
+  P.h_stage = 64 * 128 + ((reach * 128 + 1023) / 1024) * 1024;
+  P.h_stages = (190 * 1024) / P.h_stage;
+  if (P.h_stages > 8) P.h_stages = 8;
+  if (P.h_stages < 2) return BVAE_OK;
+  int rc = make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
+                         (int64_t)d->AH * d->AW * d->a_pitch, 64, PW, RH, 1, true);
+  if (rc) return rc;
+  rc = make_view_map(&P.smap[0], d->s, d->Cs, d->SW, d->SH, d->N, d->s_pitch, (int64_t)d->SW * d->s_pitch,
+                     (int64_t)d->SH * d->SW * d->s_pitch, 64, PW, RH + dy1 - dy0, 1, true);
+  if (rc) return rc;
+  // taps in ascending shift order (the second block of a pair lies behind the first)
+  int order[BVAE_MAX_TAPS];
+  for (int t = 0; t < d->ntaps; ++t) order[t] = t;
+  for (int i = 1; i < d->ntaps; ++i)
+    for (int k = i; k > 0; --k) {
+      const int a = order[k - 1], b = order[k];
+      const int sa_ = (d->dy[a] - dy0) * PW + (d->dx[a] - dx0), sb_ = (d->dy[b] - dy0) * PW + (d->dx[b] - dx0);
+      if (sa_ <= sb_) break;
+      order[k - 1] = b; order[k] = a;
+    }
+  for (int t = 0; t < d->ntaps; ++t) {
+    const int o = order[t];
+    P.h_shift[t] = (d->dy[o] - dy0) * PW + (d->dx[o] - dx0);
+    P.tap_idx[t] = d->tap_idx[o];
+  }
+  P.ntaps = d->ntaps; P.T = d->T;
+  P.tap_groups = 1; P.tpc = d->ntaps;
+  P.h_tiles_h = ceil_div(d->AH, RH);
+  P.nchunks = d->N * P.h_tiles_h;
+  P.Ca = d->Ca; P.Cs = d->Cs;
+  bool packed = false;
+  wgrad_finish(d, &P, 2, &packed);                              // one CTA per SM (it owns all 512 TMEM columns): ~148 splits
+  const long grid = P.splits;
+  const int smem = 1024 + P.h_stages * P.h_stage + (2 * P.h_stages + 1) * 8 + 16;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_halo: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    attr_smem = smem;
+  }
+  wgrad_halo_kernel<<<(int)grid, 128, smem, stream>>>(P);
+  rc = check_launch("wgrad_halo");
+  *done = 1;
+  if (rc || !packed) return rc;
+  return wgrad_unpack(d, stream);
+}
+
 int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   WgradTcParams P;
   memset(&P, 0, sizeof(P));
@@ -1089,6 +1311,11 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   const bool sw128 = (d->Ca % 64 == 0) && (d->Cs % 64 == 0);
   const int CB = sw128 ? 64 : 32;
   const int NS = sw128 ? (d->Cs % 256 == 0 ? 256 : (d->Cs % 128 == 0 ? 128 : 64)) : (d->Cs % 64 == 0 ? 64 : 32);
+  {
+    int done = 0;
+    const int rc = wgrad_halo_try(d, &vp, stream, &done);
+    if (rc || done) return rc;
+  }
   pick_box(d->N, d->AH, d->AW, 64, &P.bw, &P.bh, &P.bn);
   int rc = make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
                          (int64_t)d->AH * d->AW * d->a_pitch, CB, P.bw, P.bh, P.bn, sw128);
@@ -1115,29 +1342,8 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.Ca = d->Ca; P.Cs = d->Cs;
 
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
-  // pixel splits: aim at ~2 waves of 148 CTAs and pick the candidate that fills its last wave best
-  const int max_splits = ceil_div(P.nchunks, 8);
-  int splits = 1;
-  {
-    const int centre = ceil_div(148 * 2, out_tiles);
-    double best_fill = -1.0;
-    for (int sp = (centre > 3 ? centre - 2 : 1); sp <= centre + 2; ++sp) {
-      if (sp > max_splits) break;
-      const long ctas = (long)out_tiles * sp;
-      const long waves = (ctas + 147) / 148;
-      const double fill = (double)ctas / (double)(waves * 148);
-      if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
-    }
-  }
-  P.chunks_per_split = ceil_div(P.nchunks, splits);
-  P.splits = ceil_div(P.nchunks, P.chunks_per_split);
-  // Reduction target.  Many pixel splits over a small weight (encoder front, decoder back): vector atomics into the
-  // packed scratch, then one unpack pass.  Few splits over a large weight: scalar atomics straight into dw are cheaper
-  // than an extra pass over the weight.
-  const bool packed = d->T > 1 && d->scratch != nullptr && P.splits >= 3;
-  if (d->T == 1) { P.dw = d->dw; P.s_ra = d->Cs; P.s_t = 0; P.s_rs = 1; }
-  else if (packed) { P.dw = d->scratch; P.s_ra = (long long)d->T * d->Cs; P.s_t = d->Cs; P.s_rs = 1; }
-  else { P.dw = d->dw; P.s_ra = 0; P.s_t = 0; P.s_rs = d->T; }
+  bool packed = false;
+  wgrad_finish(d, &P, out_tiles, &packed);
   const long grid = (long)out_tiles * P.splits;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "wgrad_tc: grid too large");
   if (CB == 32) rc = NS == 64 ? launch_wgrad<32, 64, 2>(P, (int)grid, stream) : launch_wgrad<32, 32, 2>(P, (int)grid, stream);
@@ -1145,14 +1351,7 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   else if (NS == 128) rc = launch_wgrad<64, 128, 2>(P, (int)grid, stream);
   else rc = launch_wgrad<64, 64, 2>(P, (int)grid, stream);
   if (rc || !packed) return rc;
-  if (d->Cs % 128 == 0) {
-    dim3 ug(d->Cs / 128, d->Ca);
-    wgrad_unpack_kernel<128><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
-  } else {
-    dim3 ug(d->Cs / 32, d->Ca);
-    wgrad_unpack_kernel<32><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
-  }
-  return check_launch("wgrad_unpack");
+  return wgrad_unpack(d, stream);
 }
 
 }  // namespace bvae
