@@ -76,6 +76,18 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
 }
+// one lane of a CONVERGED warp (the tcgen05 issue sites sit under this predicate so that ptxas sees a single-lane
+// region and does not wrap every MMA in its per-active-lane election loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -84,6 +96,44 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// NK consecutive K = 16 steps in ONE asm statement: the descriptors advance by STEP (encoded >> 4 units) per step.
+// A single statement costs one elect/convergence wrapper in SASS instead of NK -- for N <= 64 tiles the issuing thread's
+// own instruction stream, not the tensor pipe, limits the MMA rate.
+template <int NK, int STEP>
+__device__ __forceinline__ void umma_f16_steps(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  static_assert(NK == 2 || NK == 4, "NK");
+  if (NK == 4) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u64 a1, %1, %5;\n\t"
+        "add.u64 b1, %2, %5;\n\t"
+        "add.u64 a2, %1, %6;\n\t"
+        "add.u64 b2, %2, %6;\n\t"
+        "add.u64 a3, %1, %7;\n\t"
+        "add.u64 b3, %2, %7;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, q;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, q;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "n"(STEP), "n"(2 * STEP), "n"(3 * STEP) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        ".reg .b64 a1, b1;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 q, 0, 0;\n\t"
+        "add.u64 a1, %1, %5;\n\t"
+        "add.u64 b1, %2, %5;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, q;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc), "n"(STEP) : "memory");
+  }
 }
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -403,8 +453,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 1) {
+    // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues ----------------
     uint32_t s = 0, par = 0, ti = 0;
     if (BRES) { mbar_wait(bres_bar, 0); tc_fence_after(); }
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
@@ -421,34 +471,40 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
           mbar_wait(full_bar + s, par);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          for (int t = 0; t < p.ntaps; ++t) {
-            // tap t = the same tile, p.halo_shift[t] pixel rows (128 B each) further on.  Measured on B200: the 128B
-            // swizzle XOR is taken from the absolute shared-memory address bits [7,10) - exactly how TMA wrote the
-            // tile - so a start address that is not 1024-byte aligned needs NO descriptor base offset (setting
-            // (addr >> 7) & 7 there gives wrong results).
-            const uint64_t adesc = make_sdesc(sa + (uint32_t)p.halo_shift[t] * 128u, 16, SBO, LAYOUT);
-            const uint64_t bdesc = make_sdesc(bres0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, SBO, LAYOUT);
-#pragma unroll
-            for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kc | t | j) ? 1u : 0u);
+          if (elect_one()) {
+            for (int t = 0; t < p.ntaps; ++t) {
+              // tap t = the same tile, p.halo_shift[t] pixel rows (128 B each) further on.  Measured on B200: the 128B
+              // swizzle XOR is taken from the absolute shared-memory address bits [7,10) - exactly how TMA wrote the
+              // tile - so a start address that is not 1024-byte aligned needs NO descriptor base offset (setting
+              // (addr >> 7) & 7 there gives wrong results).
+              const uint64_t adesc = make_sdesc(sa + (uint32_t)p.halo_shift[t] * 128u, 16, SBO, LAYOUT);
+              const uint64_t bdesc = make_sdesc(bres0 + (uint32_t)(t * p.kchunks + kc) * B_BYTES, 16, SBO, LAYOUT);
+              umma_f16_steps<KB / 16, 2>(tacc, adesc, bdesc, IDESC, (kc | t) ? 1u : 0u);
+            }
+            umma_commit(empty_bar + s);
           }
-          umma_commit(empty_bar + s);
+          __syncwarp();
           if (++s == nst) { s = 0; par ^= 1u; }
         }
-        umma_commit(tfull + ab);
+        if (elect_one()) umma_commit(tfull + ab);
+        __syncwarp();
         continue;
       }
       for (int kb = 0; kb < KT; ++kb) {
         mbar_wait(full_bar + s, par);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * stage_bytes);
-        const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
-        const uint64_t bdesc = make_sdesc(BRES ? bres0 + (uint32_t)kb * B_BYTES : sa + A_BYTES, 16, SBO, LAYOUT);
-#pragma unroll
-        for (int j = 0; j < KB / 16; ++j) umma_f16(tacc, adesc + 2 * j, bdesc + 2 * j, IDESC, (kb | j) ? 1u : 0u);
-        umma_commit(empty_bar + s);
+        if (elect_one()) {
+          const uint64_t adesc = make_sdesc(sa, 16, SBO, LAYOUT);
+          const uint64_t bdesc = make_sdesc(BRES ? bres0 + (uint32_t)kb * B_BYTES : sa + A_BYTES, 16, SBO, LAYOUT);
+          umma_f16_steps<KB / 16, 2>(tacc, adesc, bdesc, IDESC, kb ? 1u : 0u);
+          umma_commit(empty_bar + s);
+        }
+        __syncwarp();
         if (++s == nst) { s = 0; par ^= 1u; }
       }
-      umma_commit(tfull + ab);
+      if (elect_one()) umma_commit(tfull + ab);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ---------------- epilogue warps: TMEM -> registers -> global ----------------
@@ -675,7 +731,8 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
                       cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn);
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
+    // the whole warp walks the loop, one elected lane issues (see elect_one)
     const int ksteps = (rows_box + 15) / 16;
     int it = 0;
     for (int ck = ck0; ck < ck1; ++ck, ++it) {
@@ -684,21 +741,29 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
       const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-      // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
-      const uint64_t adesc = make_sdesc(st, ATOM_BYTES, SBO, LAYOUT);
-      // the atoms of consecutive taps are contiguous in smem and their accumulators are contiguous TMEM columns, so
-      // up to 256/NS taps go into ONE instruction with N = taps*NS (A is read once for all of them)
-      constexpr int TG = 256 / NS;
-      for (int t = 0; t < ntap; t += TG) {
-        const int tg = min(TG, ntap - t);
-        const uint32_t idesc = make_idesc(128, tg * NS, 1, 1);
-        const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, SBO, LAYOUT);
-        for (int j = 0; j < ksteps; ++j)
-          umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, idesc, (it | j) ? 1u : 0u);
+      if (elect_one()) {
+        // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
+        const uint64_t adesc = make_sdesc(st, ATOM_BYTES, SBO, LAYOUT);
+        // the atoms of consecutive taps are contiguous in smem and their accumulators are contiguous TMEM columns, so
+        // up to 256/NS taps go into ONE instruction with N = taps*NS (A is read once for all of them)
+        constexpr int TG = 256 / NS;
+        for (int t = 0; t < ntap; t += TG) {
+          const int tg = min(TG, ntap - t);
+          const uint32_t idesc = make_idesc(128, tg * NS, 1, 1);
+          const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, SBO, LAYOUT);
+          if (ksteps == 4) {
+            umma_f16_steps<4, (int)KSTEP>(tmem_base + (uint32_t)(t * NS), adesc, bdesc, idesc, it ? 1u : 0u);
+          } else {
+            for (int j = 0; j < ksteps; ++j)
+              umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, idesc, (it | j) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar + s);
       }
-      umma_commit(empty_bar + s);
+      __syncwarp();
     }
-    umma_commit(tmem_full);
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
   }
   __syncwarp();
   mbar_wait(tmem_full, 0);
@@ -791,25 +856,33 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
       tma_load_4d(st + ATOM_BYTES, &p.smap[0], full_bar + s, 0, p.h_x0, th * p.h_RH + p.h_y0, n);
       if (++s == STAGES) { s = 0; par ^= 1u; }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     const int ksteps = (p.h_rows_a + 15) / 16;
     int s = 0; uint32_t par = 0;
     for (int ck = ck0; ck < ck1; ++ck) {
       mbar_wait(full_bar + s, par);
       tc_fence_after();
       const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
-      const uint64_t bdesc = make_sdesc(st, ATOM_BYTES, SBO, 2u);                 // anchor: N = 64 channels, one block
-      for (int pi = 0; pi < npairs; ++pi) {
-        const int s0 = p.h_shift[2 * pi];
-        const int s1 = 2 * pi + 1 < p.ntaps ? p.h_shift[2 * pi + 1] : s0 + 1;     // an odd tap out pairs with a dummy block
-        const uint64_t adesc = make_sdesc(st + ATOM_BYTES + (uint32_t)s0 * ROW, (uint32_t)(s1 - s0) * ROW, SBO, 2u);
-        for (int j = 0; j < ksteps; ++j)
-          umma_f16(tmem_base + (uint32_t)(pi * 64), adesc + KSTEP * j, bdesc + KSTEP * j, IDESC, (ck > ck0 || j) ? 1u : 0u);
+      if (elect_one()) {
+        const uint64_t bdesc = make_sdesc(st, ATOM_BYTES, SBO, 2u);               // anchor: N = 64 channels, one block
+        for (int pi = 0; pi < npairs; ++pi) {
+          const int s0 = p.h_shift[2 * pi];
+          const int s1 = 2 * pi + 1 < p.ntaps ? p.h_shift[2 * pi + 1] : s0 + 1;   // an odd tap out pairs with a dummy block
+          const uint64_t adesc = make_sdesc(st + ATOM_BYTES + (uint32_t)s0 * ROW, (uint32_t)(s1 - s0) * ROW, SBO, 2u);
+          if (ksteps == 4) {
+            umma_f16_steps<4, (int)KSTEP>(tmem_base + (uint32_t)(pi * 64), adesc, bdesc, IDESC, ck > ck0 ? 1u : 0u);
+          } else {
+            for (int j = 0; j < ksteps; ++j)
+              umma_f16(tmem_base + (uint32_t)(pi * 64), adesc + KSTEP * j, bdesc + KSTEP * j, IDESC, (ck > ck0 || j) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar + s);
       }
-      umma_commit(empty_bar + s);
+      __syncwarp();
       if (++s == STAGES) { s = 0; par ^= 1u; }
     }
-    umma_commit(tmem_full);
+    if (elect_one()) umma_commit(tmem_full);
+    __syncwarp();
   }
   __syncwarp();
   mbar_wait(tmem_full, 0);
