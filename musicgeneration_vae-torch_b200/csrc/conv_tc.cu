@@ -526,10 +526,27 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       const bool valid = r < rows_box && n < p.N && qy < p.ph_QH[ph] && qx < p.ph_QW[ph];
       const int64_t opix = ((int64_t)n * p.OH + (qy * p.osy + p.ph_ooy[ph])) * p.OW + (qx * p.osx + p.ph_oox[ph]);
       const int col0 = n_tile * BN;
+      // narrow tiles (BN <= 64) have short main loops: fetch the activation mask / bf16 addend of this row BEFORE
+      // waiting for the accumulator so that their latency overlaps the MMAs instead of serialising the epilogue
+      constexpr bool PRE = BN <= 64;
+      constexpr int NPRE = PRE ? BN / 8 : 1;
+      bf16x8 pre_m[NPRE], pre_a[NPRE];
+      const bool pre_mask = PRE && p.mask && valid && !p.stats;
+      const bool pre_add = PRE && p.addend && !p.out_f32 && valid && !p.stats;
+      if (pre_mask) {
+        const bf16* mp = (const bf16*)p.mask + opix * p.mask_pitch + col0;
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) pre_m[i] = ldg8(mp + 8 * i);
+      }
+      if (pre_add) {
+        const bf16* ap = (const bf16*)p.addend + opix * p.add_pitch + col0;
+#pragma unroll
+        for (int i = 0; i < NPRE; ++i) pre_a[i] = ldg8(ap + 8 * i);
+      }
       mbar_wait(tfull + ab, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(wq * 32) << 16);
-#pragma unroll 1
+#pragma unroll(PRE ? 2 : 1)
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tacc + (uint32_t)c0, v);
@@ -601,7 +618,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               float a[8];
-              unpack8(ldg8(ap + i), a);
+              unpack8(PRE ? pre_a[PRE ? (c0 + i) / 8 : 0] : ldg8(ap + i), a);
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[i + k] += a[k];
             }
@@ -612,7 +629,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             float a[8];
-            unpack8(ldg8(mp + i), a);
+            unpack8(PRE ? pre_m[PRE ? (c0 + i) / 8 : 0] : ldg8(mp + i), a);
 #pragma unroll
             for (int k = 0; k < 8; ++k) f[i + k] *= (a[k] > 0.f) ? 1.f : p.mask_slope;
           }
