@@ -974,6 +974,56 @@ __global__ void __launch_bounds__(256) nb_bwd_w_kernel(int N, int C, int Cr, con
   atomicAdd(dw1 + (int64_t)j * C + c, a1);
 }
 
+// The same reduction tiled through shared memory: a CTA owns 64 channels x all hidden units for WB_NS samples; the
+// per-(n,c) inputs are read once as float4 rows and the per-sample hidden vectors once per CTA (the kernel above
+// re-reads every (n,c) value Cr times with 4- and 8-float strides).   grid (C/64, ceil(N/WB_NS)), block 256, C % 64 == 0
+constexpr int WB_NS = 64;
+__global__ void __launch_bounds__(256) nb_bwd_w_tiled_kernel(int N, int C, int Cr, const float* __restrict__ nc,
+                                                             const float* __restrict__ beta,
+                                                             const float* __restrict__ bwd_nc,
+                                                             const float* __restrict__ bwd_h, float* __restrict__ dw1,
+                                                             float* __restrict__ dw2) {
+  constexpr int SUB = 16;                        // samples staged per round
+  __shared__ float s_dv[SUB][64], s_mx[SUB][64], s_h[SUB][192];
+  const int c0 = blockIdx.x * 64, t = threadIdx.x;
+  const int cl = t & 63, jq = t >> 6;            // 4 thread groups share the hidden units
+  const int jn = (Cr + 3) / 4, j0 = jq * jn;     // hidden units [j0, j0 + jn) of this thread (jn <= 16)
+  const int n_begin = blockIdx.y * WB_NS, n_end = min(N, n_begin + WB_NS);
+  const float avg = beta[c0 + cl];
+  float a1[16], a2[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
+  for (int nb = n_begin; nb < n_end; nb += SUB) {
+    const int ns = min(SUB, n_end - nb);
+    __syncthreads();
+    for (int i = t; i < ns * 64; i += 256) {
+      const int s = i >> 6, c = i & 63;
+      const int64_t o = (int64_t)(nb + s) * C + c0 + c;
+      s_dv[s][c] = bwd_nc[o * BN_W + BN_DGC];
+      s_mx[s][c] = nc[o * NC_W + NC_EXTU];
+    }
+    for (int i = t; i < ns * 192; i += 256) s_h[i / 192][i % 192] = bwd_h[(int64_t)nb * 192 + i];
+    __syncthreads();
+    for (int s = 0; s < ns; ++s) {
+      const float dv = s_dv[s][cl], mx = s_mx[s][cl];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < jn && j0 + i < Cr) {
+          a2[i] = fmaf(dv, s_h[s][j0 + i], a2[i]);
+          a1[i] = fmaf(s_h[s][128 + j0 + i], mx, fmaf(s_h[s][64 + j0 + i], avg, a1[i]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (i < jn && j0 + i < Cr) {
+      atomicAdd(dw2 + (int64_t)(c0 + cl) * Cr + j0 + i, a2[i]);
+      atomicAdd(dw1 + (int64_t)(j0 + i) * C + c0 + cl, a1[i]);
+    }
+  }
+}
+
 // backward 4: dy = a * (du + [p == argmax] d_mx - m1 - uhat*m2); du is recomputed in fp32
 template <int ITERS>
 __global__ void __launch_bounds__(256, ITERS == 1 ? 3 : 1) nb_bwd3_kernel(const bf16* __restrict__ dout, int dout_pitch,
@@ -1752,8 +1802,10 @@ __device__ __forceinline__ u64 cl_max(cg::cluster_group& cl, u64* s_arr, int c, 
   return v;
 }
 
+// stage 0 = the whole forward; 1 = statistics + coefficients only (the channel MLP then runs BATCHED over samples in
+// nb_mlp_fwd_kernel); 2 = everything after the MLP, coefficients re-read from d.nc
 template <bool F32>
-__global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d, int CLn, int slice) {
+__global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ float sm[];
   const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV;
@@ -1781,10 +1833,17 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d,
   for (int c = t; c < C; c += CLT) { s_sum[c] = 0.f; s_sq[c] = 0.f; s_kmax[c] = 0; s_kmin[c] = 0; }
   for (int i = t; i < slice; i += CLT) { s_psum[i] = 0.f; s_pkey[i] = 0; }
   if (t < 18 && d.has_cbam) s_w[t] = d.wsp[t];
+  if (stage == 2) {
+    for (int c = t; c < C; c += CLT) {
+      const float4* q = reinterpret_cast<const float4*>(d.nc + ((int64_t)n * C + c) * NC_W);
+      const float4 lo = q[0], hi = q[1];          // {mean, rstd, a, b} {gc, ext_u, ext_uhat, -}
+      s_mean[c] = lo.x; s_rstd[c] = lo.y; s_a[c] = lo.z; s_b[c] = lo.w; s_gc[c] = hi.x; s_mx[c] = hi.y;
+    }
+  }
   __syncthreads();
 
   // ---- phase A: per-channel shifted sums and extrema over this CTA's pixel slice
-  {
+  if (stage != 2) {
     float shift[8], sum[8], sq[8], vmx[8], vmn[8];
     int imx[8], imn[8];
     load8<F32>(d.y, ybase + c0, shift);
@@ -1832,7 +1891,7 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d,
   }
   if (CLn > 1) cl.sync(); else __syncthreads();
   const float inv = 1.f / (float)HW;
-  for (int c = t; c < C; c += CLT) {
+  for (int c = t; c < C && stage != 2; c += CLT) {
     const int64_t o = (int64_t)n * C + c;
     const float shift = F32 ? ((const float*)d.y)[ybase + c] : bf2f(((const bf16*)d.y)[ybase + c]);
     const float tsum = CLn > 1 ? cl_sum(cl, s_sum, c, CLn) : s_sum[c];
@@ -1861,8 +1920,9 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d,
   // all remote reads of the partial arrays are done before any CTA of the cluster may overwrite them or exit
   if (CLn > 1) cl.sync(); else __syncthreads();
 
+  if (stage == 1) return;
   // ---- phase B: channel-attention MLP (every CTA of the cluster computes it redundantly: C <= 256 there)
-  if (d.has_cbam) {
+  if (d.has_cbam && stage == 0) {
     for (int c = t; c < C; c += CLT) s_sq[c] = d.beta[c];        // avg pool of an instance-normalised map == beta
     __syncthreads();
     mlp_hidden(d.w1, C, d.Cr, s_sq, s_mx, s_h, s_t);
@@ -1964,7 +2024,9 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_fwd_kernel(const bvae_nb_desc d,
   }
 }
 
-__global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d, int CLn, int slice) {
+// stage 0 = the whole backward; 1 = the reduction sweeps (totals of dgc, S1, S2 and the per-pixel spatial gradients go to
+// d.bwd_nc / d.bwd_px; the channel-MLP backward then runs BATCHED in nb_mlp_bwd_kernel); 2 = the final dy sweep
+__global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ float sm[];
   const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV, Cr = d.Cr;
@@ -2010,9 +2072,19 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
     s_dq[lp] = 0.f; s_dmean[lp] = 0.f; s_dmax[lp] = 0.f;
   }
   if (t < 32) { s_w[t] = (has_cbam && t < 18) ? d.wsp[t] : 0.f; s_dw[t] = 0.f; }
+  if (stage == 2) {
+    for (int c = t; c < C; c += CLT) {
+      const float4 v = *reinterpret_cast<const float4*>(d.bwd_nc + ((int64_t)n * C + c) * BN_W);   // {dv, a*m1, a*m2, a*d_mx}
+      s_m1[c] = v.y; s_m2[c] = v.z; s_dmx[c] = v.w;
+    }
+    for (int lp = t; lp < np; lp += CLT) {
+      const float4 v = *reinterpret_cast<const float4*>(px_n + (int64_t)(p_lo + lp) * BP_W);       // {dq, dmean / C, dmax, -}
+      s_dmean[lp] = v.y; s_dmax[lp] = v.z;
+    }
+  }
   __syncthreads();
 
-  if (has_cbam) {
+  if (has_cbam && stage != 2) {
     // ---- phase 1: dgs[p] = sum_c ds*u*gc (complete inside the CTA) ; dgc[c] += sum_p ds*u*gs (partial)
     float acc[8];
 #pragma unroll
@@ -2079,6 +2151,7 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
         }
       s_dmean[lp] = dmean / (float)C;
       s_dmax[lp] = dmax;
+      if (stage == 1) { px_n[(int64_t)p * BP_W + BP_DMEAN] = dmean / (float)C; px_n[(int64_t)p * BP_W + BP_DMAX] = dmax; }
     }
 #pragma unroll
     for (int i = 0; i < 18; ++i) {
@@ -2090,7 +2163,7 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
   }
 
   // ---- phase 3: S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u (partials over this slice) ; dres
-  {
+  if (stage != 2) {
     float a1[8], a2[8], a3[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { a1[i] = 0.f; a2[i] = 0.f; a3[i] = 0.f; }
@@ -2136,9 +2209,14 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
       }
   }
   if (CLn > 1) cl.sync(); else __syncthreads();
+  if (stage == 1) {                 // one CTA per sample (CLn == 1): the totals are complete
+    for (int c = t; c < C; c += CLT)
+      *reinterpret_cast<float4*>(d.bwd_nc + ((int64_t)n * C + c) * BN_W) = make_float4(s_dgc[c], s_S1[c], s_S2[c], 0.f);
+    return;
+  }
 
   // ---- phase 4: cluster all-reduce of (dgc, S1, S2); channel-MLP backward; dgamma / dbeta; InstanceNorm means
-  for (int c = t; c < C; c += CLT) {
+  for (int c = t; c < C && stage == 0; c += CLT) {
     const float gc = s_gc[c];
     const float dgc = CLn > 1 ? cl_sum(cl, s_dgc, c, CLn) : s_dgc[c];
     s_dv[c] = has_cbam ? dgc * gc * (1.f - gc) : 0.f;
@@ -2148,7 +2226,7 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
   }
   if (t < 64) s_dh[t] = 0.f;
   if (CLn > 1) cl.sync(); else __syncthreads();                    // remote reads done; partial arrays may be reused
-  if (has_cbam) {
+  if (has_cbam && stage == 0) {
     mlp_hidden(d.w1, C, Cr, s_b, s_dmx, s_ha, s_hm);
     mlp_cols_dot(d.w2, C, Cr, s_dv, s_dh);
     __syncthreads();
@@ -2161,7 +2239,7 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
       }
   }
   const float inv = 1.f / (float)HW;
-  for (int c = t; c < C; c += CLT) {
+  for (int c = t; c < C && stage == 0; c += CLT) {
     float d_avg = 0.f, d_mx = 0.f;
     if (has_cbam) {
 #pragma unroll 8
@@ -2216,6 +2294,217 @@ __global__ void __launch_bounds__(CLT, 3) nb_cl_bwd_kernel(const bvae_nb_desc d,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Channel-attention MLP BATCHED over samples (small maps: 256..1024 channels, one CTA per sample everywhere else).
+// Inside the per-sample kernels the two GEMVs re-read W1 / W2 (up to 2 x 256 KB) from L2 once per sample and were
+// 30-50 % of their time; here a CTA owns MLP_NS samples, so every weight element fetched is used MLP_NS times and the
+// loads of one row are all in flight together.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MLP_NS = 4;
+
+// hidden pre-activations: ha[j] = W1[j,:] . beta (the average pool of an instance-normalised map is beta),
+// hm[s][j] = W1[j,:] . mx[s,:].  warp per hidden unit, lanes over channels.
+__device__ __forceinline__ void mlpb_hidden(const float* __restrict__ w1, int C, int Cr, const float* s_beta,
+                                            const float* s_mx /* [MLP_NS][C] */, float* s_ha, float* s_hm /* [MLP_NS][64] */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int j = warp; j < Cr; j += nw) {
+    const float* row = w1 + (int64_t)j * C;
+    float pa = 0.f, pm[MLP_NS];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) pm[s] = 0.f;
+    if (C >= 128) {
+#pragma unroll 8
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + c));
+        const float4 b = *reinterpret_cast<const float4*>(s_beta + c);
+        pa += w.x * b.x + w.y * b.y + w.z * b.z + w.w * b.w;
+#pragma unroll
+        for (int s = 0; s < MLP_NS; ++s) {
+          const float4 m = *reinterpret_cast<const float4*>(s_mx + s * C + c);
+          pm[s] += w.x * m.x + w.y * m.y + w.z * m.z + w.w * m.w;
+        }
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        const float w = __ldg(row + c);
+        pa += w * s_beta[c];
+#pragma unroll
+        for (int s = 0; s < MLP_NS; ++s) pm[s] += w * s_mx[s * C + c];
+      }
+    }
+    pa = warp_sum(pa);
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) pm[s] = warp_sum(pm[s]);
+    if (lane == 0) {
+      s_ha[j] = pa;
+#pragma unroll
+      for (int s = 0; s < MLP_NS; ++s) s_hm[s * 64 + j] = pm[s];
+    }
+  }
+}
+
+// gc[n][c] = sigmoid(W2[c,:] . (relu(ha) + relu(hm[n])))      grid ceil(N / MLP_NS), block 256, smem (MLP_NS + 1) * C floats
+__global__ void __launch_bounds__(256) nb_mlp_fwd_kernel(int N, int C, int Cr, const float* __restrict__ w1,
+                                                         const float* __restrict__ w2, const float* __restrict__ beta,
+                                                         float* __restrict__ nc) {
+  extern __shared__ float sm[];
+  float* s_beta = sm;                 // [C]
+  float* s_mx = sm + C;               // [MLP_NS][C]
+  __shared__ float s_ha[64], s_hm[MLP_NS * 64], s_h[MLP_NS * 64];
+  const int n0 = blockIdx.x * MLP_NS, t = threadIdx.x;
+  for (int c = t; c < C; c += 256) {
+    s_beta[c] = beta[c];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s)
+      s_mx[s * C + c] = n0 + s < N ? nc[((int64_t)(n0 + s) * C + c) * NC_W + NC_EXTU] : 0.f;
+  }
+  __syncthreads();
+  mlpb_hidden(w1, C, Cr, s_beta, s_mx, s_ha, s_hm);
+  __syncthreads();
+  for (int i = t; i < MLP_NS * Cr; i += 256) {
+    const int s = i / Cr, j = i % Cr;
+    s_h[s * 64 + j] = fmaxf(s_ha[j], 0.f) + fmaxf(s_hm[s * 64 + j], 0.f);
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    const float* row = w2 + (int64_t)c * Cr;
+    float v[MLP_NS];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) v[s] = 0.f;
+    if (Cr >= 4) {
+#pragma unroll 16
+      for (int j = 0; j < Cr; j += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + j));
+#pragma unroll
+        for (int s = 0; s < MLP_NS; ++s)
+          v[s] += w.x * s_h[s * 64 + j] + w.y * s_h[s * 64 + j + 1] + w.z * s_h[s * 64 + j + 2] + w.w * s_h[s * 64 + j + 3];
+      }
+    } else {
+      for (int j = 0; j < Cr; ++j) {
+        const float w = __ldg(row + j);
+#pragma unroll
+        for (int s = 0; s < MLP_NS; ++s) v[s] += w * s_h[s * 64 + j];
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s)
+      if (n0 + s < N) nc[((int64_t)(n0 + s) * C + c) * NC_W + NC_GC] = 1.f / (1.f + expf(-v[s]));
+  }
+}
+
+// Backward of the same MLP for MLP_NS samples, followed by the per-(n,c) InstanceNorm-backward coefficients.
+// in : bwd_nc[n][c] = {dgc, S1, S2, -} (totals from the reduction sweeps), nc
+// out: bwd_nc[n][c] = {dv, a*m1, a*m2, a*d_mx}, bwd_h[n] (for nb_bwd_w_kernel), dgamma / dbeta (atomics, one per CTA)
+__global__ void __launch_bounds__(256) nb_mlp_bwd_kernel(int N, int HW, int C, int Cr, const float* __restrict__ w1,
+                                                         const float* __restrict__ w2, const float* __restrict__ beta,
+                                                         const float* __restrict__ nc, float* __restrict__ bwd_nc,
+                                                         float* __restrict__ bwd_h, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta) {
+  extern __shared__ float sm[];
+  float* s_beta = sm;                 // [C]
+  float* s_mx = sm + C;               // [MLP_NS][C]
+  float* s_dv = sm + (1 + MLP_NS) * C;   // [MLP_NS][C]
+  __shared__ float s_ha[64], s_hm[MLP_NS * 64], s_dh[MLP_NS * 64], s_dha[MLP_NS * 64], s_dhm[MLP_NS * 64];
+  const int n0 = blockIdx.x * MLP_NS, t = threadIdx.x;
+  const int lane = t & 31, warp = t >> 5;
+  for (int c = t; c < C; c += 256) {
+    s_beta[c] = beta[c];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) {
+      float mx = 0.f, dv = 0.f;
+      if (n0 + s < N) {
+        const int64_t o = (int64_t)(n0 + s) * C + c;
+        const float gc = nc[o * NC_W + NC_GC];
+        mx = nc[o * NC_W + NC_EXTU];
+        dv = bwd_nc[o * BN_W + BN_DGC] * gc * (1.f - gc);
+        bwd_nc[o * BN_W + BN_DGC] = dv;                              // consumed by nb_bwd_w_kernel
+      }
+      s_mx[s * C + c] = mx;
+      s_dv[s * C + c] = dv;
+    }
+  }
+  for (int i = t; i < MLP_NS * 64; i += 256) s_dh[i] = 0.f;
+  __syncthreads();
+  mlpb_hidden(w1, C, Cr, s_beta, s_mx, s_ha, s_hm);
+  // dh[s][j] = sum_c W2[c][j] * dv[s][c]: lanes over j, warps over rows, all loads of a trip independent
+  {
+    float a0[MLP_NS], a1[MLP_NS];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) { a0[s] = 0.f; a1[s] = 0.f; }
+    const bool l0 = lane < Cr, l1 = lane + 32 < Cr;
+#pragma unroll 8
+    for (int c = warp; c < C; c += 8) {
+      const float w0 = l0 ? __ldg(w2 + (int64_t)c * Cr + lane) : 0.f;
+      const float w1v = l1 ? __ldg(w2 + (int64_t)c * Cr + lane + 32) : 0.f;
+#pragma unroll
+      for (int s = 0; s < MLP_NS; ++s) {
+        const float dv = s_dv[s * C + c];
+        a0[s] = fmaf(w0, dv, a0[s]);
+        a1[s] = fmaf(w1v, dv, a1[s]);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) {
+      if (l0) atomicAdd(&s_dh[s * 64 + lane], a0[s]);
+      if (l1) atomicAdd(&s_dh[s * 64 + lane + 32], a1[s]);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < MLP_NS * Cr; i += 256) {
+    const int s = i / Cr, j = i % Cr;
+    const float ha = s_ha[j], hm = s_hm[s * 64 + j], dh = s_dh[s * 64 + j];
+    const float dha = ha > 0.f ? dh : 0.f, dhm = hm > 0.f ? dh : 0.f;
+    s_dha[s * 64 + j] = dha; s_dhm[s * 64 + j] = dhm;
+    if (n0 + s < N) {
+      float* hq = bwd_h + (int64_t)(n0 + s) * 192;
+      hq[j] = fmaxf(ha, 0.f) + fmaxf(hm, 0.f);
+      hq[64 + j] = dha;
+      hq[128 + j] = dhm;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / (float)HW;
+  for (int c = t; c < C; c += 256) {
+    float d_avg[MLP_NS], d_mx[MLP_NS];
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) { d_avg[s] = 0.f; d_mx[s] = 0.f; }
+#pragma unroll 8
+    for (int j = 0; j < Cr; ++j) {
+      const float w = __ldg(w1 + (int64_t)j * C + c);
+#pragma unroll
+      for (int s = 0; s < MLP_NS; ++s) {
+        d_avg[s] = fmaf(w, s_dha[s * 64 + j], d_avg[s]);
+        d_mx[s] = fmaf(w, s_dhm[s * 64 + j], d_mx[s]);
+      }
+    }
+    float sum_b = 0.f, sum_g = 0.f;
+#pragma unroll
+    for (int s = 0; s < MLP_NS; ++s) {
+      if (n0 + s >= N) break;
+      const int64_t o = (int64_t)(n0 + s) * C + c;
+      const float a = nc[o * NC_W + NC_A], ext_uhat = nc[o * NC_W + NC_EXTUHAT];
+      const float4 tot = *reinterpret_cast<const float4*>(bwd_nc + o * BN_W);       // {dv, S1, S2, -}
+      const float S1 = tot.y + d_mx[s];
+      const float S2 = tot.z + d_mx[s] * ext_uhat;
+      sum_b += S1 + d_avg[s];
+      sum_g += S2;
+      *reinterpret_cast<float4*>(bwd_nc + o * BN_W) = make_float4(tot.x, a * S1 * inv, a * S2 * inv, a * d_mx[s]);
+    }
+    atomicAdd(dbeta + c, sum_b);
+    atomicAdd(dgamma + c, sum_g);
+  }
+}
+
+// BVAE_NB_MLP: 0 keeps the channel MLP inside the per-sample kernels; 1 (default) batches it in the backward pass of
+// the >= 512-channel small maps (measured: C1024 backward -15 %, C512 neutral, C256 and every forward slower because
+// each extra stage pays the partial second wave of 512 CTAs again); 2 batches it everywhere (forward too)
+static bool nb_mlp_batched(const bvae_nb_desc* d, int CLn, bool backward) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_NB_MLP"); v = e ? atoi(e) : 1; }
+  if (v == 0 || CLn != 1 || !d->has_cbam || d->C < 128) return false;
+  return v == 2 || (backward && d->C >= 512);
+}
+
 static void nb_cl_geometry(const bvae_nb_desc* d, int* CLn, int* slice) {
   const int HW = d->H * d->W;
   const int cl = HW <= 128 ? 1 : (HW <= 1440 ? 4 : (HW <= 2880 ? 8 : 16));
@@ -2226,7 +2515,7 @@ static size_t nb_cl_fwd_smem(int C, int slice) { return (size_t)(8 * C) * 4 + (s
 static size_t nb_cl_bwd_smem(int C, int slice) { return (size_t)(12 * C) * 4 + (3 * 64 + 32 + 32) * 4 + (size_t)slice * 5 * 4 + 64; }
 
 template <typename K>
-static int nb_cl_launch(K kernel, const bvae_nb_desc* d, size_t smem, cudaStream_t st, const char* what) {
+static int nb_cl_launch(K kernel, const bvae_nb_desc* d, size_t smem, cudaStream_t st, const char* what, int stage = 0) {
   int CLn, slice;
   nb_cl_geometry(d, &CLn, &slice);
   cudaLaunchConfig_t cfg = {};
@@ -2239,7 +2528,7 @@ static int nb_cl_launch(K kernel, const bvae_nb_desc* d, size_t smem, cudaStream
   attr[0].val.clusterDim.x = CLn; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, *d, CLn, slice);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, *d, CLn, slice, stage);
   if (e != cudaSuccess) { set_error("%s: %s", what, cudaGetErrorString(e)); return BVAE_ERR_CUDA; }
   return check_launch(what);
 }
@@ -2275,6 +2564,23 @@ static bool nb_fast_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("BVAE_NB_FAST"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
+}
+
+static int launch_bwd_w(const bvae_nb_desc* d, cudaStream_t st) {
+  const int N = d->N, C = d->C;
+  if (C >= 512 && C % 64 == 0 && N >= 32) {        // (few CTAs and idle hidden-unit slots below 512 channels)
+    dim3 gw(C / 64, ceil_div(N, WB_NS));
+    nb_bwd_w_tiled_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2);
+    return check_launch("nb_bwd_w");
+  }
+  int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
+  if (nsplit > N) nsplit = N;
+  if (nsplit > 32) nsplit = 32;
+  if (nsplit < 1) nsplit = 1;
+  const int npb = ceil_div(N, nsplit);
+  dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
+  nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
+  return check_launch("nb_bwd_w");
 }
 
 static int validate(const bvae_nb_desc* d, const char* who) {
@@ -2317,6 +2623,17 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
     int CLn, slice;
     nb_cl_geometry(d, &CLn, &slice);
     const size_t smem = nb_cl_fwd_smem(C, slice);
+    if (nb_mlp_batched(d, CLn, false)) {
+      // statistics -> batched channel MLP -> everything else (the sample's tensors stay in L2 between the stages)
+      rc = d->y_f32 ? nb_cl_launch(nb_cl_fwd_kernel<true>, d, smem, st, "nb_cl_fwd", 1)
+                    : nb_cl_launch(nb_cl_fwd_kernel<false>, d, smem, st, "nb_cl_fwd", 1);
+      if (rc) return rc;
+      nb_mlp_fwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + MLP_NS) * C * sizeof(float), st>>>(N, C, d->Cr, d->w1, d->w2,
+                                                                                                   d->beta, d->nc);
+      if ((rc = check_launch("nb_mlp_fwd"))) return rc;
+      return d->y_f32 ? nb_cl_launch(nb_cl_fwd_kernel<true>, d, smem, st, "nb_cl_fwd", 2)
+                      : nb_cl_launch(nb_cl_fwd_kernel<false>, d, smem, st, "nb_cl_fwd", 2);
+    }
     if (d->y_f32) return nb_cl_launch(nb_cl_fwd_kernel<true>, d, smem, st, "nb_cl_fwd");
     return nb_cl_launch(nb_cl_fwd_kernel<false>, d, smem, st, "nb_cl_fwd");
   }
@@ -2436,16 +2753,22 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     }
     int CLn, slice;
     nb_cl_geometry(d, &CLn, &slice);
-    if ((rc = nb_cl_launch(nb_cl_bwd_kernel, d, nb_cl_bwd_smem(C, slice), st, "nb_cl_bwd"))) return rc;
+    if (nb_mlp_batched(d, CLn, true)) {
+      static bool attr2 = false;
+      if (!attr2) {
+        cudaFuncSetAttribute(nb_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * MLP_NS) * 1024 * 4);
+        attr2 = true;
+      }
+      if ((rc = nb_cl_launch(nb_cl_bwd_kernel, d, nb_cl_bwd_smem(C, slice), st, "nb_cl_bwd", 1))) return rc;
+      nb_mlp_bwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + 2 * MLP_NS) * C * sizeof(float), st>>>(
+          N, HW, C, d->Cr, d->w1, d->w2, d->beta, d->nc, d->bwd_nc, d->bwd_h, d->dgamma, d->dbeta);
+      if ((rc = check_launch("nb_mlp_bwd"))) return rc;
+      if ((rc = nb_cl_launch(nb_cl_bwd_kernel, d, nb_cl_bwd_smem(C, slice), st, "nb_cl_bwd", 2))) return rc;
+    } else if ((rc = nb_cl_launch(nb_cl_bwd_kernel, d, nb_cl_bwd_smem(C, slice), st, "nb_cl_bwd"))) {
+      return rc;
+    }
     if (d->has_cbam) {
-      int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
-      if (nsplit > N) nsplit = N;
-      if (nsplit > 32) nsplit = 32;
-      if (nsplit < 1) nsplit = 1;
-      const int npb = ceil_div(N, nsplit);
-      dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
-      nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
-      if ((rc = check_launch("nb_bwd_w"))) return rc;
+      if ((rc = launch_bwd_w(d, st))) return rc;
     }
     return BVAE_OK;
   }
@@ -2458,14 +2781,7 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     nb_small_bwd_kernel<<<N, 256, nb_small_bwd_smem(C), st>>>(*d);
     if ((rc = check_launch("nb_small_bwd"))) return rc;
     if (d->has_cbam) {
-      int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
-      if (nsplit > N) nsplit = N;
-      if (nsplit > 32) nsplit = 32;
-      if (nsplit < 1) nsplit = 1;
-      const int npb = ceil_div(N, nsplit);
-      dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
-      nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
-      if ((rc = check_launch("nb_bwd_w"))) return rc;
+      if ((rc = launch_bwd_w(d, st))) return rc;
     }
     return BVAE_OK;
   }
@@ -2526,14 +2842,7 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
                                           d->dbeta, d->bwd_h);
   if ((rc = check_launch("nb_bwd_coef"))) return rc;
   if (d->has_cbam) {
-    int nsplit = ceil_div(148 * 8, ceil_div(C * d->Cr, 256));
-    if (nsplit > N) nsplit = N;
-    if (nsplit > 32) nsplit = 32;
-    if (nsplit < 1) nsplit = 1;
-    const int npb = ceil_div(N, nsplit);
-    dim3 gw(ceil_div(C * d->Cr, 256), ceil_div(N, npb));
-    nb_bwd_w_kernel<<<gw, 256, 0, st>>>(N, C, d->Cr, d->nc, d->beta, d->bwd_nc, d->bwd_h, d->dw1, d->dw2, npb);
-    if ((rc = check_launch("nb_bwd_w"))) return rc;
+    if ((rc = launch_bwd_w(d, st))) return rc;
   }
   const size_t sm5 = 6 * C * sizeof(float);
   if (fast) {
