@@ -27,7 +27,8 @@ __device__ __forceinline__ void load8(const void* base, int64_t off, float* f) {
 // forward 1: per-(n,c) shifted sums and extrema (with first-index tie break) of the raw conv output
 // grid (ceil(C/256), psplit, N), block 256
 // ---------------------------------------------------------------------------------------------------
-template <bool F32>
+// EXT = false (sites without CBAM): only the sums -- nothing consumes the extrema or their positions there
+template <bool F32, bool EXT>
 __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict__ y, int pitch, int HW, int C,
                                                        int psplit, float2* __restrict__ ss, u64* __restrict__ kmax,
                                                        u64* __restrict__ kmin) {
@@ -71,8 +72,10 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
         const float dlt = v[u][i] - shift[i];
         sum[i] += dlt;
         sq[i] += dlt * dlt;
-        if (v[u][i] > vmx[i]) { vmx[i] = v[u][i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
-        if (v[u][i] < vmn[i]) { vmn[i] = v[u][i]; imn[i] = p; }
+        if (EXT) {
+          if (v[u][i] > vmx[i]) { vmx[i] = v[u][i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
+          if (v[u][i] < vmn[i]) { vmn[i] = v[u][i]; imn[i] = p; }
+        }
       }
     }
   }
@@ -86,9 +89,11 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
     for (int i = 0; i < 8; ++i) {
       sum[i] += __shfl_xor_sync(0xffffffffu, sum[i], o);
       sq[i] += __shfl_xor_sync(0xffffffffu, sq[i], o);
-      const u64 a = __shfl_xor_sync(0xffffffffu, kx[i], o), b = __shfl_xor_sync(0xffffffffu, kn[i], o);
-      kx[i] = a > kx[i] ? a : kx[i];
-      kn[i] = b > kn[i] ? b : kn[i];
+      if (EXT) {
+        const u64 a = __shfl_xor_sync(0xffffffffu, kx[i], o), b = __shfl_xor_sync(0xffffffffu, kn[i], o);
+        kx[i] = a > kx[i] ? a : kx[i];
+        kn[i] = b > kn[i] ? b : kn[i];
+      }
     }
   }
   if (grp == 0) {
@@ -96,8 +101,10 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
     for (int i = 0; i < 8; ++i) {
       atomicAdd(&s_sum[cl + i], sum[i]);
       atomicAdd(&s_sq[cl + i], sq[i]);
-      atomicMax(&s_kmax[cl + i], kx[i]);
-      atomicMax(&s_kmin[cl + i], kn[i]);
+      if (EXT) {
+        atomicMax(&s_kmax[cl + i], kx[i]);
+        atomicMax(&s_kmin[cl + i], kn[i]);
+      }
     }
   }
   __syncthreads();
@@ -110,8 +117,10 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
     } else {
       atomicAdd(&ss[o].x, s_sum[threadIdx.x]);
       atomicAdd(&ss[o].y, s_sq[threadIdx.x]);
-      atomicMax(&kmax[o], s_kmax[threadIdx.x]);
-      atomicMax(&kmin[o], s_kmin[threadIdx.x]);
+      if (EXT) {
+        atomicMax(&kmax[o], s_kmax[threadIdx.x]);
+        atomicMax(&kmin[o], s_kmin[threadIdx.x]);
+      }
     }
   }
 }
@@ -214,7 +223,8 @@ __global__ void __launch_bounds__(256) nb_coef_kernel(const void* __restrict__ y
       mean = shift + md;
       const float var = fmaxf(s.y * inv - md * md, 0.f);
       rstd = rsqrtf(var + eps);
-      if (g * rstd >= 0.f) { const u64 k = kmax[o]; yext = key_val(k); idx = key_idx(k); }
+      if (!has_cbam) { yext = mean; idx = 0; }          // the extrema only feed the channel attention
+      else if (g * rstd >= 0.f) { const u64 k = kmax[o]; yext = key_val(k); idx = key_idx(k); }
       else { const u64 k = kmin[o]; yext = -key_val(k); idx = key_idx(k); }
     }
     const float a = g * rstd, b = b0 - mean * a;
@@ -2665,8 +2675,13 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
       if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
     }
     dim3 g1(cchunks, psplit, N);
-    if (d->y_f32) nb_stats_kernel<true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
-    else nb_stats_kernel<false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+    if (d->has_cbam) {
+      if (d->y_f32) nb_stats_kernel<true, true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+      else nb_stats_kernel<false, true><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+    } else {
+      if (d->y_f32) nb_stats_kernel<true, false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+      else nb_stats_kernel<false, false><<<g1, 256, 0, st>>>(d->y, d->y_pitch, HW, C, psplit, ss, kmax, kmin);
+    }
     if ((rc = check_launch("nb_stats"))) return rc;
   }
 
