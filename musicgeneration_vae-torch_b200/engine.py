@@ -13,6 +13,7 @@ PyTorch here is device memory + streams only; all arithmetic on the hot path hap
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -51,6 +52,39 @@ def set_fuse_stats(flag: bool):
 
 def bump_param_epoch():
     _PARAM_EPOCH[0] += 1
+
+
+# ---- weight gradients on a companion stream ------------------------------------------------------------------
+# Nothing in a backward pass waits for a weight gradient until the optimiser: inside `async_wgrad()` every
+# GemmLayer.wgrad launch goes to a stream paired with the current one, so the tensor-bound weight-gradient kernels run
+# next to the HBM-bound norm-block sweeps of the data-gradient chain.  Leaving the context makes the current stream wait
+# for the companion.  BVAE_WGRAD_STREAM=0 disables.
+_WGRAD_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
+_WGRAD_ASYNC = [0]
+
+
+def _wgrad_pair():
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    ws = _WGRAD_STREAMS.get(key)
+    if ws is None:
+        ws = _WGRAD_STREAMS[key] = torch.cuda.Stream(device=cur.device)
+    return cur, ws
+
+
+class async_wgrad:
+    def __enter__(self):
+        self.on = os.environ.get("BVAE_WGRAD_STREAM", "1") != "0"
+        if self.on:
+            _WGRAD_ASYNC[0] += 1
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            _WGRAD_ASYNC[0] -= 1
+            cur, ws = _wgrad_pair()
+            cur.wait_stream(ws)
+        return False
 
 
 # ---- live per-kernel-class timing with CUDA events (bench.py's roofline block) -----------------------------
@@ -368,7 +402,18 @@ class GemmLayer:
                          mask_slope, "d")
 
     def wgrad(self, x: Act, dy: Act):
-        """weight.grad += conv_backward_weight(x, dy); bias.grad += column sums of dy."""
+        """weight.grad += conv_backward_weight(x, dy)  (on the companion stream inside engine.async_wgrad())."""
+        if _WGRAD_ASYNC[0] and self.weight.requires_grad:
+            cur, ws = _wgrad_pair()
+            ws.wait_stream(cur)                      # x and dy are complete at this point of the current stream
+            x.t.record_stream(ws)
+            dy.t.record_stream(ws)
+            with torch.cuda.stream(ws):
+                self._wgrad_launch(x, dy)
+            return
+        self._wgrad_launch(x, dy)
+
+    def _wgrad_launch(self, x: Act, dy: Act):
         lib = _lib.lib()
         st = _lib.stream_ptr()
         if self.weight.requires_grad:

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..engine import BF16, Act, grad_ptr, raw_dtype
+from ..engine import BF16, Act, async_wgrad, grad_ptr, raw_dtype
 from .cbam import CBAM
 from .encodingBlock import _norm, gemm_of, norm_block
 from .weights_initializer import weights_init
@@ -159,7 +159,8 @@ class _DecoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, drecon):
-        dz, dpz, dpf = ctx.module._bwd(ctx.saved, drecon)
+        with async_wgrad():
+            dz, dpz, dpf = ctx.module._bwd(ctx.saved, drecon)
         ctx.saved = None
         return (None, dz, dpz, dpf, None, None) + (None,) * len(ctx.module._plist)
 

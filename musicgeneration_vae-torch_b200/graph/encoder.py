@@ -4,7 +4,7 @@ the hand-written data/weight-gradient kernels and accumulates straight into the 
 import torch
 import torch.nn as nn
 
-from ..engine import BF16, Act
+from ..engine import BF16, Act, async_wgrad
 from .encodingBlock import PitchTimeModule, PoolingModule, ResidualModule, TimePitchModule, gemm_of
 from .weights_initializer import weights_init
 
@@ -15,12 +15,22 @@ class _TrunkFn(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         z, saved = module._fwd(x, need)
         ctx.module, ctx.saved = module, saved
+        ctx.stream = torch.cuda.current_stream()
         return z
 
     @staticmethod
     def backward(ctx, dz):
-        ctx.module._bwd(ctx.saved, dz)
+        with async_wgrad():
+            ctx.module._bwd(ctx.saved, dz)
         ctx.saved = None
+        # The parameter gradients are written by our kernels on THIS node's stream (autograd replays the forward
+        # stream) and are not returned to autograd, so its end-of-backward stream sync does not cover them: when the
+        # node ran on a side stream, make the stream that called backward() wait for it.
+        cur = torch.cuda.current_stream()
+        if cur != torch.cuda.default_stream(cur.device):
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: torch.cuda.current_stream().wait_event(ev))
         return (None, None) + (None,) * len(ctx.module._plist)
 
 

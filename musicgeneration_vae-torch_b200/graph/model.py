@@ -8,6 +8,8 @@ exactly like the reference's own runnable composition graph/model_with_gan.py:20
 ``vae_head=True`` adds the reparameterise + KL head of the archived generation
 (old/graphs/models/bar_v1/encoder.py:55-63): forward then returns ``(recon, mu, logvar)``.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -100,10 +102,35 @@ class Model(nn.Module):
         and the NCCL gradient all-reduce.  state_dict()/load_state_dict() keep working (parameters become views)."""
         return flatten(self)
 
+    def _phrase_branch(self, phrase):
+        """The phrase encoder does not depend on the bar encoder: run it on a second stream so that its latency-bound
+        small-map kernels and every kernel's tail overlap the other branch (autograd runs the backward node on the
+        same stream; _TrunkFn.backward makes the caller's stream wait for it).  BVAE_STREAMS=0 disables."""
+        if os.environ.get("BVAE_STREAMS", "1") == "0" or not phrase.is_cuda:
+            return self.phrase_encoder(phrase)
+        main = torch.cuda.current_stream()
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != phrase.device:
+            side = self._side_stream = torch.cuda.Stream(device=phrase.device)
+        side.wait_stream(main)
+        phrase.record_stream(side)
+        with torch.cuda.stream(side):
+            pf = self.phrase_encoder(phrase)
+        self._phrase_join = (main, side, pf)
+        return pf
+
+    def _join_phrase(self):
+        j = getattr(self, "_phrase_join", None)
+        if j is not None:
+            main, side, pf = j
+            main.wait_stream(side)
+            pf.record_stream(main)
+            self._phrase_join = None
+
     def forward(self, note, pre_note, phrase, position, is_train=True, dropout_masks=None, eps=None):
         if is_train:
             B = note.shape[0]
-            phrase_feature = self.phrase_encoder(phrase)
+            phrase_feature = self._phrase_branch(phrase)
             # encoder(note) and encoder(pre_note) share weights and have no batch-coupled op (InstanceNorm is
             # per sample): one pass over 2B bars (model.py:26-27)
             zz = self.encoder(torch.cat((note, pre_note), 0))
@@ -115,11 +142,14 @@ class Model(nn.Module):
                 e1, e2 = (None, None) if eps is None else eps
                 z = reparameterize(mu, logvar, e1)
                 pre_z = reparameterize(pre_mu, pre_logvar, e2)
+                self._join_phrase()
                 recon = self.decoder(z, pre_z, phrase_feature, position, dropout_masks)
                 self.last_pre = (pre_mu, pre_logvar)
                 return recon, mu, logvar
+            self._join_phrase()
             gen_note = self.decoder(z, pre_z, phrase_feature, position, dropout_masks)
             return gen_note, z, pre_z, phrase_feature
-        phrase_feature = self.phrase_encoder(phrase)
+        phrase_feature = self._phrase_branch(phrase)
         pre_z = self.encoder(pre_note)
+        self._join_phrase()
         return self.decoder(note, pre_z, phrase_feature, position, dropout_masks)
