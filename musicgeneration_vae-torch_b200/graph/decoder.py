@@ -162,6 +162,9 @@ class _DecoderFn(torch.autograd.Function):
         with async_wgrad():
             dz, dpz, dpf = ctx.module._bwd(ctx.saved, drecon)
         ctx.saved = None
+        cb = getattr(ctx.module, "_bvae_on_bwd_done", None)  # parallel.GradReducer: decoder gradients are complete
+        if cb is not None:                                   # (after the weight-gradient stream has been joined)
+            cb()
         return (None, dz, dpz, dpf, None, None) + (None,) * len(ctx.module._plist)
 
 
@@ -278,7 +281,4 @@ class Decoder(nn.Module):
         if emb_w.requires_grad:
             grad_ptr(emb_w)
             emb_w.grad.index_add_(0, position, dpc_f[:, 1152:])
-        cb = getattr(self, "_bvae_on_bwd_done", None)      # parallel.GradReducer: decoder gradients are complete
-        if cb is not None:
-            cb()
         return dbc_f[:, :1152].contiguous(), dbc_f[:, 1152:].contiguous(), dpc_f[:, :1152].contiguous()

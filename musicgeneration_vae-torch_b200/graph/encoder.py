@@ -23,6 +23,9 @@ class _TrunkFn(torch.autograd.Function):
         with async_wgrad():
             ctx.module._bwd(ctx.saved, dz)
         ctx.saved = None
+        cb = getattr(ctx.module, "_bvae_on_bwd_done", None)  # parallel.GradReducer: this segment's gradients are complete
+        if cb is not None:                                   # (after the weight-gradient stream has been joined)
+            cb()
         # The parameter gradients are written by our kernels on THIS node's stream (autograd replays the forward
         # stream) and are not returned to autograd, so its end-of-backward stream sync does not cover them: when the
         # node ran on a side stream, make the stream that called backward() wait for it.
@@ -90,9 +93,6 @@ class _EncoderTrunk(nn.Module):
             d = layer.bwd(c, d)
         self.time_pitch.bwd(c_tp, d.slice(32, 32))
         self.pitch_time.bwd(c_pt, d.slice(0, 32))
-        cb = getattr(self, "_bvae_on_bwd_done", None)      # parallel.GradReducer: this segment's gradients are complete
-        if cb is not None:
-            cb()
 
 
 class Encoder(_EncoderTrunk):
