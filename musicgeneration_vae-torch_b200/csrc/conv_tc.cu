@@ -60,6 +60,16 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// shared -> global tiled store (bulk async group); out-of-bounds elements of the box are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -191,6 +201,9 @@ struct alignas(64) ConvTcParams {
   float slope, mask_slope;
   // halo mode (stride-1 multi-tap layers with resident weights): ONE activation tile with its halo is loaded per
   // (output tile, K chunk) and every tap reads it through a row-shifted shared-memory descriptor
+  // TMA-store epilogue (fp32 outputs, BN <= 128): one output tensor map per phase, box {32 floats, bw, bh, bn}
+  CUtensorMap ymap[BVAE_MAX_PHASES];
+  int tma_store;
   int halo, halo_x0, halo_y0, halo_rows, halo_stage, halo_stages;
   int halo_shift[BVAE_MAX_TAPS];
 };
@@ -391,6 +404,8 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
   uint64_t* tempty = tfull + 2;               // [2]
   uint64_t* bres_bar = tempty + 2;
   uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
+  // two 16 KB slabs [128 rows][32 floats], 128B-swizzled, for the TMA-store epilogue
+  uint8_t* ystage = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);
   const bool halo = BRES && KB == 64 && p.halo;
   const uint32_t nst = halo ? (uint32_t)p.halo_stages : (uint32_t)STAGES;      // ring depth / stage size in use
   const uint32_t stage_bytes = halo ? (uint32_t)p.halo_stage : (uint32_t)STAGE_BYTES;
@@ -546,6 +561,69 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       mbar_wait(tfull + ab, aph);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(wq * 32) << 16);
+      if (BN <= 128 && p.tma_store) {
+        // fp32 output through shared memory and one tiled TMA store per 32-column slab: the direct path issues, per
+        // warp instruction, 32 separate 16-byte requests to 32 different rows (2048 L1 requests per 128x64 tile), which
+        // made the epilogue the longest stage of the small-K layers
+        constexpr int SLABS = BN / 32;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)c0, v);
+          if (c0 + 32 >= BN) { tc_fence_before(); mbar_arrive(tempty + ab); }     // accumulator drained
+          const uint32_t sl = ti * SLABS + (uint32_t)(c0 >> 5);
+          uint8_t* slab = ystage + (sl & 1u) * 16384u;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c0 + i));
+              f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+            }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = act_fwd(f[i], p.slope);
+          }
+          if (p.addend && valid) {
+            const float* ap = (const float*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(ap + i);
+              f[i] += a.x; f[i + 1] += a.y; f[i + 2] += a.z; f[i + 3] += a.w;
+            }
+          }
+          if (p.mask && valid) {
+            const bf16* mp = (const bf16*)p.mask + opix * p.mask_pitch + col0 + c0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              float a[8];
+              unpack8(ldg8(mp + i), a);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[i + k] *= (a[k] > 0.f) ? 1.f : p.mask_slope;
+            }
+          }
+          // the store issued from this slab buffer two slabs ago must have finished reading it
+          if (r == 0) tma_store_wait_read<1>();
+          epi_bar_sync();
+          {
+            uint8_t* row = slab + r * 128;
+            const int sw = r & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (r == 0) {
+            tma_store_4d(&p.ymap[ph], slab, col0 + c0, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
 #pragma unroll(PRE ? 2 : 1)
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -648,6 +726,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       mbar_arrive(tempty + ab);                    // 128 arrivals release the accumulator buffer
     }
   }
+  if (threadIdx.x == 128 && BN <= 128 && p.tma_store) tma_store_wait_all();      // thread r == 0 of the epilogue
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -987,6 +1066,23 @@ static int make_view_map(CUtensorMap* m, const void* base, int C, int Wv, int Hv
   return BVAE_OK;
 }
 
+// fp32 output view {C, Wv, Hv, N} (strides in elements), box {32 floats = 128 B, bw, bh, bn}, 128B swizzle
+static int make_out_map_f32(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int N, int64_t sw_elems,
+                            int64_t sh_elems, int64_t sn_elems, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)sw_elems * 4, (cuuint64_t)sh_elems * 4, (cuuint64_t)sn_elems * 4};
+  cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled(out f32) failed: %d (dims %d,%d,%d,%d box %d,%d,%d)",
+               (int)r, C, Wv, Hv, N, bw, bh, bn);
+  return BVAE_OK;
+}
+
 static int make_w_map(CUtensorMap* m, const void* base, int K, int rows, int pitch, int box_k, int box_rows, bool sw128) {
   EncodeTiledFn enc = get_encode();
   BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
@@ -1118,11 +1214,12 @@ template <int KB, int BN, bool BRES>
 static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t stream) {
   constexpr int B_BYTES = BN * KB * 2;
   constexpr int STAGE = BRES ? 128 * KB * 2 : 128 * KB * 2 + B_BYTES;
-  constexpr int BUDGET = BRES ? 128 * 1024 : 200 * 1024;        // resident weights take up to 72 KB of their own
+  constexpr int YSTAGE = BN <= 128 ? 33 * 1024 : 0;             // two output slabs of the TMA-store epilogue (+ alignment)
+  constexpr int BUDGET = (BRES ? 128 * 1024 : 200 * 1024) - YSTAGE;   // resident weights take up to 72 KB of their own
   constexpr int ST_RAW = BUDGET / STAGE;
   // small-channel layers are bound by the bytes in flight per SM (8 KB stages): give them a deep ring
   constexpr int STAGES = ST_RAW > 16 ? 16 : ST_RAW;
-  const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 16;
+  const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 32 + YSTAGE;
   static int attr_smem = 0;
   static int num_sms = 148;
   if (smem > attr_smem) {
@@ -1143,6 +1240,13 @@ static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) 
   // weights resident in shared memory when one N tile covers Cout and all taps fit in 96 KB
   const bool bres = P.n_tiles == 1 && (long)P.ntaps * P.kchunks * (BN * KB * 2) <= 72 * 1024 && tiles >= 2 * 148;
   return bres ? launch_conv2_impl<KB, BN, true>(P, tiles, stream) : launch_conv2_impl<KB, BN, false>(P, tiles, stream);
+}
+
+// BVAE_CONV_TMA_STORE=0 selects the direct-store epilogue for fp32 outputs
+static bool conv_tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_CONV_TMA_STORE"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
 }
 
 // BVAE_CONV_HALO: 0 = off, 1 = on (default)
@@ -1176,13 +1280,13 @@ static int plan_halo(const bvae_conv_desc* d, ConvTcParams* P, int KB, int BN) {
   if (reach < rows) reach = rows;
   const int stage = ((reach * 128 + 1023) / 1024) * 1024;
   const long tiles = (long)d->N * ceil_div(QH, RH);
-  if (RH + dy1 - dy0 > 256 || QW * RH * 10 < 128 * 8 || stage > 64 * 1024 || tiles < 2 * 148) return BVAE_OK;
+  if (RH + dy1 - dy0 > 256 || QW * RH * 10 < 128 * 8 || stage > 40 * 1024 || tiles < 2 * 148) return BVAE_OK;
   int rc = make_view_map(&P->amap[0], d->x, d->C, d->W, d->H, d->N, d->x_pitch, (int64_t)d->W * d->x_pitch,
                          (int64_t)d->H * d->W * d->x_pitch, KB, PW, RH + dy1 - dy0, 1, true);
   if (rc) return rc;
   P->halo = 1;
   P->halo_x0 = dx0; P->halo_y0 = dy0; P->halo_rows = rows; P->halo_stage = stage;
-  P->halo_stages = (128 * 1024) / stage;                     // the BRES ring region (see launch_conv2_impl)
+  P->halo_stages = (80 * 1024) / stage;                      // the BRES ring region: 5 stages of 16 KB (launch_conv2_impl)
   for (int t = 0; t < d->ntaps; ++t) P->halo_shift[t] = (d->dy[t] - dy0) * PW + (d->dx[t] - dx0);
   P->bw = PW; P->bh = RH; P->bn = 1;
   P->tiles_w = 1; P->tiles_h = ceil_div(QH, RH); P->tiles_n = d->N;
@@ -1243,6 +1347,16 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   P.slope = d->slope; P.mask_slope = d->mask_slope;
   rc = plan_halo(d, &P, KB, BN);
   if (rc) return rc;
+  if (conv_tma_store_enabled() && !use_conv_v1() && d->out_f32 && !d->stats && BN <= 128 && d->y_pitch % 4 == 0 &&
+      ((uintptr_t)d->y & 15) == 0) {
+    for (int i = 0; i < P.nphase; ++i) {
+      const float* base = (const float*)d->y + ((int64_t)P.ph_ooy[i] * d->OW + P.ph_oox[i]) * d->y_pitch;
+      rc = make_out_map_f32(&P.ymap[i], base, d->Cout, P.ph_QW[i], P.ph_QH[i], d->N, (int64_t)d->osx * d->y_pitch,
+                            (int64_t)d->osy * d->OW * d->y_pitch, (int64_t)d->OH * d->OW * d->y_pitch, P.bw, P.bh, P.bn);
+      if (rc) return rc;
+    }
+    P.tma_store = 1;
+  }
   const long grid = (long)P.tiles_w * P.tiles_h * P.tiles_n * P.n_tiles * P.nphase;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "conv_tc: grid too large");
   BVAE_REQUIRE(P.nphase == 1 || !use_conv_v1(), BVAE_ERR_UNSUPPORTED, "conv_tc: multi-phase needs the persistent kernel");
