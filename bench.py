@@ -288,11 +288,23 @@ def main():
     extra = {}
     if not args.no_profile:
         prof_steps = 2
+        # per-kernel CUDA-event timing needs the launches serialised on one stream: switch the branch / weight-gradient
+        # stream overlap off for these (untimed) profiling steps only
+        saved_env = {k: os.environ.get(k) for k in ("BVAE_STREAMS", "BVAE_WGRAD_STREAM")}
+        os.environ["BVAE_STREAMS"] = "0"
+        os.environ["BVAE_WGRAD_STREAM"] = "0"
+        step_resident()
+        torch.cuda.synchronize()
         eng.profile_begin()
         for _ in range(prof_steps):
             step_resident()
         torch.cuda.synchronize()
         prof = eng.profile_end()
+        for k, v in saved_env.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
         detail = prof.pop("detail", {})
         if os.environ.get("BVAE_PROFILE_DETAIL") and rank == 0:
             for k, (t, n) in sorted(detail.items(), key=lambda kv: -kv[1][0]):

@@ -201,7 +201,7 @@ struct alignas(64) ConvTcParams {
   float slope, mask_slope;
   // halo mode (stride-1 multi-tap layers with resident weights): ONE activation tile with its halo is loaded per
   // (output tile, K chunk) and every tap reads it through a row-shifted shared-memory descriptor
-  // TMA-store epilogue (fp32 outputs, BN <= 128): one output tensor map per phase, box {32 floats, bw, bh, bn}
+  // TMA-store epilogue (BN <= 128): one output tensor map per phase, box {32 floats or 64 bf16, bw, bh, bn}
   CUtensorMap ymap[BVAE_MAX_PHASES];
   int tma_store;
   int halo, halo_x0, halo_y0, halo_rows, halo_stage, halo_stages;
@@ -562,16 +562,19 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       tc_fence_after();
       const uint32_t tacc = tmem_base + ab * ACC_COLS + ((uint32_t)(wq * 32) << 16);
       if (BN <= 128 && p.tma_store) {
-        // fp32 output through shared memory and one tiled TMA store per 32-column slab: the direct path issues, per
-        // warp instruction, 32 separate 16-byte requests to 32 different rows (2048 L1 requests per 128x64 tile), which
-        // made the epilogue the longest stage of the small-K layers
-        constexpr int SLABS = BN / 32;
-#pragma unroll 1
+        // Output through shared memory and one tiled TMA store per 128-byte-wide slab (32 fp32 / 64 bf16 columns):
+        // the direct path issues, per warp instruction, 32 separate 16-byte requests to 32 different rows (2048 L1
+        // requests per 128x64 fp32 tile), which made the epilogue the longest stage of the small-K layers.  Rows and
+        // columns outside the output are clipped by the store.
+        const int CS = p.out_f32 ? 32 : 64;                 // columns per slab
+        const uint32_t slabs = (uint32_t)(BN / CS);
+#pragma unroll(PRE ? 2 : 1)
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c0, v);
           if (c0 + 32 >= BN) { tc_fence_before(); mbar_arrive(tempty + ab); }     // accumulator drained
-          const uint32_t sl = ti * SLABS + (uint32_t)(c0 >> 5);
+          const int cs0 = c0 & ~(CS - 1);                   // first column of this slab
+          const uint32_t sl = ti * slabs + (uint32_t)(cs0 / CS);
           uint8_t* slab = ystage + (sl & 1u) * 16384u;
           float f[32];
 #pragma unroll
@@ -588,11 +591,22 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
             for (int i = 0; i < 32; ++i) f[i] = act_fwd(f[i], p.slope);
           }
           if (p.addend && valid) {
-            const float* ap = (const float*)p.addend + opix * p.add_pitch + col0 + c0;
+            if (p.out_f32) {
+              const float* ap = (const float*)p.addend + opix * p.add_pitch + col0 + c0;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 a = *reinterpret_cast<const float4*>(ap + i);
-              f[i] += a.x; f[i + 1] += a.y; f[i + 2] += a.z; f[i + 3] += a.w;
+              for (int i = 0; i < 32; i += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(ap + i);
+                f[i] += a.x; f[i + 1] += a.y; f[i + 2] += a.z; f[i + 3] += a.w;
+              }
+            } else {
+              const bf16* ap = (const bf16*)p.addend + opix * p.add_pitch + col0 + c0;
+#pragma unroll
+              for (int i = 0; i < 32; i += 8) {
+                float a[8];
+                unpack8((PRE && pre_add) ? pre_a[PRE ? ((c0 + i) / 8) % NPRE : 0] : ldg8(ap + i), a);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[i + k] += a[k];
+              }
             }
           }
           if (p.mask && valid) {
@@ -600,25 +614,35 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
               float a[8];
-              unpack8(ldg8(mp + i), a);
+              unpack8((PRE && pre_mask) ? pre_m[PRE ? ((c0 + i) / 8) % NPRE : 0] : ldg8(mp + i), a);
 #pragma unroll
               for (int k = 0; k < 8; ++k) f[i + k] *= (a[k] > 0.f) ? 1.f : p.mask_slope;
             }
           }
-          // the store issued from this slab buffer two slabs ago must have finished reading it
-          if (r == 0) tma_store_wait_read<1>();
-          epi_bar_sync();
-          {
-            uint8_t* row = slab + r * 128;
-            const int sw = r & 7;
+          uint8_t* row = slab + r * 128;
+          const int sw = r & 7;
+          if (p.out_f32) {
+            // the store issued from this slab buffer two slabs ago must have finished reading it
+            if (r == 0) tma_store_wait_read<1>();
+            epi_bar_sync();
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            const int half = (c0 - cs0) >> 5;               // which 64-byte half of the 128-byte row
+            if (half == 0) {
+              if (r == 0) tma_store_wait_read<1>();
+              epi_bar_sync();
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(row + (((4 * half + j) ^ sw) << 4)) = pack8(f + 8 * j);
+            if (half == 0) continue;                        // the slab is complete after its second half
           }
           fence_proxy_async();
           epi_bar_sync();
           if (r == 0) {
-            tma_store_4d(&p.ymap[ph], slab, col0 + c0, tw * p.bw, th * p.bh, tn * p.bn);
+            tma_store_4d(&p.ymap[ph], slab, col0 + cs0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
         }
@@ -1066,19 +1090,20 @@ static int make_view_map(CUtensorMap* m, const void* base, int C, int Wv, int Hv
   return BVAE_OK;
 }
 
-// fp32 output view {C, Wv, Hv, N} (strides in elements), box {32 floats = 128 B, bw, bh, bn}, 128B swizzle
-static int make_out_map_f32(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int N, int64_t sw_elems,
-                            int64_t sh_elems, int64_t sn_elems, int bw, int bh, int bn) {
+// output view {C, Wv, Hv, N} (strides in elements), box {128 B of channels (32 floats / 64 bf16), bw, bh, bn}, 128B swizzle
+static int make_out_map(CUtensorMap* m, const void* base, bool f32, int C, int Wv, int Hv, int N, int64_t sw_elems,
+                        int64_t sh_elems, int64_t sn_elems, int bw, int bh, int bn) {
   EncodeTiledFn enc = get_encode();
   BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t es_ = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)sw_elems * 4, (cuuint64_t)sh_elems * 4, (cuuint64_t)sn_elems * 4};
-  cuuint32_t box[4] = {32u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint64_t strides[3] = {(cuuint64_t)sw_elems * es_, (cuuint64_t)sh_elems * es_, (cuuint64_t)sn_elems * es_};
+  cuuint32_t box[4] = {f32 ? 32u : 64u, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled(out f32) failed: %d (dims %d,%d,%d,%d box %d,%d,%d)",
+  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled(out) failed: %d (dims %d,%d,%d,%d box %d,%d,%d)",
                (int)r, C, Wv, Hv, N, bw, bh, bn);
   return BVAE_OK;
 }
@@ -1347,12 +1372,14 @@ int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   P.slope = d->slope; P.mask_slope = d->mask_slope;
   rc = plan_halo(d, &P, KB, BN);
   if (rc) return rc;
-  if (conv_tma_store_enabled() && !use_conv_v1() && d->out_f32 && !d->stats && BN <= 128 && d->y_pitch % 4 == 0 &&
-      ((uintptr_t)d->y & 15) == 0) {
+  const bool f32o = d->out_f32 != 0;
+  if (conv_tma_store_enabled() && !use_conv_v1() && !d->stats && BN <= 128 && (f32o || BN >= 64) &&
+      d->y_pitch % (f32o ? 4 : 8) == 0 && ((uintptr_t)d->y & 15) == 0) {
     for (int i = 0; i < P.nphase; ++i) {
-      const float* base = (const float*)d->y + ((int64_t)P.ph_ooy[i] * d->OW + P.ph_oox[i]) * d->y_pitch;
-      rc = make_out_map_f32(&P.ymap[i], base, d->Cout, P.ph_QW[i], P.ph_QH[i], d->N, (int64_t)d->osx * d->y_pitch,
-                            (int64_t)d->osy * d->OW * d->y_pitch, (int64_t)d->OH * d->OW * d->y_pitch, P.bw, P.bh, P.bn);
+      const int64_t off = ((int64_t)P.ph_ooy[i] * d->OW + P.ph_oox[i]) * d->y_pitch;
+      const void* base = f32o ? (const void*)((const float*)d->y + off) : (const void*)((const bf16*)d->y + off);
+      rc = make_out_map(&P.ymap[i], base, f32o, d->Cout, P.ph_QW[i], P.ph_QH[i], d->N, (int64_t)d->osx * d->y_pitch,
+                        (int64_t)d->osy * d->OW * d->y_pitch, (int64_t)d->OH * d->OW * d->y_pitch, P.bw, P.bh, P.bn);
       if (rc) return rc;
     }
     P.tma_store = 1;
