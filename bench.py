@@ -316,7 +316,9 @@ def main():
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "traffic": None, "peak_source": how + " (sustained cuBLAS bf16)",
-                    "kernel": "conv_tc_kernel + wgrad_tc_kernel (all contraction launches of one step)",
+                    "kernel": "conv_tc2_kernel + wgrad_tc_kernel / wgrad_halo_kernel (all contraction launches of one step)",
+                    "how": "CUDA events around every launch on its launching stream, in a profiling pass with the "
+                           "branch / weight-gradient stream overlap switched off (the timed steps run with it on)",
                     "kernel_ms_per_step": gemm_ms, "launches_per_step": prof.get("n_gemm", 0) / prof_steps}
         extra = {"normblock_ms_per_step": nb_ms, "step_ms_under_event_profiling": prof.get("total_ms", 0.0) / prof_steps,
                  "adam_gbs": None}

@@ -61,6 +61,11 @@ def bump_param_epoch():
 # for the companion.  BVAE_WGRAD_STREAM=0 disables.
 _WGRAD_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
 _WGRAD_ASYNC = [0]
+# Operands of in-flight companion-stream launches are kept referenced until the join instead of record_stream()-ed:
+# record_stream defers the caching allocator's reuse of a block until an event query succeeds, and with the host
+# several steps ahead of the GPU those deferred frees pile up until the allocator falls back to cudaMalloc/cudaFree
+# (measured: sporadic 55-116 ms steps).  After the join every later use on the current stream is ordered anyway.
+_WGRAD_KEEP: Dict[tuple, list] = {}
 
 
 def _wgrad_pair():
@@ -84,6 +89,7 @@ class async_wgrad:
             _WGRAD_ASYNC[0] -= 1
             cur, ws = _wgrad_pair()
             cur.wait_stream(ws)
+            _WGRAD_KEEP.pop((cur.device.index, cur.cuda_stream), None)
         return False
 
 
@@ -406,8 +412,7 @@ class GemmLayer:
         if _WGRAD_ASYNC[0] and self.weight.requires_grad:
             cur, ws = _wgrad_pair()
             ws.wait_stream(cur)                      # x and dy are complete at this point of the current stream
-            x.t.record_stream(ws)
-            dy.t.record_stream(ws)
+            _WGRAD_KEEP.setdefault((cur.device.index, cur.cuda_stream), []).append((x.t, dy.t))
             with torch.cuda.stream(ws):
                 self._wgrad_launch(x, dy)
             return

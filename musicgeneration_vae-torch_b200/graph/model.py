@@ -113,7 +113,7 @@ class Model(nn.Module):
         if side is None or side.device != phrase.device:
             side = self._side_stream = torch.cuda.Stream(device=phrase.device)
         side.wait_stream(main)
-        phrase.record_stream(side)
+        phrase.record_stream(side)      # the caller may drop its input right after the call (one block per step)
         with torch.cuda.stream(side):
             pf = self.phrase_encoder(phrase)
         self._phrase_join = (main, side, pf)
@@ -123,8 +123,10 @@ class Model(nn.Module):
         j = getattr(self, "_phrase_join", None)
         if j is not None:
             main, side, pf = j
+            # no record_stream on the phrase feature: it is saved by the decoder node, and the side stream next touches
+            # its block only after side.wait_stream(main) of the following step (record_stream-ing every tensor that
+            # crosses streams made the caching allocator pile up deferred frees and fall back to cudaMalloc)
             main.wait_stream(side)
-            pf.record_stream(main)
             self._phrase_join = None
 
     def forward(self, note, pre_note, phrase, position, is_train=True, dropout_masks=None, eps=None):
