@@ -263,8 +263,7 @@ def main():
         trainer.step(*dbatch)
 
     def step_e2e():
-        b = tuple(t.to(dev, non_blocking=True) for t in hbatch)
-        loss = trainer.step(*b)
+        loss = trainer.step_from_host(*hbatch)      # pinned host tensors -> H2D copies -> step (public API)
         return loss.item()               # D2H read of the step's result, as agent/barGen.py:335 does
 
     for _ in range(max(3, args.warmup)):

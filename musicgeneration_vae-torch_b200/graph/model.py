@@ -102,6 +102,15 @@ class Model(nn.Module):
         and the NCCL gradient all-reduce.  state_dict()/load_state_dict() keep working (parameters become views)."""
         return flatten(self)
 
+    def side_stream(self, device):
+        """the stream the phrase encoder runs on (None when BVAE_STREAMS=0)"""
+        if os.environ.get("BVAE_STREAMS", "1") == "0":
+            return None
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != torch.device(device):
+            side = self._side_stream = torch.cuda.Stream(device=device)
+        return side
+
     def _phrase_branch(self, phrase):
         """The phrase encoder does not depend on the bar encoder: run it on a second stream so that its latency-bound
         small-map kernels and every kernel's tail overlap the other branch (autograd runs the backward node on the
@@ -109,9 +118,7 @@ class Model(nn.Module):
         if os.environ.get("BVAE_STREAMS", "1") == "0" or not phrase.is_cuda:
             return self.phrase_encoder(phrase)
         main = torch.cuda.current_stream()
-        side = getattr(self, "_side_stream", None)
-        if side is None or side.device != phrase.device:
-            side = self._side_stream = torch.cuda.Stream(device=phrase.device)
+        side = self.side_stream(phrase.device)
         side.wait_stream(main)
         phrase.record_stream(side)      # the caller may drop its input right after the call (one block per step)
         with torch.cuda.stream(side):

@@ -30,6 +30,22 @@ class GeneratorTrainer:
         engine.adam_step(self.flat, self.lr, self.step_count, self.betas, self.eps, scale)
         return loss.detach()
 
+    def step_from_host(self, note, pre_note, pre_phrase, position, dropout_masks=None):
+        """The same step from (pinned) HOST tensors, as the reference's loop feeds it (agent/barGen.py:302-311 moves
+        every batch with .cuda()).  The phrase tensor -- two thirds of the bytes -- is copied on the phrase encoder's
+        stream, so the bar encoder starts as soon as its own inputs have arrived."""
+        dev = self.flat.data.device
+        note_d = note.to(dev, non_blocking=True)
+        pre_d = pre_note.to(dev, non_blocking=True)
+        pos_d = position.to(dev, non_blocking=True)
+        side = self.model.side_stream(dev) if hasattr(self.model, "side_stream") else None
+        if side is None:
+            phrase_d = pre_phrase.to(dev, non_blocking=True)
+        else:
+            with torch.cuda.stream(side):
+                phrase_d = pre_phrase.to(dev, non_blocking=True)
+        return self.step(note_d, pre_d, phrase_d, pos_d, dropout_masks)
+
     # torch.optim-style state for checkpoints (agent/barGen.py:174-197)
     def state_dict(self):
         return {"step": self.step_count, "lr": self.lr,
