@@ -1241,6 +1241,156 @@ __global__ void __launch_bounds__(256, 3) nbf_bwd1_kernel(const bf16* __restrict
   flush_nc<1>(acc, G, sub, grp, C, sm, bwd_nc + (int64_t)n * C * BN_W, BN_DGC);
 }
 
+// CBAM sites, split form of the two reduction sweeps.  With du = ds*(direct + gc*g_p) + gc*dsp_p (dsp_p = dmean_p, plus
+// dmax_p on the pixel's arg-max channel) every per-(n,c) total is LINEAR in sums that either do not need the spatial
+// gradients (dmean, dmax) or do not need dout / out:
+//   S1  = direct*sum ds      + gc*sum ds*g      + gc*sum dsp
+//   S2  = direct*sum ds*uhat + gc*sum ds*g*uhat + gc*sum dsp*uhat
+//   dgc = gamma*sum ds*g*uhat + beta*sum ds*g   + gamma*sum dsp*uhat + beta*sum dsp
+// nbf_bwd1x accumulates the four ds-sums in the SAME sweep that produces dq (it also writes dres), nbf_bwd2x then only
+// sweeps uhat (2 B/element instead of 6) for the two dsp-sums.  Each CTA applies the per-channel factors to its partial
+// sums before the atomics, so the scratch layout {dgc, S1, S2} and everything downstream stay as they were.
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) nbf_bwd1x_kernel(const bf16* __restrict__ dout, int dout_pitch,
+                                                           const bf16* __restrict__ out, int out_pitch,
+                                                           const bf16* __restrict__ uhat, int HW, int C,
+                                                           const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, const float* __restrict__ gs,
+                                                           float slope, bf16* __restrict__ dres, int dres_pitch,
+                                                           float* __restrict__ bwd_nc, float* __restrict__ bwd_px, int ppc) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  float h_g[8], h_b[8], h_gc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    h_g[i] = __ldg(gamma + c + i);
+    h_b[i] = __ldg(beta + c + i);
+    h_gc[i] = __ldg(nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
+  }
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  const bf16* pu = uhat + q0 * C + c;
+  const bf16* po = out + q0 * out_pitch + c;
+  const bf16* pd = dout + q0 * dout_pitch + c;
+  bf16* pr = (MODE == 2 && dres) ? dres + q0 * dres_pitch + c : nullptr;
+  const float* pg = gs + q0;
+  float* pq = bwd_px + q0 * BP_W + BP_DQ;
+  const int64_t su = (int64_t)step * C, so = (int64_t)step * out_pitch, sd = (int64_t)step * dout_pitch;
+  const int64_t sr = (int64_t)step * dres_pitch;
+  float A1[8], A2[8], B1[8], B2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { A1[i] = 0.f; A2[i] = 0.f; B1[i] = 0.f; B2[i] = 0.f; }
+  for (; p < p_end + grp; p += 2 * step) {           // "+ grp": every lane of the warp runs the same trips (shuffles)
+    const bool v0 = p < p_end, v1 = p + step < p_end;
+    bf16x8 ru[2], ro[2], rd[2];
+    float g[2] = {0.f, 0.f};
+    if (v0) { ru[0] = ldg8(pu); ro[0] = ldg8(po); rd[0] = ldg8(pd); g[0] = pg[0]; }
+    if (v1) { ru[1] = ldg8(pu + su); ro[1] = ldg8(po + so); rd[1] = ldg8(pd + sd); g[1] = pg[step]; }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const bool v = u ? v1 : v0;
+      float dgs = 0.f;
+      if (v) {
+        float uh[8], ds[8];
+        unpack8(ru[u], uh);
+        nbf_ds8(rd[u], ro[u], slope, ds);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float dsg = ds[i] * g[u];
+          dgs = fmaf(ds[i] * fmaf(h_g[i], uh[i], h_b[i]), h_gc[i], dgs);
+          A1[i] += ds[i];
+          A2[i] += dsg;
+          B1[i] = fmaf(ds[i], uh[i], B1[i]);
+          B2[i] = fmaf(dsg, uh[i], B2[i]);
+        }
+        if (MODE == 2 && pr) stg8(pr + (int64_t)u * sr, pack8(ds));
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (v && sub == 0) pq[(int64_t)u * step * BP_W] = dgs * g[u] * (1.f - g[u]);
+    }
+    pu += 2 * su; po += 2 * so; pd += 2 * sd; pg += 2 * step; pq += (int64_t)2 * step * BP_W;
+    if (MODE == 2 && pr) pr += 2 * sr;
+  }
+  float s1[1][8], s2[1][8], sg[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    s1[0][i] = (MODE == 1 ? A1[i] : 0.f) + h_gc[i] * A2[i];
+    s2[0][i] = (MODE == 1 ? B1[i] : 0.f) + h_gc[i] * B2[i];
+    sg[0][i] = h_g[i] * B2[i] + h_b[i] * A2[i];
+  }
+  float* dst = bwd_nc + (int64_t)n * C * BN_W;
+  flush_nc<1>(s1, G, sub, grp, C, sm, dst, BN_S1);
+  flush_nc<1>(s2, G, sub, grp, C, sm, dst, BN_S2);
+  flush_nc<1>(sg, G, sub, grp, C, sm, dst, BN_DGC);
+}
+
+__global__ void __launch_bounds__(256, 3) nbf_bwd2x_kernel(const bf16* __restrict__ uhat, int HW, int C,
+                                                           const float* __restrict__ nc, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta,
+                                                           const int32_t* __restrict__ cidx,
+                                                           const float* __restrict__ bwd_px, float* __restrict__ bwd_nc,
+                                                           int ppc) {
+  extern __shared__ float sm[];
+  const int n = blockIdx.y, G = C >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (G - 1), grp = lane / G, gpw = 32 / G, c = sub * 8;
+  const int p_end = min(HW, (int)(blockIdx.x + 1) * ppc), step = 8 * gpw;
+  int p = blockIdx.x * ppc + warp * gpw + grp;
+  const int64_t q0 = (int64_t)n * HW + p;
+  const bf16* pu = uhat + q0 * C + c;
+  const float4* px4 = reinterpret_cast<const float4*>(bwd_px);
+  const int64_t su = (int64_t)step * C;
+  const float invC = 1.f / (float)C;
+  float SD[8], C1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { SD[i] = 0.f; C1[i] = 0.f; }
+  int64_t q = q0;
+  for (; p < p_end; p += 4 * step, q += 4 * step) {
+    bf16x8 ru[4];
+    float dmean[4], dmx[4];
+    int k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      dmean[u] = 0.f; dmx[u] = 0.f; k[u] = -1;
+      ru[u] = make_uint4(0, 0, 0, 0);
+      if (p + u * step < p_end) {
+        ru[u] = ldg8(pu + u * su);
+        const float4 v = px4[q + u * step];             // {dq, dmean, dmax, -}
+        dmean[u] = v.y * invC;
+        dmx[u] = dmean[u] + v.z;
+        k[u] = cidx[q + u * step] - c;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float uh[8];
+      unpack8(ru[u], uh);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float dsp = (i == k[u]) ? dmx[u] : dmean[u];
+        SD[i] += dsp;
+        C1[i] = fmaf(dsp, uh[i], C1[i]);
+      }
+    }
+    pu += 4 * su;
+  }
+  float s1[1][8], s2[1][8], sg[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float gc = __ldg(nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
+    s1[0][i] = gc * SD[i];
+    s2[0][i] = gc * C1[i];
+    sg[0][i] = __ldg(gamma + c + i) * C1[i] + __ldg(beta + c + i) * SD[i];
+  }
+  float* dst = bwd_nc + (int64_t)n * C * BN_W;
+  flush_nc<1>(s1, G, sub, grp, C, sm, dst, BN_S1);
+  flush_nc<1>(s2, G, sub, grp, C, sm, dst, BN_S2);
+  flush_nc<1>(sg, G, sub, grp, C, sm, dst, BN_DGC);
+}
+
 // backward 2: per-(n,c) S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u ; writes dres (MODE 2)
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) nbf_bwd2_kernel(const bf16* __restrict__ dout, int dout_pitch,
@@ -2569,6 +2719,13 @@ static int pick_ppc(int HW, int N, int G) {
   return ppc;
 }
 
+// BVAE_NB_SPLIT=0 keeps the two full reduction sweeps (nbf_bwd1 + nbf_bwd2) on the CBAM sites
+static bool nb_split_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BVAE_NB_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // BVAE_NB_FAST=0 selects the generic tiled backward kernels (kept as the reference implementation of the fast ones)
 static bool nb_fast_enabled() {
   static int v = -1;
@@ -2819,8 +2976,15 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     case 2: { constexpr int MD = 2; __VA_ARGS__; } break;       \
     default: { constexpr int MD = 3; __VA_ARGS__; } break;      \
   }
+  const bool split = fast && d->has_cbam && nb_split_enabled();     // ds-sums in the dq sweep, dsp-sums from uhat alone
   if (d->has_cbam) {
-    if (fast) {
+    if (split) {
+      NBF_MODES({
+        nbf_bwd1x_kernel<(MD == 0 ? 1 : MD)><<<gp, 256, C * sizeof(float), st>>>(
+            (const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out, d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc,
+            d->gamma, d->beta, d->gs, d->slope, (bf16*)d->dres, d->dres_pitch, d->bwd_nc, d->bwd_px, ppc);
+      });
+    } else if (fast) {
       nbf_bwd1_kernel<<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
                                                           d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
                                                           d->beta, d->gs, d->slope, d->bwd_nc, d->bwd_px, ppc);
@@ -2836,7 +3000,10 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
     nb_bwd_sp_kernel<<<gs, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->bwd_px, d->dwsp);
     if ((rc = check_launch("nb_bwd_sp"))) return rc;
   }
-  if (fast) {
+  if (split) {
+    nbf_bwd2x_kernel<<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->uhat, HW, C, d->nc, d->gamma, d->beta, d->cidx,
+                                                         d->bwd_px, d->bwd_nc, ppc);
+  } else if (fast) {
     NBF_MODES({
       nbf_bwd2_kernel<MD><<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
                                                               d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
