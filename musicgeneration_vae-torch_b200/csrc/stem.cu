@@ -22,16 +22,54 @@ __global__ void __launch_bounds__(256) stem_fwd_kernel(const bvae_conv_desc d) {
   float bs[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) bs[i] = d.bias ? d.bias[sub * 8 + i] : 0.f;
-  const int64_t stride = (int64_t)gridDim.x * (blockDim.x / G);
-  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; p < P; p += stride) {
-    const int qx = (int)(p % d.QW);
-    const int qy = (int)((p / d.QW) % d.QH);
-    const int n = (int)(p / ((int64_t)d.QW * d.QH));
+  // A CTA pass covers 256/G pixel slots laid out as whole output rows of the padded width RW (a power of two >= QW):
+  // slot -> (row, qx) by shift / mask and ONE 32-bit division per pass, instead of three 64-bit div/mod per pixel
+  // (the first version was bound by that integer arithmetic).  Consecutive CTAs keep working on consecutive rows:
+  // unrolling a CTA over several distant rows was 2x SLOWER (it scatters the write stream over DRAM pages).
+  const int slots = blockDim.x / G;
+  int RW = 1;
+  while (RW < d.QW && RW < slots) RW <<= 1;
+  if (RW < d.QW) {                                   // rows wider than a pass: generic per-pixel indexing
+    const int64_t stride = (int64_t)gridDim.x * slots;
+    for (int64_t p = (int64_t)blockIdx.x * slots + threadIdx.x / G; p < P; p += stride) {
+      const int qx = (int)(p % d.QW);
+      const int qy = (int)((p / d.QW) % d.QH);
+      const int n = (int)(p / ((int64_t)d.QW * d.QH));
+      float xv[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int iy = qy * d.sy + d.dy[t], ix = qx * d.sx + d.dx[t];
+        xv[t] = (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) ? bf2f(x[(((int64_t)n * d.H + iy) * d.W + ix) * d.x_pitch]) : 0.f;
+      }
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = bs[i];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) v += wr[i][t] * xv[t];
+        o[i] = d.act ? act_fwd(v, d.slope) : v;
+      }
+      const int64_t opix = ((int64_t)n * d.OH + (qy * d.osy + d.ooy)) * d.OW + (qx * d.osx + d.oox);
+      stg8(y + opix * d.y_pitch + sub * 8, pack8(o));
+    }
+    return;
+  }
+  const int rpp = slots / RW;                        // rows per pass
+  const int slot = threadIdx.x / G;
+  const int qx = slot & (RW - 1), rl = slot / RW;
+  const int rows = d.N * d.QH;
+  int dyt[NT], dxt[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) { dyt[t] = d.dy[t]; dxt[t] = qx * d.sx + d.dx[t]; }
+  if (qx >= d.QW) return;
+  for (int row = blockIdx.x * rpp + rl; row < rows; row += gridDim.x * rpp) {
+    const int n = row / d.QH, qy = row - n * d.QH;
+    const bf16* xn = x + (int64_t)n * d.H * d.W * d.x_pitch;
     float xv[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      const int iy = qy * d.sy + d.dy[t], ix = qx * d.sx + d.dx[t];
-      xv[t] = (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) ? bf2f(x[(((int64_t)n * d.H + iy) * d.W + ix) * d.x_pitch]) : 0.f;
+      const int iy = qy * d.sy + dyt[t], ix = dxt[t];
+      xv[t] = (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) ? bf2f(xn[(iy * d.W + ix) * d.x_pitch]) : 0.f;
     }
     float o[8];
 #pragma unroll
@@ -63,22 +101,53 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const bvae_wgrad_desc d
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int t = 0; t < NT; ++t) acc[i][t] = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * (blockDim.x / G);
-  for (int64_t p = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; p < P; p += stride) {
-    const int ax = (int)(p % d.AW);
-    const int ay = (int)((p / d.AW) % d.AH);
-    const int n = (int)(p / ((int64_t)d.AW * d.AH));
-    float av[8], xv[NT];
-    unpack8(ldg8(a + p * d.a_pitch + sub * 8), av);
+  const int slots = blockDim.x / G;
+  int RW = 1;
+  while (RW < d.AW && RW < slots) RW <<= 1;
+  if (RW < d.AW) {                                   // rows wider than a pass: generic per-pixel indexing
+    const int64_t stride = (int64_t)gridDim.x * slots;
+    for (int64_t p = (int64_t)blockIdx.x * slots + threadIdx.x / G; p < P; p += stride) {
+      const int ax = (int)(p % d.AW);
+      const int ay = (int)((p / d.AW) % d.AH);
+      const int n = (int)(p / ((int64_t)d.AW * d.AH));
+      float av[8], xv[NT];
+      unpack8(ldg8(a + p * d.a_pitch + sub * 8), av);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
-      const int yy = ay * d.sy + d.dy[t], xx = ax * d.sx + d.dx[t];
-      xv[t] = (yy >= 0 && yy < d.SH && xx >= 0 && xx < d.SW) ? bf2f(s[(((int64_t)n * d.SH + yy) * d.SW + xx) * d.s_pitch]) : 0.f;
+      for (int t = 0; t < NT; ++t) {
+        const int yy = ay * d.sy + d.dy[t], xx = ax * d.sx + d.dx[t];
+        xv[t] = (yy >= 0 && yy < d.SH && xx >= 0 && xx < d.SW) ? bf2f(s[(((int64_t)n * d.SH + yy) * d.SW + xx) * d.s_pitch]) : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) acc[i][t] += av[i] * xv[t];
     }
+  } else {
+    // whole anchor rows of the padded width RW per pass (see stem_fwd_kernel): no per-pixel divisions
+    const int rpp = slots / RW;
+    const int slot = threadIdx.x / G;
+    const int ax = slot & (RW - 1), rl = slot / RW;
+    const int rows = d.N * d.AH;
+    int dyt[NT], dxt[NT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int t = 0; t < NT; ++t) { dyt[t] = d.dy[t]; dxt[t] = ax * d.sx + d.dx[t]; }
+    if (ax < d.AW) {
+      for (int row = blockIdx.x * rpp + rl; row < rows; row += gridDim.x * rpp) {
+        const int n = row / d.AH, ay = row - n * d.AH;
+        const bf16* sn = s + (int64_t)n * d.SH * d.SW * d.s_pitch;
+        float av[8], xv[NT];
+        unpack8(ldg8(a + ((int64_t)row * d.AW + ax) * d.a_pitch + sub * 8), av);
 #pragma unroll
-      for (int t = 0; t < NT; ++t) acc[i][t] += av[i] * xv[t];
+        for (int t = 0; t < NT; ++t) {
+          const int yy = ay * d.sy + dyt[t], xx = dxt[t];
+          xv[t] = (yy >= 0 && yy < d.SH && xx >= 0 && xx < d.SW) ? bf2f(sn[(yy * d.SW + xx) * d.s_pitch]) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int t = 0; t < NT; ++t) acc[i][t] += av[i] * xv[t];
+      }
+    }
   }
   for (int o = G; o < 32; o <<= 1)
 #pragma unroll
