@@ -174,7 +174,15 @@ def decode_bench(args, pkg, Model, dev, rank, world):
                       "notes_on": float(roll.mean())}))
 
 
+def _quiet_nccl():
+    """NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set on some boxes): keep stdout to the one JSON
+    line the driver parses.  An explicit INFO / TRACE request is left alone."""
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def main():
+    _quiet_nccl()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
