@@ -2996,7 +2996,9 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
       });
     }
     if ((rc = check_launch("nb_bwd1"))) return rc;
-    dim3 gs(ceil_div(HW, 256 * 8), N);          // up to 8 pixels per thread, one block reduction of dwsp
+    // one block reduction of dwsp per CTA, then 18 same-address global atomics: with several CTAs per sample those
+    // atomics (1536 per address at 512 bars) serialised at L2 and were most of this kernel's time
+    dim3 gs(N >= 296 ? 1 : ceil_div(HW, 256 * 8), N);
     nb_bwd_sp_kernel<<<gs, 256, 0, st>>>(d->H, d->W, d->wsp, d->sa, d->bwd_px, d->dwsp);
     if ((rc = check_launch("nb_bwd_sp"))) return rc;
   }
