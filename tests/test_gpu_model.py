@@ -201,3 +201,43 @@ def test_fused_statistics_path_matches(oracle):
     e = rel_fro(z1, z0)
     report(test="fused_stats", z_rel=e)
     assert e < 1e-2, e
+
+
+def test_trainer_stream_and_segment_paths_agree(oracle, monkeypatch):
+    """GeneratorTrainer.step with the branch / weight-gradient streams (the default) must give the same parameters as
+    the fully serial path: the overlap only reorders independent launches.  The fp32 atomics make the weight gradients
+    differ in summation order from run to run and Adam's normalisation turns that into update-sized differences on
+    near-zero gradients, so the comparison is against the run-to-run floor of the SERIAL path (two serial runs), in
+    units of the mean parameter update; `step_from_host` must match as well."""
+    O = oracle
+    Model = pkg("graph.model").Model
+    Trainer = pkg("trainer").GeneratorTrainer
+    sd = O.make_state_dict(O.generator_spec(), 21, "lively")
+    batch = tuple(t.cuda() for t in O.make_inputs(4, 9))
+    hbatch = tuple(t.cpu().pin_memory() for t in batch)
+    masks = tuple(m.cuda() for m in O.draw_dropout_masks(4, 5))
+
+    def run(env, from_host=False):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        model = _load(Model(), sd).train()
+        tr = Trainer(model, lr=0.002)
+        start = tr.flat.data.clone()
+        for _ in range(2):
+            loss = tr.step_from_host(*hbatch, masks) if from_host else tr.step(*batch, masks)
+        torch.cuda.synchronize()
+        return tr.flat.data.clone(), start, float(loss)
+
+    off = {"BVAE_STREAMS": "0", "BVAE_WGRAD_STREAM": "0"}
+    on = {"BVAE_STREAMS": "1", "BVAE_WGRAD_STREAM": "1"}
+    serial, start, l0 = run(off)
+    serial2, _, _ = run(off)
+    overlap, _, l1 = run(on)
+    host, _, l2 = run(on, from_host=True)
+    upd = (serial - start).abs().mean().item()
+    floor = (serial2 - serial).abs().mean().item() / upd          # run-to-run: fp32 atomics order x Adam's normalisation
+    e1 = (overlap - serial).abs().mean().item() / upd
+    e2 = (host - serial).abs().mean().item() / upd
+    report(test="trainer_paths", floor=floor, overlap_vs_serial=e1, host_vs_serial=e2, losses=[l0, l1, l2])
+    assert e1 < 2 * floor + 0.05 and e2 < 2 * floor + 0.05, (floor, e1, e2)
+    assert abs(l1 - l0) < 2e-2 * abs(l0) and abs(l2 - l0) < 2e-2 * abs(l0), (l0, l1, l2)
