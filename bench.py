@@ -104,7 +104,7 @@ def synthetic_batch(B, seed, device, pin=False):
     return tuple(t.pin_memory() for t in ts) if pin else ts
 
 
-def cpu_reference_arm(batch, steps, warmup):
+def cpu_reference_arm(batch, steps, warmup, target_s=0.0):
     """The reference algorithm (CPU oracle port of graph/*.py + bar_loss.py + torch.optim.Adam semantics) on all host
     cores; returns bars/s.  Bounded sample: `batch` bars per step."""
     import torch
@@ -118,13 +118,17 @@ def cpu_reference_arm(batch, steps, warmup):
     m = OrderedDict((k, torch.zeros_like(v)) for k, v in sd.items())
     v = OrderedDict((k, torch.zeros_like(t)) for k, t in sd.items())
     times = []
-    for i in range(warmup + steps):
+    i = 0
+    while i < warmup + steps:
         t0 = time.perf_counter()
         O.train_step(sd, b, m, v, i + 1, 0.002, None, True)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
+            if target_s and len(times) == 1:        # size the bounded sample to ~target_s seconds of CPU work
+                steps = max(steps, min(40, int(target_s / max(times[0], 1e-3) + 0.999)))
+        i += 1
     dt = sum(times) / len(times)
-    return batch / dt, dt, cores, torch.get_num_threads()
+    return batch / dt, dt, cores, torch.get_num_threads(), len(times)
 
 
 def decode_bench(args, pkg, Model, dev, rank, world):
@@ -209,7 +213,7 @@ def main():
             return
         steps = max(1, min(args.steps, 5))
         warm = max(1, min(args.warmup, 1))
-        bars_s, dt, cores, threads = cpu_reference_arm(args.cpu_batch, steps, warm)
+        bars_s, dt, cores, threads, _ = cpu_reference_arm(args.cpu_batch, steps, warm)
         line = {"impl": "reference", "metric": "train_bars_per_sec", "value": bars_s, "unit": "bars/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -353,9 +357,9 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        bars_s, dt, cores, threads = cpu_reference_arm(args.cpu_batch, 3, 1)
+        bars_s, dt, cores, threads, nst = cpu_reference_arm(args.cpu_batch, 3, 1, target_s=12.0)
         cpu = {"value": bars_s, "unit": "bars/s", "cores": threads, "kind": "port",
-               "sample": "3 steps of %d bars (fwd+bwd+Adam) of the oracle port, %.1f s/step" % (args.cpu_batch, dt)}
+               "sample": "%d steps of %d bars (fwd+bwd+Adam) of the oracle port, %.1f s/step" % (nst, args.cpu_batch, dt)}
     line = {"metric": "train_bars_per_sec", "value": value, "unit": "bars/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
