@@ -1035,21 +1035,60 @@ __global__ void __launch_bounds__(128) wgrad_halo_kernel(const __grid_constant__
 
 // packed scratch [ra][tap][rs] -> parameter layout [ra][rs][tap] (accumulating), and re-zero the scratch.
 // One CTA per (ra, RC shifted channels): float4 reads of T x RC floats, coalesced read-modify-write of RC*T floats.
+// UNPACK_RA anchor rows per CTA (a CTA per row was 1152 floats of work: launch / tail bound, 4x off the HBM time).
+constexpr int UNPACK_RA = 4;
 template <int RC>
-__global__ void __launch_bounds__(256) wgrad_unpack_kernel(float* __restrict__ scratch, float* __restrict__ dw, int Cs, int T) {
-  __shared__ float s[BVAE_MAX_TAPS][RC + 1];
-  const int ra = blockIdx.y, rs0 = blockIdx.x * RC;
-  float* src = scratch + ((int64_t)ra * T) * Cs + rs0;
-  for (int e = threadIdx.x; e < T * (RC / 4); e += blockDim.x) {
-    const int t = e / (RC / 4), r = (e % (RC / 4)) * 4;
-    float4* q = reinterpret_cast<float4*>(src + (int64_t)t * Cs + r);
-    const float4 v = *q;
-    *q = make_float4(0.f, 0.f, 0.f, 0.f);
-    s[t][r] = v.x; s[t][r + 1] = v.y; s[t][r + 2] = v.z; s[t][r + 3] = v.w;
+__global__ void __launch_bounds__(256) wgrad_unpack_kernel(float* __restrict__ scratch, float* __restrict__ dw, int Ca, int Cs, int T) {
+  __shared__ float s[UNPACK_RA][BVAE_MAX_TAPS][RC + 1];
+  const int ra0 = blockIdx.y * UNPACK_RA, rs0 = blockIdx.x * RC;
+  const int nra = min(UNPACK_RA, Ca - ra0);
+  const int per = T * (RC / 4);
+  for (int e0 = threadIdx.x; e0 < nra * per; e0 += 3 * 256) {
+    float4* q[3];
+    float4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = e0 + u * 256;
+      q[u] = nullptr;
+      if (e < nra * per) {
+        const int a = e / per, e2 = e - a * per;
+        const int t = e2 / (RC / 4), r = (e2 % (RC / 4)) * 4;
+        q[u] = reinterpret_cast<float4*>(scratch + ((int64_t)(ra0 + a) * T + t) * Cs + rs0 + r);
+        v[u] = *q[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int e = e0 + u * 256;
+      if (!q[u]) continue;
+      const int a = e / per, e2 = e - a * per;
+      const int t = e2 / (RC / 4), r = (e2 % (RC / 4)) * 4;
+      *q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s[a][t][r] = v[u].x; s[a][t][r + 1] = v[u].y; s[a][t][r + 2] = v[u].z; s[a][t][r + 3] = v[u].w;
+    }
   }
   __syncthreads();
-  float* dst = dw + ((int64_t)ra * Cs + rs0) * T;
-  for (int e = threadIdx.x; e < T * RC; e += blockDim.x) dst[e] += s[e % T][e / T];
+  const int row = T * RC;
+  const int total = nra * row;
+  // read-modify-write in batches of 6 independent loads per thread (the plain loop exposed one DRAM latency per element)
+  for (int e0 = threadIdx.x; e0 < total; e0 += 6 * 256) {
+    float* ptr[6];
+    float old[6], add[6];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) {
+      const int e = e0 + u * 256;
+      ptr[u] = nullptr;
+      if (e < total) {
+        const int a = e / row, e2 = e - a * row;
+        ptr[u] = dw + ((int64_t)(ra0 + a) * Cs + rs0) * T + e2;
+        add[u] = s[a][e2 % T][e2 / T];
+        old[u] = *ptr[u];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 6; ++u)
+      if (ptr[u]) *ptr[u] = old[u] + add[u];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1460,11 +1499,11 @@ static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_til
 
 static int wgrad_unpack(const bvae_wgrad_desc* d, cudaStream_t stream) {
   if (d->Cs % 128 == 0) {
-    dim3 ug(d->Cs / 128, d->Ca);
-    wgrad_unpack_kernel<128><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+    dim3 ug(d->Cs / 128, ceil_div(d->Ca, UNPACK_RA));
+    wgrad_unpack_kernel<128><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Ca, d->Cs, d->T);
   } else {
-    dim3 ug(d->Cs / 32, d->Ca);
-    wgrad_unpack_kernel<32><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Cs, d->T);
+    dim3 ug(d->Cs / 32, ceil_div(d->Ca, UNPACK_RA));
+    wgrad_unpack_kernel<32><<<ug, 256, 0, stream>>>(d->scratch, d->dw, d->Ca, d->Cs, d->T);
   }
   return check_launch("wgrad_unpack");
 }
