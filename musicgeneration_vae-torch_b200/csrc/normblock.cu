@@ -132,6 +132,33 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
 __device__ __forceinline__ void mlp_hidden(const float* __restrict__ w1, int C, int Cr, const float* s_a, const float* s_m,
                                            float* s_pa, float* s_pm) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (C >= 128 && Cr >= 2 * nw) {
+    // two hidden units per trip: their row loads are all in flight together (a warp owns Cr / nw units in sequence and
+    // each used to cost one L2 round trip)
+    for (int j = warp; j < Cr; j += 2 * nw) {
+      const int j2 = j + nw;
+      const float* row = w1 + (int64_t)j * C;
+      const float* row2 = w1 + (int64_t)(j2 < Cr ? j2 : j) * C;
+      float pa = 0.f, pm = 0.f, qa = 0.f, qm = 0.f;
+#pragma unroll 8
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + c));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(row2 + c));
+        const float4 a = make_float4(s_a[c], s_a[c + 1], s_a[c + 2], s_a[c + 3]);       // (callers' arrays are only 4-byte aligned)
+        const float4 m = make_float4(s_m[c], s_m[c + 1], s_m[c + 2], s_m[c + 3]);
+        pa += w.x * a.x + w.y * a.y + w.z * a.z + w.w * a.w;
+        pm += w.x * m.x + w.y * m.y + w.z * m.z + w.w * m.w;
+        qa += u.x * a.x + u.y * a.y + u.z * a.z + u.w * a.w;
+        qm += u.x * m.x + u.y * m.y + u.z * m.z + u.w * m.w;
+      }
+      pa = warp_sum(pa); pm = warp_sum(pm); qa = warp_sum(qa); qm = warp_sum(qm);
+      if (lane == 0) {
+        s_pa[j] = pa; s_pm[j] = pm;
+        if (j2 < Cr) { s_pa[j2] = qa; s_pm[j2] = qm; }
+      }
+    }
+    return;
+  }
   for (int j = warp; j < Cr; j += nw) {
     const float* row = w1 + (int64_t)j * C;
     float pa = 0.f, pm = 0.f;
@@ -151,6 +178,26 @@ __device__ __forceinline__ void mlp_hidden(const float* __restrict__ w1, int C, 
 }
 // v[c] = sum_j W2[c][j] * h[j]: one thread per row (Cr <= 64 floats = at most two full cache lines, all loads independent)
 __device__ __forceinline__ void mlp_rows_dot(const float* __restrict__ w2, int C, int Cr, const float* s_h, float* s_out) {
+  if (Cr >= 16 && C >= 2 * (int)blockDim.x) {
+    // two rows per trip (2 x Cr/4 independent 16-byte loads in flight)
+    for (int c = threadIdx.x; c < C; c += 2 * blockDim.x) {
+      const int c2 = c + blockDim.x;
+      const float* row = w2 + (int64_t)c * Cr;
+      const float* row2 = w2 + (int64_t)(c2 < C ? c2 : c) * Cr;
+      float v = 0.f, v2 = 0.f;
+#pragma unroll 16
+      for (int j = 0; j < Cr; j += 4) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(row + j));
+        const float4 u = __ldg(reinterpret_cast<const float4*>(row2 + j));
+        const float4 h = make_float4(s_h[j], s_h[j + 1], s_h[j + 2], s_h[j + 3]);
+        v += w.x * h.x + w.y * h.y + w.z * h.z + w.w * h.w;
+        v2 += u.x * h.x + u.y * h.y + u.z * h.z + u.w * h.w;
+      }
+      s_out[c] = v;
+      if (c2 < C) s_out[c2] = v2;
+    }
+    return;
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float* row = w2 + (int64_t)c * Cr;
     float v = 0.f;
