@@ -234,6 +234,21 @@ int bvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
 /* fp32 -> bf16 cast of a contiguous buffer (piano-roll inputs: [N,1,H,W] with C == 1 is already NHWC) */
 int bvae_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Bit-packed piano-rolls.  The reference moves every batch to the device as fp32
+ * (data/bar_dataset.py:22-25 -> agent/barGen.py:134-141 -> .cuda() at :302-306) and reads every generated bar back
+ * as fp32 (maker_bar.py:38-40).  Cells are binary, so one bit per cell is lossless: MSB first within a byte, cells
+ * in C order -- the layout of numpy.packbits(x.reshape(-1)).
+ *   bvae_unpack_bits: out_bf16[i] (encoder / phrase-encoder input, nullable) and out_f32[i] for i < nbits_f32 (the
+ *     BCE target, nullable) = bit i of `bits`, as 0.0 / 1.0.  nbits_f32 is a multiple of 8 or equals nbits.
+ *   bvae_threshold_pack: bit i of `bits` (nullable) = p[i] > threshold, and out_f32[i] (nullable) the same as
+ *     0.0 / 1.0 -- torch.gt(pre_bar, 0.3).type(FloatTensor) of maker_bar.py:39 fused with the packing of the result.
+ * Outputs 16-byte aligned; `bits` holds ceil(n / 8) bytes, unused low bits of the last byte are written as 0.
+ * ------------------------------------------------------------------------------------------------------------ */
+int bvae_unpack_bits(const void* bits, int64_t nbits, void* out_bf16, float* out_f32, int64_t nbits_f32,
+                     void* stream);
+int bvae_threshold_pack(const float* p, int64_t n, float threshold, void* bits, float* out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,7 @@ from torch.utils.data import DataLoader
 
 from .. import parallel
 from ..data.bar_dataset import NoteDataset, SyntheticBars
+from ..data.packed import PackedBatch
 from ..graph.model import Model
 from ..maker_bar import sample_songs
 from ..metrics import AverageMeter
@@ -109,6 +110,9 @@ class BarGen(object):
 
     def make_batch(self, samples):
         cat = lambda k: np.concatenate([s[k] for s in samples], axis=0)
+        if getattr(self.config, "packed_input", False):
+            # bit-packed batch (data/packed.py): 4320 B per sample across PCIe instead of 138 KB, expanded on the device
+            return PackedBatch.from_arrays(cat("note"), cat("pre_note"), cat("pre_phrase"), cat("position"))
         return (torch.tensor(cat("note"), dtype=torch.float), torch.tensor(cat("pre_note"), dtype=torch.float),
                 torch.tensor(cat("pre_phrase"), dtype=torch.float), torch.tensor(cat("position"), dtype=torch.long))
 
@@ -127,8 +131,10 @@ class BarGen(object):
         sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["generator_state_dict"].items()}
         sd = {k: v for k, v in sd.items() if not k.startswith("refiner.")}       # the reference's Refiner is not built
         self.generator.load_state_dict(sd, strict=False)
-        if isinstance(ck.get("gen_optimizer1"), dict) and "exp_avg" in ck["gen_optimizer1"]:
-            self.opt_gen1.load_state_dict(ck["gen_optimizer1"])
+        opt = ck.get("gen_optimizer1")
+        if isinstance(opt, dict) and ("exp_avg" in opt or "param_groups" in opt):   # ours, or torch.optim.Adam's (reference)
+            self.opt_gen1.load_state_dict(opt)
+            self.lr_gen1 = self.opt_gen1.lr
         self.epoch = ck.get("epoch", 0)
 
     def save_checkpoint(self, file_name, epoch):
@@ -161,11 +167,14 @@ class BarGen(object):
         self.opt_gen1.is_pretraining = self.epoch <= self.pretraining_step_size
         avg_gen_loss = AverageMeter()
         dev_sum, n = torch.zeros((), device=self.device), 0
-        for note, pre_note, pre_phrase, position in self.dataloader:
-            note, pre_note, pre_phrase, position = (t.to(self.device, non_blocking=self.config.async_loading)
-                                                    for t in (note, pre_note, pre_phrase, position))
+        for batch in self.dataloader:
             self.iteration += 1
-            dev_sum += self.opt_gen1.step(note, pre_note, pre_phrase, position)     # stays on the device
+            if isinstance(batch, PackedBatch):
+                dev_sum += self.opt_gen1.step_from_packed(batch)
+            else:
+                note, pre_note, pre_phrase, position = (t.to(self.device, non_blocking=self.config.async_loading)
+                                                        for t in batch)
+                dev_sum += self.opt_gen1.step(note, pre_note, pre_phrase, position)     # stays on the device
             n += 1
         if n:
             avg_gen_loss.update(float(dev_sum) / n, n)                                  # one D2H read per epoch

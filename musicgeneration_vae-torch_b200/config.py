@@ -25,3 +25,4 @@ class Config(object):
     # --- additions ---
     bucket_mb = 64         # NCCL gradient bucket size
     vae_head = False
+    packed_input = False   # loader emits bit-packed batches (data/packed.py): 32x less host->device traffic

@@ -1,0 +1,136 @@
+"""Bit-packed piano-roll batches.
+
+The reference keeps every bar as fp32 on disk, in the loader and across PCIe (data/bar_dataset.py:22-25,
+agent/barGen.py:134-141,302-306): 138 KB per training sample.  Cells are binary, so this module stores one bit per
+cell -- ``numpy.packbits`` order: cells in C order, MSB first -- which is 4320 bytes per sample (32x less) and
+lossless.  ``PackedBatch`` is one contiguous (pinned) uint8 buffer
+
+    [ note: B*720 B | pre_note: B*720 B | pre_phrase: B*2880 B ]        + position [B] int64
+
+that crosses PCIe in ONE copy and is expanded on the device by ``bvae_unpack_bits`` (csrc/bits.cu) straight into the
+bf16 tensors the encoder stems read (note and pre_note land contiguously = the 2B-bar encoder batch) plus the fp32
+copy of ``note`` the BCE loss uses as its target.  The generated bars of the sampling loop take the reverse route
+(``threshold_pack``: torch.gt(bar, 0.3) of maker_bar.py:39 and the packing in one kernel; 720 B per bar D2H).
+
+Host-side packing is loader work (numpy); everything on the device goes through libbarvae.so -- no fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _lib
+
+BAR_CELLS = 96 * 60            # config.py: one bar = 96 time steps x 60 pitches
+PHRASE_CELLS = 384 * 60        # 4 bars
+BAR_BYTES = BAR_CELLS // 8     # 720
+PHRASE_BYTES = PHRASE_CELLS // 8
+
+
+def pack_cells(x) -> np.ndarray:
+    """{0,1}-valued array (any shape / dtype, numpy or CPU tensor) -> uint8 bits, numpy.packbits order.
+    Raises ValueError if a cell is neither 0 nor 1: the packing must stay lossless."""
+    a = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+    flat = np.ascontiguousarray(a).reshape(-1)
+    b = flat.astype(np.uint8)
+    if not np.array_equal(b, flat) or (b.size and b.max() > 1):
+        raise ValueError("pack_cells: piano-roll cells must be exactly 0 or 1")
+    return np.packbits(b)
+
+
+def unpack_cells_host(bits: np.ndarray, shape) -> np.ndarray:
+    """host inverse of pack_cells (used on the D2H side of the sampling loop and by loaders); float32 {0,1}"""
+    n = int(np.prod(shape))
+    return np.unpackbits(np.asarray(bits, dtype=np.uint8), count=n).astype(np.float32).reshape(shape)
+
+
+class PackedBatch:
+    """One training batch as bits.  ``bits`` is a uint8 CPU tensor (pinned when ``pin``), ``position`` int64."""
+
+    def __init__(self, bits: torch.Tensor, position: torch.Tensor, batch: int):
+        if bits.dtype != torch.uint8 or bits.numel() != batch * (2 * BAR_BYTES + PHRASE_BYTES):
+            raise ValueError("PackedBatch: bits must be uint8 with %d bytes per bar" % (2 * BAR_BYTES + PHRASE_BYTES))
+        self.bits, self.position, self.batch = bits, position, batch
+
+    @classmethod
+    def from_arrays(cls, note, pre_note, pre_phrase, position, pin: bool = False) -> "PackedBatch":
+        B = int(np.asarray(position).shape[0]) if not isinstance(position, torch.Tensor) else position.shape[0]
+        for name, t, cells in (("note", note, BAR_CELLS), ("pre_note", pre_note, BAR_CELLS),
+                               ("pre_phrase", pre_phrase, PHRASE_CELLS)):
+            n = t.numel() if isinstance(t, torch.Tensor) else np.asarray(t).size
+            if n != B * cells:
+                raise ValueError("PackedBatch: %s has %d cells, expected %d x %d" % (name, n, B, cells))
+        bits = torch.from_numpy(np.concatenate([pack_cells(note), pack_cells(pre_note), pack_cells(pre_phrase)]))
+        pos = position if isinstance(position, torch.Tensor) else torch.from_numpy(np.asarray(position))
+        pos = pos.to(torch.long)
+        if pin:
+            bits, pos = bits.pin_memory(), pos.pin_memory()
+        return cls(bits, pos, B)
+
+    def pin_memory(self) -> "PackedBatch":
+        """DataLoader(pin_memory=True) calls this on the collated batch"""
+        return PackedBatch(self.bits.pin_memory(), self.position.pin_memory(), self.batch)
+
+    @property
+    def nbytes(self) -> int:
+        return self.bits.numel() + self.position.numel() * self.position.element_size()
+
+    def to_host_arrays(self):
+        """(note, pre_note, pre_phrase, position) as float32 numpy arrays in the reference's shapes"""
+        B, b = self.batch, self.bits.numpy()
+        o1, o2 = B * BAR_BYTES, 2 * B * BAR_BYTES
+        return (unpack_cells_host(b[:o1], (B, 1, 96, 60)), unpack_cells_host(b[o1:o2], (B, 1, 96, 60)),
+                unpack_cells_host(b[o2:], (B, 1, 384, 60)), self.position.numpy())
+
+    def to_device(self, device, phrase_stream=None):
+        """H2D copy of the bits + expansion on the device.  Returns ``(note_f32, bars_bf16, phrase_bf16, position,
+        dbits)``: note_f32 [B,1,96,60] fp32 (BCE target), bars_bf16 [2B,1,96,60] bf16 (= cat(note, pre_note): the
+        encoder batch), phrase_bf16 [B,1,384,60] bf16.  With ``phrase_stream`` the phrase bits are expanded on that
+        stream (the one the phrase encoder runs on) after it has waited for the copy; the caller must then keep
+        ``dbits`` referenced until the main stream has joined ``phrase_stream`` again (the trainer holds it through the
+        step) -- cheaper for the caching allocator than record_stream."""
+        B = self.batch
+        main = torch.cuda.current_stream(device)
+        dbits = self.bits.to(device, non_blocking=True)
+        pos = self.position.to(device, non_blocking=True)
+        bars = torch.empty(2 * B, 1, 96, 60, device=device, dtype=torch.bfloat16)
+        note = torch.empty(B, 1, 96, 60, device=device, dtype=torch.float32)
+        phrase = torch.empty(B, 1, 384, 60, device=device, dtype=torch.bfloat16)
+        nbar_bits = 2 * B * BAR_CELLS
+        unpack_bits(dbits[:2 * B * BAR_BYTES], nbar_bits, bars, note, B * BAR_CELLS)
+        if phrase_stream is None:
+            unpack_bits(dbits[2 * B * BAR_BYTES:], B * PHRASE_CELLS, phrase, None, 0)
+        else:
+            phrase_stream.wait_stream(main)
+            with torch.cuda.stream(phrase_stream):
+                unpack_bits(dbits[2 * B * BAR_BYTES:], B * PHRASE_CELLS, phrase, None, 0)
+        return note, bars, phrase, pos, dbits
+
+
+def unpack_bits(bits: torch.Tensor, nbits: int, out_bf16, out_f32, nbits_f32: int):
+    """bvae_unpack_bits on the current stream (device tensors; outputs may be None)"""
+    if not bits.is_cuda:
+        raise RuntimeError("unpack_bits runs on the device (libbarvae.so); use unpack_cells_host for host arrays")
+    assert bits.dtype == torch.uint8 and bits.is_contiguous() and bits.numel() * 8 >= nbits
+    assert out_bf16 is None or (out_bf16.dtype == torch.bfloat16 and out_bf16.is_contiguous()
+                                and out_bf16.numel() >= nbits)
+    assert out_f32 is None or (out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+                               and out_f32.numel() >= nbits_f32)
+    _lib.check(_lib.lib().bvae_unpack_bits(bits.data_ptr(), nbits, None if out_bf16 is None else out_bf16.data_ptr(),
+                                           None if out_f32 is None else out_f32.data_ptr(), nbits_f32,
+                                           _lib.stream_ptr()), "unpack_bits")
+
+
+def threshold_pack(probs: torch.Tensor, threshold: float, want_bits: bool = True, want_float: bool = False):
+    """bvae_threshold_pack: ``(bits uint8 [ceil(n/8)] | None, (probs > threshold).float() | None)``"""
+    if not probs.is_cuda:
+        raise RuntimeError("threshold_pack runs on the device (libbarvae.so); there is no CPU fallback")
+    p = probs.contiguous().float()
+    n = p.numel()
+    bits = torch.empty((n + 7) // 8, device=p.device, dtype=torch.uint8) if want_bits else None
+    out = torch.empty_like(p) if want_float else None
+    _lib.check(_lib.lib().bvae_threshold_pack(p.data_ptr(), n, float(threshold),
+                                              None if bits is None else bits.data_ptr(),
+                                              None if out is None else out.data_ptr(), _lib.stream_ptr()),
+               "threshold_pack")
+    return bits, out

@@ -81,6 +81,18 @@ def kl_divergence(mu, logvar):
     return _KLFn.apply(mu, logvar)
 
 
+def _cat_bars(note, pre_note):
+    """torch.cat((note, pre_note), 0) -- as a VIEW when the two already sit back to back in one buffer (the bit-packed
+    input path expands both into one [2B,1,96,60] tensor, data/packed.py)."""
+    if (note.dtype == pre_note.dtype and note.shape == pre_note.shape and note.is_contiguous()
+            and pre_note.is_contiguous() and not note.requires_grad and not pre_note.requires_grad
+            and note.untyped_storage().data_ptr() == pre_note.untyped_storage().data_ptr()
+            and pre_note.storage_offset() == note.storage_offset() + note.numel()):
+        shape = (2 * note.shape[0],) + tuple(note.shape[1:])
+        return note.as_strided(shape, torch.empty(shape, device="meta").stride(), note.storage_offset())
+    return torch.cat((note, pre_note), 0)
+
+
 class Model(nn.Module):
     def __init__(self, vae_head: bool = False):
         super().__init__()
@@ -142,7 +154,7 @@ class Model(nn.Module):
             phrase_feature = self._phrase_branch(phrase)
             # encoder(note) and encoder(pre_note) share weights and have no batch-coupled op (InstanceNorm is
             # per sample): one pass over 2B bars (model.py:26-27)
-            zz = self.encoder(torch.cat((note, pre_note), 0))
+            zz = self.encoder(_cat_bars(note, pre_note))
             z, pre_z = zz[:B], zz[B:]
             if self.vae_head:
                 mu, pre_mu = z, pre_z

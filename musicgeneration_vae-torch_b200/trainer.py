@@ -19,11 +19,12 @@ class GeneratorTrainer:
         self.is_pretraining = is_pretraining
         self.step_count = 0
 
-    def step(self, note, pre_note, pre_phrase, position, dropout_masks=None):
-        """One optimisation step; returns the (device) loss tensor without synchronising."""
+    def step(self, note, pre_note, pre_phrase, position, dropout_masks=None, target=None):
+        """One optimisation step; returns the (device) loss tensor without synchronising.  ``target`` (default: ``note``)
+        is the fp32 BCE target when ``note`` itself arrives as bf16 (bit-packed input path)."""
         self.flat.attach_grads(zero=True)
         gen, z, pre_z, pf = self.model(note, pre_note, pre_phrase, position, True, dropout_masks)
-        loss = self.loss_fn(gen, note, self.is_pretraining)
+        loss = self.loss_fn(gen, note if target is None else target, self.is_pretraining)
         loss.backward()
         scale = self.reducer.finish() if self.reducer is not None else 1.0
         self.step_count += 1
@@ -46,13 +47,73 @@ class GeneratorTrainer:
                 phrase_d = pre_phrase.to(dev, non_blocking=True)
         return self.step(note_d, pre_d, phrase_d, pos_d, dropout_masks)
 
+    def step_from_packed(self, packed, dropout_masks=None):
+        """The same step from a bit-packed host batch (data/packed.py: 4320 B per sample instead of 138 KB): ONE H2D
+        copy of the bits, expanded on the device by bvae_unpack_bits into the bf16 encoder inputs (note and pre_note
+        contiguous, so Model.forward's torch.cat is a view) and the fp32 BCE target; the phrase bits are expanded on the
+        phrase encoder's stream."""
+        dev = self.flat.data.device
+        side = self.model.side_stream(dev) if hasattr(self.model, "side_stream") else None
+        note_f32, bars, phrase, pos, dbits = packed.to_device(dev, side)
+        B = packed.batch
+        loss = self.step(bars[:B], bars[B:], phrase, pos, dropout_masks, target=note_f32)
+        del dbits        # held until here: the main stream has joined the phrase stream inside the step
+        return loss
+
     # torch.optim-style state for checkpoints (agent/barGen.py:174-197)
     def state_dict(self):
         return {"step": self.step_count, "lr": self.lr,
                 "exp_avg": None if self.flat.exp_avg is None else self.flat.exp_avg.clone(),
                 "exp_avg_sq": None if self.flat.exp_avg_sq is None else self.flat.exp_avg_sq.clone()}
 
+    def torch_state_dict(self):
+        """The same state in ``torch.optim.Adam.state_dict()`` form -- what the reference stores under
+        ``gen_optimizer1`` (agent/barGen.py:60,176): ``state[i] = {step, exp_avg, exp_avg_sq}`` for the i-th entry of
+        ``generator.parameters()``, one param group.  Parameters that never received a gradient (the unused ``bn1``
+        affine pairs) carry zero moments here; torch would have no entry for them."""
+        flat, state = self.flat, {}
+        if flat.exp_avg is not None:
+            for i, (p, o) in enumerate(zip(flat.params, flat.offsets)):
+                n = p.numel()
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": flat.exp_avg[o:o + n].view(p.shape).clone(),
+                            "exp_avg_sq": flat.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "params": list(range(len(flat.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def _load_torch_state_dict(self, sd):
+        """``torch.optim.Adam.state_dict()`` of the reference's generator optimiser.  Entries are matched by position in
+        ``generator.parameters()`` and must agree in shape; trailing entries this model does not have (the reference's
+        Refiner, graph/model.py:18) are ignored.  The flat Adam keeps ONE step counter (bias correction), so per-parameter
+        counters collapse to their maximum -- they are all equal in the reference's loop except for parameters that
+        never get a gradient."""
+        flat = self.flat
+        group = sd["param_groups"][0]
+        self.lr = group.get("lr", self.lr)
+        self.betas = tuple(group.get("betas", self.betas))
+        self.eps = group.get("eps", self.eps)
+        ids = list(group["params"])
+        dev = flat.data.device
+        m, v, step = torch.zeros_like(flat.data), torch.zeros_like(flat.data), 0
+        for i, (p, o) in enumerate(zip(flat.params, flat.offsets)):
+            if i >= len(ids):
+                break
+            st = sd["state"].get(ids[i])
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("optimizer state %d has shape %s, parameter %d has %s" %
+                                 (ids[i], tuple(st["exp_avg"].shape), i, tuple(p.shape)))
+            n = p.numel()
+            m[o:o + n].copy_(st["exp_avg"].reshape(-1).to(dev))
+            v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1).to(dev))
+            step = max(step, int(st["step"]))
+        flat.exp_avg, flat.exp_avg_sq, self.step_count = m, v, step
+
     def load_state_dict(self, sd):
+        if "param_groups" in sd and "state" in sd:
+            return self._load_torch_state_dict(sd)
         self.step_count, self.lr = sd["step"], sd["lr"]
         if sd["exp_avg"] is not None:
             self.flat.exp_avg = sd["exp_avg"].to(self.flat.data.device).clone()
