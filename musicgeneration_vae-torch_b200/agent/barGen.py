@@ -23,7 +23,7 @@ from torch.utils.data import DataLoader
 
 from .. import parallel
 from ..data.bar_dataset import NoteDataset, SyntheticBars
-from ..data.packed import PackedBatch
+from ..data.packed import PackedBatch, PackedNoteDataset, collate_packed
 from ..graph.model import Model
 from ..maker_bar import sample_songs
 from ..metrics import AverageMeter
@@ -64,6 +64,9 @@ class BarGen(object):
         data_dir = os.path.join(config.root_path, config.data_path)
         if dataset is not None:
             self.dataset = dataset
+        elif getattr(config, "packed_data_path", None) and os.path.isdir(os.path.join(config.root_path,
+                                                                                      config.packed_data_path)):
+            self.dataset = PackedNoteDataset(config.root_path, config)
         elif os.path.isdir(data_dir):
             self.dataset = NoteDataset(config.root_path, config)
         else:
@@ -110,6 +113,8 @@ class BarGen(object):
 
     def make_batch(self, samples):
         cat = lambda k: np.concatenate([s[k] for s in samples], axis=0)
+        if "note_bits" in samples[0]:          # items already stored as bits (PackedNoteDataset): byte-level concat
+            return collate_packed(samples)
         if getattr(self.config, "packed_input", False):
             # bit-packed batch (data/packed.py): 4320 B per sample across PCIe instead of 138 KB, expanded on the device
             return PackedBatch.from_arrays(cat("note"), cat("pre_note"), cat("pre_phrase"), cat("position"))

@@ -107,6 +107,83 @@ class PackedBatch:
         return note, bars, phrase, pos, dbits
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# on-disk format: one .npz per item like the reference's (data/bar_dataset.py:22-25), cells stored as bits
+# ---------------------------------------------------------------------------------------------------------------
+PACKED_KEYS = ("note_bits", "pre_note_bits", "pre_phrase_bits", "position")
+
+
+def pack_item(item) -> dict:
+    """reference item ``{'note' [n,1,96,60], 'pre_note', 'pre_phrase' [n,1,384,60], 'position' [n]}`` -> packed item
+    ``{'note_bits' [n,720] u8, 'pre_note_bits' [n,720] u8, 'pre_phrase_bits' [n,2880] u8, 'position' [n] i64}``.
+    A bar is 5760 cells = 720 whole bytes, so rows stay per-bar and items concatenate along axis 0 like the
+    reference's collate (agent/barGen.py:134-141) without touching a bit."""
+    n = int(np.asarray(item["position"]).shape[0])
+    return {"note_bits": pack_cells(item["note"]).reshape(n, BAR_BYTES),
+            "pre_note_bits": pack_cells(item["pre_note"]).reshape(n, BAR_BYTES),
+            "pre_phrase_bits": pack_cells(item["pre_phrase"]).reshape(n, PHRASE_BYTES),
+            "position": np.asarray(item["position"]).astype(np.int64)}
+
+
+def unpack_item(packed) -> dict:
+    """inverse of pack_item (float32 arrays in the reference's shapes)"""
+    n = packed["position"].shape[0]
+    return {"note": unpack_cells_host(packed["note_bits"], (n, 1, 96, 60)),
+            "pre_note": unpack_cells_host(packed["pre_note_bits"], (n, 1, 96, 60)),
+            "pre_phrase": unpack_cells_host(packed["pre_phrase_bits"], (n, 1, 384, 60)),
+            "position": np.asarray(packed["position"])}
+
+
+def collate_packed(samples, pin: bool = False) -> PackedBatch:
+    """DataLoader collate_fn for packed items: three byte-level concatenations written straight into the batch buffer"""
+    B = sum(int(s["position"].shape[0]) for s in samples)
+    bits = torch.empty(B * (2 * BAR_BYTES + PHRASE_BYTES), dtype=torch.uint8, pin_memory=pin)
+    buf, off = bits.numpy(), 0
+    for key, width in (("note_bits", BAR_BYTES), ("pre_note_bits", BAR_BYTES), ("pre_phrase_bits", PHRASE_BYTES)):
+        for s in samples:
+            a = np.asarray(s[key], dtype=np.uint8).reshape(-1)
+            if a.size != int(s["position"].shape[0]) * width:
+                raise ValueError("collate_packed: %s has %d bytes, expected %d per bar" % (key, a.size, width))
+            buf[off:off + a.size] = a
+            off += a.size
+    pos = torch.from_numpy(np.concatenate([np.asarray(s["position"]).astype(np.int64) for s in samples]))
+    return PackedBatch(bits, pos.pin_memory() if pin else pos, B)
+
+
+class PackedNoteDataset(torch.utils.data.Dataset):
+    """Directory of packed .npz items (written by ``convert_dataset`` / tools/pack_dataset.py): same item granularity
+    and file names as the reference's NoteDataset (data/bar_dataset.py:9-25), 32x fewer bytes to read and collate."""
+
+    def __init__(self, root_dir, config):
+        import os
+        self.dir = os.path.join(root_dir, getattr(config, "packed_data_path", config.data_path))
+        self.file_list = sorted(f for f in os.listdir(self.dir) if f.endswith(".npz"))
+        self.num_iterations = (len(self.file_list) + config.batch_size - 1) // config.batch_size
+
+    def __len__(self):
+        return len(self.file_list)
+
+    def __getitem__(self, idx):
+        import os
+        with np.load(os.path.join(self.dir, self.file_list[idx])) as d:
+            return {k: d[k] for k in PACKED_KEYS}
+
+
+def convert_dataset(src_dir: str, dst_dir: str) -> int:
+    """reference-format directory of .npz items -> packed directory (same file names); returns the number of bars"""
+    import os
+    os.makedirs(dst_dir, exist_ok=True)
+    bars = 0
+    for name in sorted(os.listdir(src_dir)):
+        if not name.endswith(".npz"):
+            continue
+        with np.load(os.path.join(src_dir, name)) as d:
+            item = pack_item({k: d[k] for k in ("note", "pre_note", "pre_phrase", "position")})
+        np.savez(os.path.join(dst_dir, name), **item)
+        bars += int(item["position"].shape[0])
+    return bars
+
+
 def unpack_bits(bits: torch.Tensor, nbits: int, out_bf16, out_f32, nbits_f32: int):
     """bvae_unpack_bits on the current stream (device tensors; outputs may be None)"""
     if not bits.is_cuda:

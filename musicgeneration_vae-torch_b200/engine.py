@@ -564,12 +564,18 @@ class FlatParams:
         return self.grad[o:o + p.numel()].view(p.shape)
 
     def attach_grads(self, zero: bool = True):
-        """Point every .grad at its slice of the flat gradient bucket (one memset instead of 221)."""
+        """Point every .grad at its slice of the flat gradient bucket (one memset instead of 221).  The view objects
+        are built once and re-attached only where ``p.grad`` is no longer that object: creating 221 views every step
+        cost ~1 ms of host time in front of the step's first kernel -- GPU idle time in a loop that reads the loss back
+        every step (agent/barGen.py:335)."""
         if zero:
             self.grad.zero_()
-        for p in self.params:
-            if p.requires_grad:
-                p.grad = self.grad_view(p)
+        views = getattr(self, "_grad_views", None)
+        if views is None:
+            views = self._grad_views = [self.grad_view(p) for p in self.params]
+        for p, v in zip(self.params, views):
+            if p.requires_grad and p.grad is not v:
+                p.grad = v
 
     def intact(self) -> bool:
         p, o = self.params[0], self.offsets[0]

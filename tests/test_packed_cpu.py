@@ -117,3 +117,38 @@ def test_midi_roundtrip(tmp_path, density):
     sparse[39990:39995, 5] = 1
     M.write_midi(sparse, path)
     assert np.array_equal(M.midi_to_roll(path, 40000), sparse)
+
+
+def test_packed_dataset_on_disk_and_collate(tmp_path):
+    """reference-format .npz items -> convert_dataset -> PackedNoteDataset -> collate_packed == packing the
+    reference's own collate (np.concatenate along axis 0, agent/barGen.py:134-141); ragged items (different bar counts)"""
+    P = pkg("data.packed")
+    src, dst = tmp_path / "f32", tmp_path / "bits"
+    src.mkdir()
+    r = np.random.RandomState(5)
+    items = []
+    for i, n in enumerate((3, 1, 4)):
+        it = {"note": (r.rand(n, 1, 96, 60) < 0.05).astype(np.float32),
+              "pre_note": (r.rand(n, 1, 96, 60) < 0.05).astype(np.float32),
+              "pre_phrase": (r.rand(n, 1, 384, 60) < 0.05).astype(np.float32),
+              "position": r.randint(0, 332, size=(n,)).astype(np.int64)}
+        np.savez(src / ("%03d.npz" % i), **it)
+        items.append(it)
+    assert P.convert_dataset(str(src), str(dst)) == 8
+
+    class Cfg:
+        data_path, packed_data_path, batch_size = "f32", "bits", 2
+    ds = P.PackedNoteDataset(str(tmp_path), Cfg)
+    assert len(ds) == 3 and ds.num_iterations == 2
+    assert ds[0]["note_bits"].shape == (3, 720) and ds[2]["pre_phrase_bits"].shape == (4, 2880)
+    back = P.unpack_item(ds[1])
+    assert all(np.array_equal(back[k], items[1][k]) for k in items[1])
+    pb = P.collate_packed([ds[i] for i in range(3)])
+    cat = lambda k: np.concatenate([it[k] for it in items], axis=0)
+    want = P.PackedBatch.from_arrays(cat("note"), cat("pre_note"), cat("pre_phrase"), cat("position"))
+    assert pb.batch == 8 and torch.equal(pb.bits, want.bits) and torch.equal(pb.position, want.position)
+    assert np.array_equal(pb.bits.numpy(), BO.batch_layout(cat("note"), cat("pre_note"), cat("pre_phrase")))
+    bad = dict(ds[0])
+    bad["note_bits"] = bad["note_bits"][:, :-1]
+    with pytest.raises(ValueError):
+        P.collate_packed([bad])
