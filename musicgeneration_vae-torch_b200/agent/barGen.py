@@ -172,14 +172,10 @@ class BarGen(object):
         self.opt_gen1.is_pretraining = self.epoch <= self.pretraining_step_size
         avg_gen_loss = AverageMeter()
         dev_sum, n = torch.zeros((), device=self.device), 0
-        for batch in self.dataloader:
+        # fp32 4-tuples or PackedBatch from the loader; the next batch's H2D copy overlaps the current step
+        for batch in self.opt_gen1.prefetch(self.dataloader):
             self.iteration += 1
-            if isinstance(batch, PackedBatch):
-                dev_sum += self.opt_gen1.step_from_packed(batch)
-            else:
-                note, pre_note, pre_phrase, position = (t.to(self.device, non_blocking=self.config.async_loading)
-                                                        for t in batch)
-                dev_sum += self.opt_gen1.step(note, pre_note, pre_phrase, position)     # stays on the device
+            dev_sum += self.opt_gen1.step_batch(batch)                                  # stays on the device
             n += 1
         if n:
             avg_gen_loss.update(float(dev_sum) / n, n)                                  # one D2H read per epoch

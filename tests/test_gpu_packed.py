@@ -223,3 +223,48 @@ def test_adam_continues_from_reference_optimizer_state():
     worst = max(float((p - c).abs().max()) for p, c in zip(flat.params, clones))
     report(test="adam_from_torch_state", worst_abs=worst)
     assert tr.step_count == 2 and worst < 2e-6, worst
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_prefetcher_hands_out_the_right_batches_while_steps_run(packed):
+    """trainer.prefetch: 5 DISTINCT host batches (the last one smaller) through the two alternating device buffer sets
+    with a training step running on each -- every DeviceBatch must equal its host batch bit for bit when it is handed
+    out AND still after its step has been enqueued (the next copy must not overwrite a buffer that is in use), and the
+    losses must match the sequential step_from_host loop on the same batches"""
+    P = pkg("data.packed")
+    O = __import__("barvae_oracle")
+    Model = pkg("graph.model").Model
+    Trainer = pkg("trainer").GeneratorTrainer
+    sd = O.make_state_dict(O.generator_spec(), 21, "lively")
+    sizes = [3, 3, 3, 3, 2]
+    host = [O.make_inputs(b, 40 + i) for i, b in enumerate(sizes)]
+    masks = [tuple(m.cuda() for m in O.draw_dropout_masks(b, 5 + i)) for i, b in enumerate(sizes)]
+    feed = [P.PackedBatch.from_arrays(*hb, pin=True) if packed else tuple(t.pin_memory() for t in hb) for hb in host]
+
+    def fresh():
+        model = Model()
+        model.load_state_dict(sd)
+        return Trainer(model.cuda().train(), lr=0.002)
+
+    tr = fresh()
+    losses, snaps = [], []
+    for i, db in enumerate(tr.prefetch(feed)):
+        before = [t.clone() for t in db]
+        loss = tr.step_batch(db, masks[i])
+        snaps.append((before, [t.clone() for t in db], None if db.target is None else db.target.clone()))
+        losses.append(loss)
+    torch.cuda.synchronize()
+    assert len(snaps) == len(host)
+    for (before, after, target), hb in zip(snaps, host):
+        for b, a, h in zip(before, after, hb):
+            assert torch.equal(b.float().cpu(), h.float()) and torch.equal(a.float().cpu(), h.float())
+        if packed:
+            assert torch.equal(target.cpu(), hb[0]) and before[0].dtype == torch.bfloat16
+    tr2 = fresh()
+    want = [float(tr2.step_from_host(*(t.pin_memory() for t in hb), masks[i])) for i, hb in enumerate(host)]
+    got = [float(l) for l in losses]
+    report(test="prefetch_losses", packed=packed, got=got, want=want)
+    assert abs(got[0] - want[0]) < 1e-2 * abs(want[0]), (got, want)
+    assert all(abs(g - w) < 0.15 * abs(w) for g, w in zip(got, want)), (got, want)
+    # the trainer reuses one prefetcher (one copy stream, one pair of buffer sets) across epochs
+    assert tr.prefetch(feed) is tr.prefetch(feed)
