@@ -165,7 +165,7 @@ typedef struct bvae_nb_desc {
   int32_t stats_fused;  /* 1: `stats` was filled by bvae_conv_gemm's epilogue (see bvae_conv_desc.stats) */
   float slope, eps;
   const void* y;        /* raw conv output [N,H,W,C] (forward only; not needed by backward) */
-  void* uhat;           /* bf16 [N,H,W,C] dense: normalised activations, saved for backward */
+  void* uhat;           /* bf16 [N,H,W,C] dense: normalised activations, saved for backward; NULL in bvae_nb_forward = inference, not written */
   void* out;            /* bf16 block output */
   void* stats;          /* forward scratch, 24*N*C bytes */
   const void* res;      /* bf16 external residual (res_mode 2) */

@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(256) nb_pool_kernel(const void* __restrict__ y
           float uh[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) uh[i] = (v[i] - p_mean[i]) * p_rstd[i];
-          stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
+          if (uhat != nullptr) stg8(uhat + ubase + (int64_t)p * C + c, pack8(uh));
           if (has_cbam) {
             if (fused) {
 #pragma unroll
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(256, 3) nbf_pool_kernel(const void* __restrict
         float uh[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) uh[i] = fmaf(v[u][i], h_r[i], h_nm[i]);
-        stg8(pu + u * su, pack8(uh));
+        if (uhat != nullptr) stg8(pu + u * su, pack8(uh));      // inference: nothing is saved
         if (CBAM) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -1739,7 +1739,7 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
         if (u1 > mx) { mx = u1; mxc = c0 + i; }
         o[i] = act_fwd(u, d.slope);
       }
-      stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
+      if (uhat != nullptr) stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
       if (!d.has_cbam) stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
     }
     if (d.has_cbam) {
@@ -2165,7 +2165,7 @@ __global__ void __launch_bounds__(CLT, 6) nb_cl_fwd_kernel(const bvae_nb_desc d,
         if (u1 > mx) { mx = u1; mxc = c0 + i; }
         o[i] = act_fwd(u, d.slope);
       }
-      stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
+      if (uhat != nullptr) stg8(uhat + ubase + (int64_t)p * C + c0, pack8(uh));
       if (!d.has_cbam) stg8(out + obase + (int64_t)p * d.out_pitch + c0, pack8(o));
     }
     if (d.has_cbam) {
@@ -2962,6 +2962,7 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   int rc = validate(d, "nb_backward");
   if (rc) return rc;
   BVAE_REQUIRE(d->dout_pitch % 8 == 0 && d->dy_pitch % 8 == 0, BVAE_ERR_ALIGN, "nb_backward: pitches % 8 != 0");
+  BVAE_REQUIRE(d->uhat != nullptr, BVAE_ERR_SHAPE, "nb_backward: uhat is NULL (the forward pass ran in inference mode)");
   const int N = d->N, HW = d->H * d->W, C = d->C;
   if (use_nb_cluster(d)) {
     static bool attr = false;

@@ -50,6 +50,28 @@ def set_fuse_stats(flag: bool):
     _FUSE_STATS[0] = bool(flag)
 
 
+_SAVE_FOR_BACKWARD = True
+
+
+class saving:
+    """``with saving(False):`` -- forward passes issued inside do not write what only the backward needs (the bf16
+    normalised activation of every norm site: 2 of the 16 bytes per element the norm-block forward moves).  Entered by
+    the trunk / decoder autograd nodes with ``any(ctx.needs_input_grad)``: sampling (maker_bar.py:32-44, torch.no_grad)
+    and frozen-generator passes save nothing."""
+
+    def __init__(self, flag: bool):
+        self.flag = bool(flag)
+
+    def __enter__(self):
+        global _SAVE_FOR_BACKWARD
+        self.prev, _SAVE_FOR_BACKWARD = _SAVE_FOR_BACKWARD, self.flag
+
+    def __exit__(self, *exc):
+        global _SAVE_FOR_BACKWARD
+        _SAVE_FOR_BACKWARD = self.prev
+        return False
+
+
 def bump_param_epoch():
     _PARAM_EPOCH[0] += 1
 
@@ -478,7 +500,7 @@ class NormBlock:
         N, H, W, Cc = y.N, y.H, y.W, self.C
         dev = y.t.device
         ctx = {"N": N, "H": H, "W": W, "out": out,
-               "uhat": torch.empty((N, H, W, Cc), dtype=BF16, device=dev),
+               "uhat": torch.empty((N, H, W, Cc), dtype=BF16, device=dev) if _SAVE_FOR_BACKWARD else None,
                "nc": torch.empty((N, Cc, 8), dtype=torch.float32, device=dev),
                "nc_idx": torch.empty((N, Cc), dtype=torch.int32, device=dev)}
         fused = stats is not None
@@ -486,7 +508,8 @@ class NormBlock:
             stats = torch.empty((N * Cc * 6,), dtype=torch.float32, device=dev)
         d = self._desc(y.pitch, y.f32, out, N, H, W)
         d.stats_fused = int(fused)
-        d.y, d.uhat, d.out, d.stats = y.ptr, ctx["uhat"].data_ptr(), out.ptr, stats.data_ptr()
+        d.y, d.out, d.stats = y.ptr, out.ptr, stats.data_ptr()
+        d.uhat = ctx["uhat"].data_ptr() if ctx["uhat"] is not None else None      # NULL: inference, not written
         d.nc, d.nc_idx = ctx["nc"].data_ptr(), ctx["nc_idx"].data_ptr()
         if self.cbam is not None:
             ctx["sa"] = torch.empty((N, H * W, 2), dtype=torch.float32, device=dev)
@@ -505,6 +528,8 @@ class NormBlock:
         dev = dout.t.device
         out: Act = ctx["out"]
         d = self._desc(0, True, out, N, H, W)
+        if ctx["uhat"] is None:
+            raise RuntimeError("norm block: backward of a forward pass that ran under engine.saving(False)")
         d.uhat, d.out, d.nc, d.nc_idx = ctx["uhat"].data_ptr(), out.ptr, ctx["nc"].data_ptr(), ctx["nc_idx"].data_ptr()
         bwd_nc = torch.empty((N, Cc, 4), dtype=torch.float32, device=dev)
         d.bwd_nc = bwd_nc.data_ptr()

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..engine import BF16, Act, async_wgrad, grad_ptr, raw_dtype
+from ..engine import BF16, Act, async_wgrad, grad_ptr, raw_dtype, saving
 from .cbam import CBAM
 from .encodingBlock import _norm, gemm_of, norm_block
 from .weights_initializer import weights_init
@@ -153,7 +153,8 @@ class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, z, pre_z, phrase_feature, position, masks, *params):
         need = any(ctx.needs_input_grad)
-        recon, saved = module._fwd(z, pre_z, phrase_feature, position, masks, need)
+        with saving(need):
+            recon, saved = module._fwd(z, pre_z, phrase_feature, position, masks, need)
         ctx.module, ctx.saved = module, saved
         return recon
 

@@ -4,7 +4,7 @@ the hand-written data/weight-gradient kernels and accumulates straight into the 
 import torch
 import torch.nn as nn
 
-from ..engine import BF16, Act, async_wgrad
+from ..engine import BF16, Act, async_wgrad, saving
 from .encodingBlock import PitchTimeModule, PoolingModule, ResidualModule, TimePitchModule, gemm_of
 from .weights_initializer import weights_init
 
@@ -13,7 +13,8 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, *params):
         need = any(ctx.needs_input_grad)
-        z, saved = module._fwd(x, need)
+        with saving(need):
+            z, saved = module._fwd(x, need)
         ctx.module, ctx.saved = module, saved
         ctx.stream = torch.cuda.current_stream()
         return z

@@ -339,3 +339,31 @@ def test_pack_plan_matches_single_packs():
         ref_f = l._pack(l.Cout, l.Cin, l.f_src, l.f_perm)
         ref_d = l._pack(l.Cin, l.Cout, l.d_src, l.d_perm)
         assert torch.equal(bf, ref_f) and torch.equal(bd, ref_d)
+
+
+def test_norm_block_inference_mode_skips_saved_activation():
+    """engine.saving(False): the norm-block forward gets uhat = NULL and must produce the same block output without
+    writing it (every forward variant: tiled / fast / small-map); backward of such a pass is refused"""
+    eng = pkg("engine")
+    torch.manual_seed(4)
+    for (N, H, W, Cc, cbam) in [(3, 24, 15, 64, True), (3, 24, 15, 64, False), (2, 6, 3, 512, True), (5, 12, 8, 256, True),
+                                (2, 48, 30, 32, True)]:
+        gamma = torch.nn.Parameter(torch.randn(Cc, device="cuda") * 0.5 + 1)
+        beta = torch.nn.Parameter(torch.randn(Cc, device="cuda") * 0.1)
+        cb = None
+        if cbam:
+            cb = (torch.nn.Parameter(torch.randn(Cc // 16, Cc, 1, 1, device="cuda") * 0.1),
+                  torch.nn.Parameter(torch.randn(Cc, Cc // 16, 1, 1, device="cuda") * 0.1),
+                  torch.nn.Parameter(torch.randn(1, 2, 3, 3, device="cuda") * 0.1))
+        nb = eng.NormBlock(Cc, gamma, beta, cb, 1 if cbam else 0, 0.0)
+        y = eng.Act(torch.randn(N, H, W, Cc, device="cuda"), N, H, W, Cc)
+        o1, o2 = eng.Act.empty(N, H, W, Cc), eng.Act.empty(N, H, W, Cc)
+        c1 = nb.forward(y, o1)
+        with eng.saving(False):
+            c2 = nb.forward(y, o2)
+        torch.cuda.synchronize()
+        assert c1["uhat"] is not None and c2["uhat"] is None
+        e = rel_fro(o2.t.float(), o1.t.float())
+        assert e < 2e-3, ((N, H, W, Cc, cbam), e)          # same kernels, same inputs: only atomics order differs
+        with pytest.raises(RuntimeError):
+            nb.backward(c2, eng.Act.empty(N, H, W, Cc), eng.Act.empty(N, H, W, Cc))
