@@ -1,0 +1,115 @@
+"""GPU: the fully connected discriminators and graph/model_with_gan.Model (tcgen05 GEMMs through libbarvae.so) against
+the CPU oracle (oracle/disc_oracle.py, pinned to the reference's own outputs by tests/test_disc_cpu.py).
+Tolerances: four bf16 GEMM layers with fp32 accumulation -> probabilities within 3e-2, gradients within 10 %
+rel-Frobenius (measured values are written to gpurun_out/parity_report.jsonl; a wiring error shows as ~100 %)."""
+from collections import OrderedDict
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import pkg, rel_fro, report
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_run(fwd, sd, x):
+    sd = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    x = x.clone().requires_grad_(True)
+    out = fwd(x, sd)
+    loss = F.binary_cross_entropy(out, torch.ones_like(out))
+    loss.backward()
+    return out.detach(), float(loss), x.grad, OrderedDict((k, v.grad) for k, v in sd.items())
+
+
+@pytest.mark.parametrize("name", ["bar_z", "phrase_z", "feature"])
+def test_discriminator_forward_backward_vs_oracle(name):
+    import disc_oracle as D
+    DLoss = pkg("graph.loss.bar_loss").DLoss
+    if name == "feature":
+        cls, spec, fwd = pkg("graph.bar_discriminator_with_feature").BarFeatureDiscriminator, D.feature_disc_spec(), D.feature_disc_forward
+    else:
+        Z = pkg("graph.z_discriminator")
+        cls = Z.BarZDiscriminator if name == "bar_z" else Z.PhraseZDiscriminator
+        spec, fwd = D.z_disc_spec(), D.z_disc_forward
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 1152, generator=g)                        # a batch that is not a multiple of anything
+    sd = D.make_disc_state_dict(spec, 5, "lively")
+    want_out, want_loss, want_dx, want_g = _oracle_run(fwd, sd, x)
+    m = cls()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    xg = x.cuda().requires_grad_(True)
+    out = m(xg)
+    assert out.shape == (37, 1)
+    loss = DLoss()(out, torch.ones_like(out))                      # graph/loss/bar_loss.py:36-42
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {"out_maxabs": float((out.detach().cpu() - want_out).abs().max()),
+            "loss_rel": abs(float(loss) - want_loss) / want_loss, "dx": rel_fro(xg.grad, want_dx)}
+    for k, p in m.named_parameters():
+        errs[k] = rel_fro(p.grad, want_g[k])
+    report(test="disc_" + name, **errs)
+    assert errs["out_maxabs"] < 3e-2 and errs["loss_rel"] < 3e-2, errs
+    assert all(v < 0.1 for k, v in errs.items() if k not in ("out_maxabs", "loss_rel")), errs
+    # frozen discriminator while the generator trains (agent/barGen_with_gan.py freezes D): no parameter gradient,
+    # the input gradient still flows
+    for p in m.parameters():
+        p.requires_grad = False
+        p.grad = None
+    xg2 = x.cuda().requires_grad_(True)
+    DLoss()(m(xg2), torch.ones(37, 1, device="cuda")).backward()
+    assert all(p.grad is None for p in m.parameters())
+    assert rel_fro(xg2.grad, want_dx) < 0.1
+
+
+def test_discriminator_reference_init_is_finite():
+    """N(-1,1) weights (graph/weights_initializer.py:19-23): the second layer's ReLU kills every unit, the output is
+    sigmoid of the bias path; must agree with the oracle to 1e-2 and give finite gradients"""
+    import disc_oracle as D
+    Z = pkg("graph.z_discriminator")
+    sd = D.make_disc_state_dict(D.z_disc_spec(), 6, "reference")
+    x = torch.randn(6, 1152, generator=torch.Generator().manual_seed(77))
+    m = Z.BarZDiscriminator()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    out = m(x.cuda())
+    out.mean().backward()
+    want = D.z_disc_forward(x, sd)
+    assert float((out.detach().cpu() - want).abs().max()) < 1e-2
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+def test_model_with_gan_forward(oracle):
+    """graph/model_with_gan.py:20-38: 5-tuple / 2-tuple; the extra output is encoder(gen > 0.3).  The re-encoded feature
+    is compared with the ORACLE encoder applied to the bar this implementation thresholded (bf16 differences in gen may
+    flip cells that sit on the threshold, so the oracle's own thresholded bar is not the reference point)."""
+    import disc_oracle as D
+    O = oracle
+    Model = pkg("graph.model_with_gan").Model
+    sd = O.make_state_dict(O.generator_spec(), 11, "lively")
+    batch = O.make_inputs(2, 31)
+    model = Model()
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        gen, z, pre_z, pf, zf = model(*(t.cuda() for t in batch))
+        ogen, oz, opz, opf, _ = D.model_with_gan_forward(*batch, sd, True, None)
+        fake = D.fake_note(gen.cpu())
+        want_zf = O.encoder_forward(fake, sd, "encoder.")
+        lat = torch.randn(2, 1152, generator=torch.Generator().manual_seed(5))
+        gen2, zf2 = model(lat.cuda(), *(t.cuda() for t in batch[1:]), False)
+        want_zf2 = O.encoder_forward(D.fake_note(gen2.cpu()), sd, "encoder.")
+    e = {"gen": float((gen.cpu() - ogen).abs().max()), "z": rel_fro(z, oz), "pf": rel_fro(pf, opf),
+         "z_fake": rel_fro(zf, want_zf), "z_fake_sample": rel_fro(zf2, want_zf2),
+         "flipped_cells": float((fake != D.fake_note(ogen)).float().mean())}
+    report(test="model_with_gan", **e)
+    assert gen.shape == (2, 1, 96, 60) and zf.shape == (2, 1152) and gen2.shape == (2, 1, 96, 60) and zf2.shape == (2, 1152)
+    assert e["gen"] < 6e-2 and e["z"] < 2e-2 and e["pf"] < 2e-2, e
+    assert e["z_fake"] < 2e-2 and e["z_fake_sample"] < 2e-2, e
+    # training mode: gradients reach the encoder through both the reconstruction and the re-encoded feature
+    model.train()
+    out = model(*(t.cuda() for t in batch))
+    (out[0].mean() + out[4].mean()).backward()
+    assert all(torch.isfinite(p.grad).all() for n, p in model.named_parameters() if p.grad is not None)
+    assert float(model.encoder.linear.weight.grad.abs().sum()) > 0
