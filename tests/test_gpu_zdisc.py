@@ -13,6 +13,35 @@ from gpu_util import pkg, rel_fro, report
 pytestmark = pytest.mark.gpu
 
 
+class _RoundGrad(torch.autograd.Function):
+    """identity whose gradient is rounded to bf16 (what the kernels store between layers)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).float()
+
+
+def _ste_bf16(t):
+    """value rounded to bf16, gradient passed through"""
+    return t + (t.to(torch.bfloat16).float() - t).detach()
+
+
+def _z_disc_bf16_emulated(x, sd):
+    """disc_oracle.z_disc_forward with the storage precision of the CUDA path made explicit: bf16 GEMM operands
+    (weights, activations, inter-layer gradients), fp32 accumulation, bias and ReLU in fp32, fp32 head.  With the
+    roundings in the same places the ReLU masks agree, so this comparison is tight; against the pure fp32 oracle a
+    flipped mask entry is a 100 % error on that entry."""
+    h = _RoundGrad.apply(_ste_bf16(x))
+    for i in (0, 2, 4, 6):
+        pre = torch.nn.functional.linear(h, _ste_bf16(sd["net.%d.weight" % i]), sd["net.%d.bias" % i])
+        h = _RoundGrad.apply(_ste_bf16(torch.relu(_RoundGrad.apply(pre))))
+    return torch.sigmoid(torch.nn.functional.linear(h, sd["net.8.weight"], sd["net.8.bias"]))
+
+
 def _oracle_run(fwd, sd, x):
     sd = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
     x = x.clone().requires_grad_(True)
@@ -51,7 +80,19 @@ def test_discriminator_forward_backward_vs_oracle(name):
         errs[k] = rel_fro(p.grad, want_g[k])
     report(test="disc_" + name, **errs)
     assert errs["out_maxabs"] < 3e-2 and errs["loss_rel"] < 3e-2, errs
-    assert all(v < 0.1 for k, v in errs.items() if k not in ("out_maxabs", "loss_rel")), errs
+    # vs the pure fp32 oracle: a ReLU unit whose pre-activation sits within bf16 rounding of zero flips its mask, a
+    # 100 % error on that entry; a fraction f of flipped entries costs sqrt(f) rel-Frobenius per layer (measured:
+    # 0.2 % at the head growing to 12 % at the first layer).  Loose bound here, tight bound against the emulation below.
+    assert all(v < 0.3 for k, v in errs.items() if k not in ("out_maxabs", "loss_rel")), errs
+    if name != "feature":
+        _, _, emu_dx, emu_g = _oracle_run(_z_disc_bf16_emulated, sd, x)
+        emu = {"dx": rel_fro(xg.grad, emu_dx)}
+        for k, p in m.named_parameters():
+            emu[k] = rel_fro(p.grad, emu_g[k])
+        report(test="disc_%s_vs_bf16_emulation" % name, **emu)
+        assert all(v < 3e-2 for v in emu.values()), emu
+    else:
+        assert all(v < 2e-2 for k, v in errs.items() if k not in ("out_maxabs", "loss_rel")), errs
     # frozen discriminator while the generator trains (agent/barGen_with_gan.py freezes D): no parameter gradient,
     # the input gradient still flows
     for p in m.parameters():
@@ -60,7 +101,7 @@ def test_discriminator_forward_backward_vs_oracle(name):
     xg2 = x.cuda().requires_grad_(True)
     DLoss()(m(xg2), torch.ones(37, 1, device="cuda")).backward()
     assert all(p.grad is None for p in m.parameters())
-    assert rel_fro(xg2.grad, want_dx) < 0.1
+    assert rel_fro(xg2.grad, xg.grad) < 2e-2                       # same kernels, same inputs
 
 
 def test_discriminator_reference_init_is_finite():
