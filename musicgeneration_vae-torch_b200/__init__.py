@@ -16,7 +16,8 @@ def install_dropin():
     pkg = __name__
     for name in ("graph", "graph.model", "graph.encoder", "graph.decoder", "graph.phrase_encoder", "graph.cbam",
                  "graph.encodingBlock", "graph.weights_initializer", "graph.loss", "graph.loss.bar_loss",
-                 "config", "agent", "agent.barGen"):
+                 "graph.model_with_gan", "graph.z_discriminator", "graph.bar_discriminator_with_feature",
+                 "data", "data.bar_dataset", "config", "agent", "agent.barGen", "maker_bar"):
         try:
             sys.modules[name] = importlib.import_module(pkg + "." + name)
         except ImportError:
