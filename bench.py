@@ -167,7 +167,7 @@ def decode_bench(args, pkg, Model, dev, rank, world):
     # algorithmic work per bar with the phrase feature cached per 4 bars: 5.3223 GFLOP
     tf_peak, _, how = measured_peaks()
     val = bars / (ms * 1e-3)
-    print(json.dumps({"metric": "decode_bars_per_sec", "value": val, "unit": "bars/s", "n_gpus": world,
+    emit({"metric": "decode_bars_per_sec", "value": val, "unit": "bars/s", "n_gpus": world,
                       "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                       "config": {"workload": "maker_bar sampling loop, %d songs/GPU in lock-step, 4 bars per step, phrase "
@@ -175,18 +175,35 @@ def decode_bench(args, pkg, Model, dev, rank, world):
                                  "songs_per_gpu": S, "parallelism": "dp%d (independent songs, no collective)" % world},
                       "gpu_launches": pkg.launch_count(), "tflops_end_to_end": 5.3223e9 * val / 1e12,
                       "frac_of_tensor_peak": 5.3223e9 * val / 1e12 / tf_peak, "peak_source": how,
-                      "notes_on": float(roll.mean())}))
+                      "notes_on": float(roll.mean())})
 
 
-def _quiet_nccl():
-    """NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION (set on some boxes): keep stdout to the one JSON
-    line the driver parses.  An explicit INFO / TRACE request is left alone."""
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+_JSON_OUT = None
+
+
+def _protect_stdout():
+    """Keep stdout to the ONE JSON line the driver parses.  Libraries write to file descriptor 1 behind Python's back
+    (NCCL printf()s its version banner there at NCCL_DEBUG=VERSION and above -- measured on the 2-GPU run): point fd 1
+    at stderr for the whole run and write the JSON line to a saved duplicate of the original descriptor.  A
+    VERSION-only NCCL_DEBUG (set on some boxes) is dropped as well; an explicit WARN / INFO / TRACE request is left alone
+    and simply lands on stderr."""
+    global _JSON_OUT
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        del os.environ["NCCL_DEBUG"]
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
-    _quiet_nccl()
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -222,7 +239,7 @@ def main():
                                  "sample": "%d steps of %d bars (fwd+bwd+Adam), oracle port of the reference modules; "
                                            "/root/reference is not present on the GPU box" % (steps, args.cpu_batch)},
                 "e2e": {"value": bars_s, "unit": "bars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch
@@ -397,7 +414,7 @@ def main():
             "e2e_sequential": e2e_seq,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "e2e_packed": e2e_packed, "extra": extra}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
