@@ -961,7 +961,6 @@ __global__ void __launch_bounds__(256) nb_bwd_coef_kernel(int HW, int C, int has
   float* s_dh = s_hm + 64;      // [Cr]
   const int n = blockIdx.x;
   const float inv = 1.f / (float)HW;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* bn = bwd_nc + (int64_t)n * C * BN_W;
   const float* q0 = nc + (int64_t)n * C * NC_W;
   if (has_cbam) {
@@ -1641,7 +1640,6 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
   const int n = blockIdx.x, t = threadIdx.x;
   const int cv = t % NV, pl = t / NV, c0 = cv * 8;
   const int G = NV < 32 ? NV : 32;              // lanes of a warp that share a pixel
-  const int lane = t & 31, warp = t >> 5;
   const int64_t ybase = (int64_t)n * HW * d.y_pitch, ubase = (int64_t)n * HW * C;
   const int64_t obase = (int64_t)n * HW * d.out_pitch, rbase = (int64_t)n * HW * d.res_pitch;
   bf16* uhat = (bf16*)d.uhat;
@@ -1810,7 +1808,7 @@ __global__ void __launch_bounds__(256) nb_small_bwd_kernel(const bvae_nb_desc d)
   const int n = blockIdx.x, t = threadIdx.x;
   const int cv = t % NV, pl = t / NV, c0 = cv * 8;
   const int G = NV < 32 ? NV : 32;
-  const int lane = t & 31, warp = t >> 5;
+  const int lane = t & 31;
   const int has_cbam = d.has_cbam, res_mode = d.res_mode;
   const float slope = d.slope;
   const bf16* dout = (const bf16*)d.dout; const bf16* out = (const bf16*)d.out; const bf16* uhat = (const bf16*)d.uhat;
