@@ -9,8 +9,12 @@ samples (agent/barGen2.py:316-336 == maker_bar.py:32-44).
 What is different on purpose: one process per GPU with NCCL gradient all-reduce instead of nn.DataParallel
 (agent/barGen.py:96-105) -- launch with torchrun; no per-step ``.item()`` (the running loss stays on the device and
 is read once per logging interval); scalars go to a JSONL file when tensorboardX is absent.
-Out of scope: the GAN phase's discriminators; after ``pretraining_step_size``
-epochs the generator keeps training on the label-smoothed BCE (``Loss(..., is_pretraining=False)``)."""
+Also different: batches reach the device through ``GeneratorTrainer.prefetch`` (the next batch's H2D copy overlaps the
+current step), optionally as bits (``config.packed_input`` / ``config.packed_data_path``, data/packed.py); reference
+checkpoints load including the ``torch.optim.Adam`` state.
+Out of scope: the GAN schedules and the convolutional BarDiscriminator (the
+Linear-stack discriminators and graph/model_with_gan.Model exist); after ``pretraining_step_size`` epochs the
+generator keeps training on the label-smoothed BCE (``Loss(..., is_pretraining=False)``)."""
 import json
 import logging
 import os
