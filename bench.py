@@ -360,6 +360,7 @@ def main():
             else:
                 os.environ[k] = v
         detail = prof.pop("detail", {})
+        classes = prof.pop("classes", {})
         if os.environ.get("BVAE_PROFILE_DETAIL") and rank == 0:
             for k, (t, n) in sorted(detail.items(), key=lambda kv: -kv[1][0]):
                 print("%9.3f ms %4d  %s" % (t / prof_steps, n // prof_steps, k), file=sys.stderr)
@@ -374,6 +375,19 @@ def main():
                     "how": "CUDA events around every launch on its launching stream, in a profiling pass with the "
                            "branch / weight-gradient stream overlap switched off (the timed steps run with it on)",
                     "kernel_ms_per_step": gemm_ms, "launches_per_step": prof.get("n_gemm", 0) / prof_steps}
+        # the same launches split by their narrower channel count: FLOPs accounted per launch by engine.GemmLayer
+        # (SURVEY.md section 8 convention), time = CUDA events around that launch
+        try:
+            by_class = {}
+            for name, (cms, cfl, cn) in sorted(classes.items()):
+                tf = cfl / (cms * 1e-3) / 1e12 if cms > 0 else 0.0
+                by_class[name] = {"ms_per_step": cms / prof_steps, "tflops": tf, "frac": tf / tf_peak,
+                                  "launches_per_step": cn / prof_steps,
+                                  "share_of_flops": cfl / prof_steps / flops if flops else None}
+            roofline["by_class"] = by_class
+            roofline["flops_accounted_frac"] = sum(c[1] for c in classes.values()) / prof_steps / flops
+        except Exception as exc:
+            roofline["by_class"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         extra = {"normblock_ms_per_step": nb_ms, "step_ms_under_event_profiling": prof.get("total_ms", 0.0) / prof_steps,
                  "adam_gbs": None}
         # fused Adam alone: 28 B/param

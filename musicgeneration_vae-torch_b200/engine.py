@@ -124,8 +124,10 @@ def profile_begin():
     _PROF[0]["_start"].record()
 
 
-def _timed(tag, fn, *args, detail=None):
-    """run one library call; when profiling, bracket it with CUDA events on the launching stream"""
+def _timed(tag, fn, *args, detail=None, flops=0.0, cls=None):
+    """run one library call; when profiling, bracket it with CUDA events on the launching stream.  ``flops`` /
+    ``cls`` (contraction launches only): algorithmic FLOPs of the launch (SURVEY.md section 8 convention) and its
+    channel class, for the per-class tensor roofline in bench.py."""
     prof = _PROF[0]
     if prof is None:
         return fn(*args)
@@ -133,8 +135,12 @@ def _timed(tag, fn, *args, detail=None):
     e0.record()
     rc = fn(*args)
     e1.record()
-    prof.setdefault(tag, []).append((e0, e1, detail))
+    prof.setdefault(tag, []).append((e0, e1, detail, flops, cls))
     return rc
+
+
+def profiling() -> bool:
+    return _PROF[0] is not None
 
 
 def profile_end() -> dict:
@@ -144,15 +150,23 @@ def profile_end() -> dict:
     torch.cuda.synchronize()
     out = {"total_ms": prof.pop("_start").elapsed_time(end)}
     detail = {}
+    classes = {}
     for tag, evs in prof.items():
-        out[tag] = sum(a.elapsed_time(b) for a, b, _ in evs)
+        out[tag] = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
         out["n_" + tag] = len(evs)
-        for a, b, d in evs:
+        for a, b, d, fl, cl in evs:
+            ms = a.elapsed_time(b)
             if d is not None:
                 k = tag + ":" + d
                 t, n = detail.get(k, (0.0, 0))
-                detail[k] = (t + a.elapsed_time(b), n + 1)
+                detail[k] = (t + ms, n + 1)
+            if cl is not None:
+                c = classes.setdefault(cl, [0.0, 0.0, 0])      # ms, algorithmic FLOPs, launches
+                c[0] += ms
+                c[1] += fl
+                c[2] += 1
     out["detail"] = detail
+    out["classes"] = classes
     out["n_gemm"] = out.get("n_conv_gemm", 0) + out.get("n_wgrad_gemm", 0)
     return out
 
@@ -322,6 +336,18 @@ class GemmLayer:
             self._wd_key = k
         return self._wd
 
+    def channel_class(self) -> str:
+        """contraction launches by their narrower channel count (which decides what bounds them)"""
+        c = min(self.Cin, self.Cout)
+        return "ch>=256" if c >= 256 else ("ch128" if c >= 128 else "ch<=64")
+
+    def algorithmic_flops(self, n: int, hw_in: int, hw_out: int) -> float:
+        """SURVEY.md section 8 convention, one pass (forward == data gradient == weight gradient):
+        Conv 2*Cout*Hout*Wout*Cin*kh*kw, ConvT 2*Cin*Hin*Win*Cout*kh*kw, Linear 2*in*out -- per sample, times n.
+        hw_in / hw_out: pixels of the layer's input / output map."""
+        hw = hw_in if self.kind == "convT" else hw_out
+        return 2.0 * n * hw * self.Cin * self.Cout * self.kh * self.kw
+
     # ---- launches -------------------------------------------------------------------------------------
     def _run_phases(self, phases, wpk: torch.Tensor, x: Act, y: Act, cout: int, grid_of, bias, act, slope,
                     addend: Optional[Act], mask: Optional[Act], mask_slope: float, tag: str, want_stats: bool = False):
@@ -396,11 +422,19 @@ class GemmLayer:
         bp = bias.data_ptr() if bias is not None else None
         ap = addend.ptr if addend is not None else None
         mp = mask.ptr if mask is not None else None
+        fl, cl = 0.0, None
+        if profiling():
+            # forward: x is the layer's input, y its output; data gradient: x is dy (output side), y is dx (input side)
+            hw_in, hw_out = (x.H * x.W, y.H * y.W) if tag == "f" else (y.H * y.W, x.H * x.W)
+            fl, cl = self.algorithmic_flops(x.N, hw_in, hw_out) / max(1, len(descs)), self.channel_class()
+            if self.Cin == 1 and tag == "d":
+                fl = 0.0                     # the data gradient of a C_in = 1 stem is never needed
         for d, woff in descs:
             d.x, d.w, d.y, d.bias, d.addend, d.mask, d.stats = xp, wp + woff, yp, bp, ap, mp, sp
             _lib.check(_timed("conv_gemm", lib.bvae_conv_gemm, C.byref(d), _IMPL[0], st,
                               detail="%s %s %d->%d k%dx%d s%dx%d in%dx%d" % (tag, self.kind, self.Cin, self.Cout, self.kh,
-                                                                             self.kw, self.sy, self.sx, x.H, x.W)),
+                                                                             self.kw, self.sy, self.sx, x.H, x.W),
+                              flops=fl, cls=cl),
                        "conv_gemm[%s]" % tag)
         return stats
 
@@ -460,9 +494,13 @@ class GemmLayer:
                 if self._wscratch is None or self._wscratch.device != self.weight.device:
                     self._wscratch = torch.zeros(self.weight.numel(), dtype=torch.float32, device=self.weight.device)
                 d.scratch = self._wscratch.data_ptr()
+            fl, cl = 0.0, None
+            if profiling():
+                fl, cl = self.algorithmic_flops(x.N, x.H * x.W, dy.H * dy.W), self.channel_class()
             _lib.check(_timed("wgrad_gemm", lib.bvae_wgrad_gemm, C.byref(d), _IMPL[0], st,
                               detail="w %s %d->%d k%dx%d s%dx%d in%dx%d" % (self.kind, self.Cin, self.Cout, self.kh, self.kw,
-                                                                            self.sy, self.sx, x.H, x.W)), "wgrad_gemm")
+                                                                            self.sy, self.sx, x.H, x.W),
+                              flops=fl, cls=cl), "wgrad_gemm")
 
     def bias_grad(self, dy: Act):
         if self.bias is not None and self.bias.requires_grad:
