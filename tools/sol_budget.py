@@ -35,7 +35,7 @@ def main():
     B = a.bars
     t_gemm = GFLOP_PER_BAR * 1e9 * B / tf * 1e3
     plain = NORM_ELEMS_PER_BAR - CBAM_ELEMS_PER_BAR
-    impl_bytes = (CBAM_ELEMS_PER_BAR * (16 + 16) + plain * (10 + 14)) * B          # CBAM sites / plain IN sites
+    impl_bytes = (CBAM_ELEMS_PER_BAR * (16 + 16) + plain * (12 + 14)) * B          # CBAM sites / plain IN sites
     algo_bytes = NORM_ELEMS_PER_BAR * (4 + 6) * B
     t_nb_impl, t_nb_algo = impl_bytes / bw * 1e3, algo_bytes / bw * 1e3
     t_opt = (N_PARAMS * 28 + N_PARAMS * 1.14 * 6) / bw * 1e3                       # Adam 28 B/param + bf16 repack (2 operands)
