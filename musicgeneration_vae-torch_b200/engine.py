@@ -115,6 +115,48 @@ class async_wgrad:
         return False
 
 
+# ---- independent branches of one block on a companion stream (EXPERIMENTAL, off by default) --------------------
+# The two transposed-convolution branches of every decoder up-sampling block, and the decoder's two head stems, are
+# independent until they are concatenated; on one stream their latency-bound small-map norm blocks run back to back
+# with most SMs idle.  `with fork() as f: ...; f.join()` issues the enclosed launches on a companion of the current
+# stream.  Rules kept by the callers: no weight-gradient launch inside a fork (async_wgrad joins only the companion of
+# the stream that is current at its exit); tensors allocated inside belong to the companion's pool and are reused
+# there only after the next fork's wait on the current stream.  BVAE_DEC_STREAMS=1 enables (and BVAE_STREAMS=0 still
+# switches every overlap off); written after this round's last GPU minute, so it ships disabled until it has been
+# checked on a device (tests/test_gpu_model.py::test_decoder_branch_streams_agree, BVAE_TEST_EXPERIMENTAL=1).
+_FORK_STREAMS: Dict[tuple, "torch.cuda.Stream"] = {}
+
+
+def fork_enabled() -> bool:
+    return os.environ.get("BVAE_DEC_STREAMS", "0") == "1" and os.environ.get("BVAE_STREAMS", "1") != "0"
+
+
+class fork:
+    def __init__(self):
+        self.on = fork_enabled()
+
+    def __enter__(self):
+        if self.on:
+            self.cur = torch.cuda.current_stream()
+            key = (self.cur.device.index, self.cur.cuda_stream)
+            self.side = _FORK_STREAMS.get(key)
+            if self.side is None:
+                self.side = _FORK_STREAMS[key] = torch.cuda.Stream(device=self.cur.device)
+            self.side.wait_stream(self.cur)
+            self._ctx = torch.cuda.stream(self.side)
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self._ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.on:
+            self.cur.wait_stream(self.side)
+
+
 # ---- live per-kernel-class timing with CUDA events (bench.py's roofline block) -----------------------------
 _PROF = [None]
 

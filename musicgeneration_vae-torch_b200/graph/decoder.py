@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib
-from ..engine import BF16, Act, async_wgrad, grad_ptr, raw_dtype, saving
+from ..engine import BF16, Act, async_wgrad, fork, fork_enabled, grad_ptr, raw_dtype, saving
 from .cbam import CBAM
 from .encodingBlock import _norm, gemm_of, norm_block
 from .weights_initializer import weights_init
@@ -79,13 +79,21 @@ class _UpBlock(nn.Module):
     def fwd(self, x: Act, out: Act):
         Cc = out.C
         cat = Act.empty(out.N, out.H, out.W, 2 * Cc)
-        bctx = []
-        for i, (deconv, bn, cbam, mode) in enumerate(self._branches()):
+        def branch(i, deconv, bn, cbam, mode):
             g = gemm_of(deconv)
             y = Act.empty(out.N, out.H, out.W, Cc, dtype=raw_dtype())
             st = g.forward(x, y, want_stats=True)
             nb = norm_block(bn, cbam, mode, 0.0)
-            bctx.append((g, nb, nb.forward(y, cat.slice(i * Cc, Cc), stats=st)))
+            return (g, nb, nb.forward(y, cat.slice(i * Cc, Cc), stats=st))
+
+        b0, b1 = self._branches()
+        if fork_enabled():                      # EXPERIMENTAL (engine.fork): second branch on the companion stream
+            with fork() as f:
+                c1 = branch(1, *b1)
+            bctx = [branch(0, *b0), c1]
+            f.join()
+        else:
+            bctx = [branch(0, *b0), branch(1, *b1)]
         g3 = gemm_of(self.conv)
         y3 = Act.empty(out.N, out.H, out.W, Cc, dtype=raw_dtype())
         st3 = g3.forward(cat, y3, want_stats=True)
@@ -101,12 +109,30 @@ class _UpBlock(nn.Module):
         dcat = Act.empty(dout.N, dout.H, dout.W, 2 * Cc)
         g3.dgrad(dy3, dcat)
         dx = Act.empty(x.N, x.H, x.W, x.C)
+        # DeConvPitchPadding applies ONE InstanceNorm (bn2) to both branches: their backward passes accumulate into the
+        # same d-gamma / d-beta and must stay ordered on one stream
+        if not fork_enabled() or bctx[0][1].gamma is bctx[1][1].gamma:
+            for i, (g, nb, nctx) in enumerate(bctx):
+                dy = Act.empty(dout.N, dout.H, dout.W, Cc)
+                nb.backward(nctx, dcat.slice(i * Cc, Cc), dy)
+                g.wgrad(x, dy)
+                g.zero_bias_grad()          # bias feeds an InstanceNorm: gradient is identically zero
+                g.dgrad(dy, dx, addend=dx if i > 0 else None)
+            return dx
+        # EXPERIMENTAL (engine.fork): norm-block backward of the second branch on the companion stream; its weight /
+        # data gradients follow after the join (no weight-gradient launch inside a fork)
+        dys = [None, None]
+        with fork() as f:
+            dys[1] = Act.empty(dout.N, dout.H, dout.W, Cc)
+            bctx[1][1].backward(bctx[1][2], dcat.slice(Cc, Cc), dys[1])
+        dys[0] = Act.empty(dout.N, dout.H, dout.W, Cc)
+        bctx[0][1].backward(bctx[0][2], dcat.slice(0, Cc), dys[0])
         for i, (g, nb, nctx) in enumerate(bctx):
-            dy = Act.empty(dout.N, dout.H, dout.W, Cc)
-            nb.backward(nctx, dcat.slice(i * Cc, Cc), dy)
-            g.wgrad(x, dy)
-            g.zero_bias_grad()          # bias feeds an InstanceNorm: gradient is identically zero
-            g.dgrad(dy, dx, addend=dx if i > 0 else None)
+            if i == 1:
+                f.join()
+            g.wgrad(x, dys[i])
+            g.zero_bias_grad()
+            g.dgrad(dys[i], dx, addend=dx if i > 0 else None)
         return dx
 
 
@@ -218,8 +244,14 @@ class Decoder(nn.Module):
         else:
             keep, x = None, lin
         hcat = Act.empty(B, 6, 3, 2048)                     # torch.cat((pitch, time), 1)
-        c_p = self.pitch.fwd(x, hcat.slice(0, 1024))
-        c_t = self.time.fwd(x, hcat.slice(1024, 1024))
+        if fork_enabled():                      # EXPERIMENTAL (engine.fork): the two head stems are independent
+            with fork() as f:
+                c_t = self.time.fwd(x, hcat.slice(1024, 1024))
+            c_p = self.pitch.fwd(x, hcat.slice(0, 1024))
+            f.join()
+        else:
+            c_p = self.pitch.fwd(x, hcat.slice(0, 1024))
+            c_t = self.time.fwd(x, hcat.slice(1024, 1024))
         g1 = gemm_of(self.fit1)
         y = Act.empty(B, 6, 3, 1024, dtype=raw_dtype())
         st1 = g1.forward(hcat, y, want_stats=True)
