@@ -27,7 +27,7 @@ from torch.utils.data import DataLoader
 
 from .. import parallel
 from ..data.bar_dataset import NoteDataset, SyntheticBars
-from ..data.packed import PackedBatch, PackedNoteDataset, collate_packed
+from ..data.packed import PackedBatch, PackedMemmapDataset, PackedNoteDataset, collate_packed
 from ..graph.model import Model
 from ..maker_bar import sample_songs
 from ..metrics import AverageMeter
@@ -55,6 +55,17 @@ class _Plateau:
         return lr
 
 
+class _MemmapLoader:
+    """re-iterable view of PackedMemmapDataset.batches for one rank (same order every epoch, like the reference's
+    DataLoader(shuffle=False), agent/barGen.py:38-41)"""
+
+    def __init__(self, dataset, batch_size, rank, world, pin):
+        self.dataset, self.batch_size, self.rank, self.world, self.pin = dataset, batch_size, rank, world, pin
+
+    def __iter__(self):
+        return self.dataset.batches(self.batch_size, shuffle=False, rank=self.rank, world=self.world, pin=self.pin)
+
+
 class BarGen(object):
     def __init__(self, config, dataset=None):
         self.config = config
@@ -68,6 +79,9 @@ class BarGen(object):
         data_dir = os.path.join(config.root_path, config.data_path)
         if dataset is not None:
             self.dataset = dataset
+        elif getattr(config, "packed_array_path", None) and os.path.isdir(os.path.join(config.root_path,
+                                                                                       config.packed_array_path)):
+            self.dataset = PackedMemmapDataset(os.path.join(config.root_path, config.packed_array_path))
         elif getattr(config, "packed_data_path", None) and os.path.isdir(os.path.join(config.root_path,
                                                                                       config.packed_data_path)):
             self.dataset = PackedNoteDataset(config.root_path, config)
@@ -78,9 +92,14 @@ class BarGen(object):
         # DistributedSampler semantics of agent/barGen_horovod.py:49-50: each rank takes a disjoint shard
         b, e = parallel.shard_range(len(self.dataset), self.rank, self.world)
         self.indices = list(range(b, e))
-        self.dataloader = DataLoader(torch.utils.data.Subset(self.dataset, self.indices), batch_size=self.batch_size,
-                                     shuffle=False, num_workers=1, pin_memory=config.pin_memory,
-                                     collate_fn=self.make_batch)
+        if isinstance(self.dataset, PackedMemmapDataset):
+            # flat memory-mapped bit arrays: whole batches gathered with three fancy-index reads in this process
+            # (~0.5 M bars/s measured), no worker; batch_size counts BARS here (an .npz item holds several)
+            self.dataloader = _MemmapLoader(self.dataset, self.batch_size, self.rank, self.world, config.pin_memory)
+        else:
+            self.dataloader = DataLoader(torch.utils.data.Subset(self.dataset, self.indices),
+                                         batch_size=self.batch_size, shuffle=False, num_workers=1,
+                                         pin_memory=config.pin_memory, collate_fn=self.make_batch)
 
         self.manual_seed = random.randint(1, 10000)
         torch.manual_seed(self.manual_seed)

@@ -25,5 +25,6 @@ class Config(object):
     # --- additions ---
     bucket_mb = 64         # NCCL gradient bucket size
     vae_head = False
+    packed_array_path = None  # directory of flat memory-mappable bit arrays (tools/pack_dataset.py --arrays); wins if it exists
     packed_data_path = None   # directory of bit-packed .npz items (tools/pack_dataset.py); used when it exists
     packed_input = False   # loader emits bit-packed batches (data/packed.py): 32x less host->device traffic

@@ -152,3 +152,61 @@ def test_packed_dataset_on_disk_and_collate(tmp_path):
     bad["note_bits"] = bad["note_bits"][:, :-1]
     with pytest.raises(ValueError):
         P.collate_packed([bad])
+
+
+def test_memmap_dataset_batches(tmp_path):
+    """convert_dataset_to_arrays + PackedMemmapDataset: contiguous and shuffled batches equal packing the reference-
+    format bars directly; rank shards are disjoint and cover everything (agent/barGen_horovod.py:49-50 semantics)"""
+    P = pkg("data.packed")
+    src, dst = tmp_path / "f32", tmp_path / "arr"
+    src.mkdir()
+    r = np.random.RandomState(9)
+    items = []
+    for i, n in enumerate((3, 2, 4, 1)):
+        it = {"note": (r.rand(n, 1, 96, 60) < 0.05).astype(np.float32),
+              "pre_note": (r.rand(n, 1, 96, 60) < 0.05).astype(np.float32),
+              "pre_phrase": (r.rand(n, 1, 384, 60) < 0.05).astype(np.float32),
+              "position": r.randint(0, 332, size=(n,)).astype(np.int64)}
+        np.savez(src / ("%03d.npz" % i), **it)
+        items.append(it)
+    assert P.convert_dataset_to_arrays(str(src), str(dst)) == 10
+    ds = P.PackedMemmapDataset(str(dst))
+    assert len(ds) == 10
+    cat = lambda k: np.concatenate([it[k] for it in items], axis=0)
+
+    def want(idx):
+        return P.PackedBatch.from_arrays(cat("note")[idx], cat("pre_note")[idx], cat("pre_phrase")[idx], cat("position")[idx])
+
+    for idx in ([2, 3, 4, 5], [7, 0, 9, 3, 3], [4]):
+        got, w = ds.batch(idx), want(np.asarray(idx))
+        assert got.batch == len(idx) and torch.equal(got.bits, w.bits) and torch.equal(got.position, w.position)
+    one = P.collate_packed([ds[6], ds[1]])
+    w = want(np.asarray([6, 1]))
+    assert torch.equal(one.bits, w.bits) and torch.equal(one.position, w.position)
+    seen = []
+    for rank in range(3):
+        for b in ds.batches(2, shuffle=True, seed=4, rank=rank, world=3):
+            seen.extend(b.position.tolist())
+            assert b.batch <= 2
+    assert sorted(seen) == sorted(cat("position").tolist())
+    assert sum(b.batch for b in ds.batches(4, drop_last=True)) == 8
+
+
+def test_memmap_loader_is_reiterable_and_sharded(tmp_path):
+    P = pkg("data.packed")
+    Loader = pkg("agent.barGen")._MemmapLoader
+    ds0 = pkg("data.bar_dataset").SyntheticBars(n_items=5, bars_per_item=2, batch_size=2, seed=2)
+    src, dst = tmp_path / "f32", tmp_path / "arr"
+    src.mkdir()
+    for i in range(5):
+        np.savez(src / ("%03d.npz" % i), **ds0[i])
+    P.convert_dataset_to_arrays(str(src), str(dst))
+    ds = P.PackedMemmapDataset(str(dst))
+    for world in (1, 2):
+        total = []
+        for rank in range(world):
+            ld = Loader(ds, 4, rank, world, False)
+            first = [b.position.tolist() for b in ld]
+            assert first == [b.position.tolist() for b in ld]              # a second epoch sees the same batches
+            total += [p for b in first for p in b]
+        assert total == np.load(dst / "position.npy").tolist()
