@@ -79,6 +79,7 @@ class _UpBlock(nn.Module):
     def fwd(self, x: Act, out: Act):
         Cc = out.C
         cat = Act.empty(out.N, out.H, out.W, 2 * Cc)
+
         def branch(i, deconv, bn, cbam, mode):
             g = gemm_of(deconv)
             y = Act.empty(out.N, out.H, out.W, Cc, dtype=raw_dtype())

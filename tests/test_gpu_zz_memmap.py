@@ -35,3 +35,20 @@ def test_bargen_trains_from_memmapped_bits(tmp_path):
     l2 = agent.train_epoch()
     report(test="bargen_memmap", loss_epoch1=l1, loss_epoch2=l2, iterations=agent.iteration)
     assert agent.iteration == 4 and l1 == l1 and l2 == l2 and l2 < l1 * 1.5
+
+
+def test_unpack_kernel_against_committed_golden():
+    """tests/golden/packed_v1.npz (a reference-format batch loaded by the reference's own NoteDataset,
+    oracle/gen_golden_bits.py): the committed bits expand on the device to exactly the committed cells"""
+    from gpu_util import ROOT
+    P = pkg("data.packed")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "packed_v1.npz"))
+    B = g["position"].shape[0]
+    pb = P.PackedBatch(torch.from_numpy(g["bits"].copy()), torch.from_numpy(g["position"].copy()), B)
+    note32, bars, phrase16, pos, _ = pb.to_device(torch.device("cuda", 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(note32.cpu().numpy(), g["note"].astype(np.float32))
+    assert np.array_equal(bars.float().cpu().numpy(), np.concatenate([g["note"], g["pre_note"]]).astype(np.float32))
+    assert np.array_equal(phrase16.float().cpu().numpy(), g["pre_phrase"].astype(np.float32))
+    back, _ = P.threshold_pack(torch.cat((bars.float().reshape(-1), phrase16.float().reshape(-1))), 0.5)
+    assert np.array_equal(back.cpu().numpy(), g["bits"])

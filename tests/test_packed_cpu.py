@@ -210,3 +210,22 @@ def test_memmap_loader_is_reiterable_and_sharded(tmp_path):
             assert first == [b.position.tolist() for b in ld]              # a second epoch sees the same batches
             total += [p for b in first for p in b]
         assert total == np.load(dst / "position.npy").tolist()
+
+
+def test_golden_reference_format_batch():
+    """tests/golden/packed_v1.npz (oracle/gen_golden_bits.py: a batch loaded by the reference's own NoteDataset and
+    collated as agent/barGen.py:134-141): oracle, host packer and collate all produce the committed bits, and the bits
+    expand back to the reference-format arrays"""
+    P = pkg("data.packed")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "packed_v1.npz"))
+    note, pre, phrase = (g[k].astype(np.float32) for k in ("note", "pre_note", "pre_phrase"))
+    assert note.shape == (6, 1, 96, 60) and phrase.shape == (6, 1, 384, 60)
+    assert np.array_equal(BO.batch_layout(note, pre, phrase), g["bits"])
+    pb = P.PackedBatch.from_arrays(note, pre, phrase, g["position"])
+    assert np.array_equal(pb.bits.numpy(), g["bits"])
+    items = [P.pack_item({"note": note[a:b], "pre_note": pre[a:b], "pre_phrase": phrase[a:b], "position": g["position"][a:b]})
+             for a, b in ((0, 2), (2, 3), (3, 6))]
+    assert np.array_equal(P.collate_packed(items).bits.numpy(), g["bits"])
+    n2, p2, ph2, pos2 = pb.to_host_arrays()
+    assert np.array_equal(n2, note) and np.array_equal(p2, pre) and np.array_equal(ph2, phrase)
+    assert np.array_equal(BO.unpack(g["bits"][:6 * 720], 6 * 5760).reshape(note.shape), note)
