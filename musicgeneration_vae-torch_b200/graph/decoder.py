@@ -183,6 +183,8 @@ class _DecoderFn(torch.autograd.Function):
         with saving(need):
             recon, saved = module._fwd(z, pre_z, phrase_feature, position, masks, need)
         ctx.module, ctx.saved = module, saved
+        if getattr(module, "_bvae_keep_state", False):      # parity tests read the stored forward state (tests/gpu_util.py)
+            module._bvae_state = (recon, saved)
         return recon
 
     @staticmethod
@@ -240,8 +242,9 @@ class Decoder(nn.Module):
         gb.forward(bcat, lin.slice(0, 1152), act=True, slope=0.0)
         gp.forward(pcat, lin.slice(1152, 1152), act=True, slope=0.0)
         if masks is not None:
-            keep = torch.cat((masks[1], masks[0]), 1).to(BF16) * (1.0 / 0.7)     # bar first in the concat
-            x = Act(lin.t.view(B, 2304) * keep, B, 1, 1, 2304)
+            # nn.Dropout scales the kept values by 1/(1-p) in fp32 (decoder.py:196,201); the product is rounded once
+            keep = torch.cat((masks[1], masks[0]), 1).float() * (1.0 / 0.7)      # bar first in the concat
+            x = Act((lin.t.view(B, 2304).float() * keep).to(BF16), B, 1, 1, 2304)
         else:
             keep, x = None, lin
         hcat = Act.empty(B, 6, 3, 2048)                     # torch.cat((pitch, time), 1)
@@ -296,7 +299,7 @@ class Decoder(nn.Module):
         # dropout + ReLU backward on the [B,2304] latent features (tiny; PyTorch glue)
         dl = dx.t.view(B, 2304)
         if keep is not None:
-            dl = dl * keep
+            dl = (dl.float() * keep).to(BF16)
         dl = (dl * (lin.t.view(B, 2304) > 0)).contiguous()
         dlin = Act(dl, B, 1, 1, 2304)
         gb, gp = gemm_of(self.bar_linear), gemm_of(self.phrase_linear)

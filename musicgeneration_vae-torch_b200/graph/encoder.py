@@ -17,6 +17,8 @@ class _TrunkFn(torch.autograd.Function):
             z, saved = module._fwd(x, need)
         ctx.module, ctx.saved = module, saved
         ctx.stream = torch.cuda.current_stream()
+        if getattr(module, "_bvae_keep_state", False):      # parity tests read the stored forward state (tests/gpu_util.py)
+            module._bvae_state = (z, saved)
         return z
 
     @staticmethod

@@ -128,3 +128,37 @@ def test_sampling_loop(golden, oracle):
         roll = O.sample_song(sd, c["latents"], c["music_length"])
     assert roll.shape == (1, c["music_length"] * 4 * 96, 60)
     assert torch.equal(roll[0].to(torch.uint8), c["roll"])
+
+
+def test_emulation_exact_mode_is_the_oracle(oracle):
+    """oracle/barvae_emul.py with every rounding switched off must BE the fp32 oracle: pins its hand-written norm-block
+    backward (InstanceNorm projection on the saved normalised activation, CBAM routes taken at saved arg-max positions)
+    against plain autograd through barvae_oracle.  Tensors below 1e-6 of the gradient norm (biases in front of an
+    InstanceNorm: analytically zero) are rounding noise on both sides."""
+    import barvae_emul as E
+    from collections import OrderedDict
+    O = oracle
+    sd = O.make_state_dict(O.generator_spec(), 11, "lively")
+    batch = O.make_inputs(2, 21)
+    masks = O.draw_dropout_masks(2, 77)
+    leaves = OrderedDict((k, v.clone().requires_grad_(True)) for k, v in sd.items())
+    og = O.model_forward(*batch, leaves, True, masks)[0]
+    ol = O.loss_forward(og, batch[0], True)
+    ol.backward()
+    with E.exact():
+        el, egen, ez, eg = E.train_grads(sd, batch, masks)
+    assert float((egen - og.detach()).abs().max()) < 1e-4
+    assert abs(float(el) - float(ol)) < 1e-5 * abs(float(ol))
+    gnorm = sum(float(v.grad.norm()) ** 2 for v in leaves.values() if v.grad is not None) ** 0.5
+    for k, v in leaves.items():
+        if v.grad is None:
+            assert eg[k] is None, k
+            continue
+        n = float(v.grad.norm())
+        if n < 1e-6 * gnorm:
+            assert float(eg[k].norm()) < 1e-6 * gnorm, k
+            continue
+        assert float((eg[k] - v.grad).norm()) < 2e-2 * n, (k, float((eg[k] - v.grad).norm()) / n)
+    # and the rounded mode differs from the oracle only by bf16-sized forward changes
+    l2, gen2, _, _ = E.train_grads(sd, batch, masks)
+    assert float((gen2 - og.detach()).abs().max()) < 6e-2
