@@ -131,28 +131,34 @@ def cpu_reference_arm(batch, steps, warmup, target_s=0.0):
     return batch / dt, dt, cores, torch.get_num_threads(), len(times)
 
 
-def decode_bench(args, pkg, Model, dev, rank, world):
-    """BASELINE configs[4]: the maker_bar.py:32-44 sampling loop, S songs in lock-step per GPU (songs are independent,
-    so ranks need no collective).  One step = one 4-bar phrase: phrase encoder once, then 4 x (encoder + decoder)."""
+GFLOP_PER_BAR_DECODE_CACHED = 5.3223     # phrase feature computed once per 4 bars
+NB_ALGO_BYTES_PER_BAR = 4.26e6 * (4 + 6)   # 4.26 M InstanceNorm-site elements/bar, 4 B fwd + 6 B bwd
+
+
+def decode_measure(pkg, Model, dev, rank, world, songs, phrases, model=None, refine=False):
+    """BASELINE configs[4]: the maker_bar.py:32-44 sampling loop, `songs` songs in lock-step per GPU (songs are
+    independent, so ranks need no collective).  One step = one 4-bar phrase: phrase encoder once, then 4 x (encoder +
+    decoder).  Returns a dict (max over ranks of the CUDA-event time)."""
     import torch
     import torch.distributed as dist
     maker = importlib.import_module(PKG + ".maker_bar")
-    model = Model().to(dev).eval()
-    S = args.songs
+    if model is None:
+        model = Model().to(dev)
+    model.eval()
     g = torch.Generator(device=dev).manual_seed(99 + rank)
 
-    def run(phrases):
-        lat = torch.randn(phrases * 4, S, 1152, device=dev, generator=g)
-        return maker.sample_songs(model, lat, phrases)
+    def run(n):
+        lat = torch.randn(n * 4, songs, 1152, device=dev, generator=g)
+        return maker.sample_songs(model, lat, n)
 
     run(1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    pkg.reset_launch_count()
+    n0 = pkg.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    roll = run(args.steps)
+    roll = run(phrases)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -160,22 +166,90 @@ def decode_bench(args, pkg, Model, dev, rank, world):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+    bars = songs * 4 * phrases * world
+    tf_peak, _, how = measured_peaks()
+    val = bars / (ms * 1e-3)
+    tfl = GFLOP_PER_BAR_DECODE_CACHED * 1e9 * val / world / 1e12          # per GPU
+    return {"metric": "decode_bars_per_sec", "value": val, "unit": "bars/s", "n_gpus": world, "phrases": phrases,
+            "songs_per_gpu": songs, "ms_per_phrase": ms / phrases, "gpu_launches": pkg.launch_count() - n0,
+            "tflops_per_gpu": tfl, "frac_of_tensor_peak": tfl / tf_peak,
+            "ceiling_bars_per_sec_per_gpu": tf_peak * 1e12 / (GFLOP_PER_BAR_DECODE_CACHED * 1e9),
+            "peak_source": how, "notes_on": float(roll.float().mean()),
+            "what": "maker_bar sampling loop, %d songs/GPU in lock-step, 4 bars per phrase, phrase feature computed once "
+                    "per phrase, threshold 0.3 on the device; dp%d, independent songs, no collective" % (songs, world)}
+
+
+def decode_bench(args, pkg, Model, dev, rank, world):
+    import torch.distributed as dist
+    d = decode_measure(pkg, Model, dev, rank, world, args.songs, max(1, args.steps))
+    if world > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
-    bars = S * 4 * args.steps * world
-    # algorithmic work per bar with the phrase feature cached per 4 bars: 5.3223 GFLOP
-    tf_peak, _, how = measured_peaks()
-    val = bars / (ms * 1e-3)
-    emit({"metric": "decode_bars_per_sec", "value": val, "unit": "bars/s", "n_gpus": world,
-                      "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                      "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                      "config": {"workload": "maker_bar sampling loop, %d songs/GPU in lock-step, 4 bars per step, phrase "
-                                             "feature computed once per phrase, threshold 0.3 on device" % S,
-                                 "songs_per_gpu": S, "parallelism": "dp%d (independent songs, no collective)" % world},
-                      "gpu_launches": pkg.launch_count(), "tflops_end_to_end": 5.3223e9 * val / 1e12,
-                      "frac_of_tensor_peak": 5.3223e9 * val / 1e12 / tf_peak, "peak_source": how,
-                      "notes_on": float(roll.mean())})
+    emit({"metric": d["metric"], "value": d["value"], "unit": "bars/s", "n_gpus": world, "steps": d["phrases"], "warmup": 1,
+          "ms_per_step": d["ms_per_phrase"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "bf16", "data": "synthetic",
+          "config": {"workload": d["what"], "songs_per_gpu": args.songs, "parallelism": "dp%d" % world},
+          "gpu_launches": d["gpu_launches"], "tflops_end_to_end": d["tflops_per_gpu"] * world,
+          "frac_of_tensor_peak": d["frac_of_tensor_peak"], "peak_source": d["peak_source"], "notes_on": d["notes_on"]})
+
+
+def torch_eager_gpu(dev, bars, steps=3):
+    """SURVEY.md section 8(d) 'library comparator': the reference algorithm (oracle port: stock torch.nn.functional ops ->
+    cuDNN / cuBLAS / ATen kernels) run by PyTorch eager on the SAME B200, fp32 and bf16-autocast, forward + backward +
+    torch.optim.Adam.  `bars` per step is bounded (eager autograd keeps ~10x the activations this repo's path saves)."""
+    import torch
+    from collections import OrderedDict
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import barvae_oracle as O
+    out = {"bars_per_step": bars, "steps": steps,
+           "what": "oracle port of the reference modules on cuda through PyTorch eager (cuDNN/cuBLAS/ATen), fwd+bwd+"
+                   "torch.optim.Adam; TF32 off (fp32 row), torch.autocast(bfloat16) (bf16 row)"}
+    sd = O.make_state_dict(O.generator_spec(), 0, "reference")
+    batch = tuple(t.to(dev) for t in O.make_inputs(bars, 1234))
+    for name, autocast in (("fp32", False), ("bf16_autocast", True)):
+        try:
+            leaves = OrderedDict((k, v.to(dev).clone().requires_grad_(True)) for k, v in sd.items())
+            opt = torch.optim.Adam(list(leaves.values()), lr=0.002)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    gen = O.model_forward(*batch, leaves, True, None)[0]
+                loss = O.loss_forward(gen.float(), batch[0], True)
+                loss.backward()
+                opt.step()
+
+            step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"bars_per_sec": bars / (ms * 1e-3), "ms_per_step": ms,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            del leaves, opt
+        except Exception as exc:            # an auxiliary comparator must not take the headline measurement down
+            out[name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+    return out
+
+
+def ncu_traffic_table():
+    """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full` captures, kept under
+    profiles/ (this round's file first); keyed by kernel instance"""
+    for name in ("traffic_r2.json", "traffic_r1.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            try:
+                return json.load(open(p)), name
+            except ValueError:
+                pass
+    return {}, None
 
 
 _JSON_OUT = None
@@ -216,6 +290,9 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "decode"],
                     help="train = BASELINE configs[1] (the driver's default); decode = configs[4], maker_bar sampling")
     ap.add_argument("--songs", type=int, default=8192, help="decode: songs generated in lock-step per GPU")
+    ap.add_argument("--no-decode", action="store_true", help="train mode: skip the extra.decode measurement")
+    ap.add_argument("--no-eager", action="store_true", help="train mode: skip extra.torch_eager_gpu")
+    ap.add_argument("--eager-bars", type=int, default=64, help="bars per step of the PyTorch-eager comparator")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -226,18 +303,22 @@ def main():
            "l2": "per-step working set (~25 MB/bar of saved activations) is >> 126 MB L2; no flush needed"}
 
     if args.impl == "reference":
+        # The reference's own CPU implementation of the path (oracle port of graph/*.py + bar_loss.py + Adam; the
+        # reference is a script tree without setup.py, /root/reference does not exist on the GPU box) on all host cores.
+        # Same metric / unit / config as this repo's arm; --steps and --warmup are honoured as given; each step is a
+        # BOUNDED SAMPLE of the workload: --cpu-batch bars (BASELINE configs[0]) instead of the 512 of one GPU step.
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 5))
-        warm = max(1, min(args.warmup, 1))
-        bars_s, dt, cores, threads, _ = cpu_reference_arm(args.cpu_batch, steps, warm)
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        bars_s, dt, cores, threads, nst = cpu_reference_arm(args.cpu_batch, steps, warm)
         line = {"impl": "reference", "metric": "train_bars_per_sec", "value": bars_s, "unit": "bars/s",
                 "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": dict(cfg, cpu_sample="%d bars/step" % args.cpu_batch),
+                "config": cfg,
                 "cpu_baseline": {"value": bars_s, "unit": "bars/s", "cores": threads, "kind": "port",
-                                 "sample": "%d steps of %d bars (fwd+bwd+Adam), oracle port of the reference modules; "
-                                           "/root/reference is not present on the GPU box" % (steps, args.cpu_batch)},
+                                 "sample": "%d timed steps (after %d warm-up) of %d bars each (fwd+bwd+Adam) -- a bounded "
+                                           "sample of the %d-bar step; oracle port of the reference modules on %d host "
+                                           "threads" % (nst, warm, args.cpu_batch, args.batch, threads)},
                 "e2e": {"value": bars_s, "unit": "bars/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return
@@ -339,6 +420,7 @@ def main():
 
     # live roofline of the contraction kernels: CUDA events around every bvae_conv_gemm / bvae_wgrad_gemm launch
     roofline = None
+    roofline_hbm = None
     extra = {}
     if not args.no_profile:
         prof_steps = 2
@@ -369,12 +451,41 @@ def main():
         nb_ms = (prof.get("nb_forward", 0.0) + prof.get("nb_backward", 0.0)) / prof_steps
         flops = GFLOP_PER_BAR_TRAIN * 1e9 * B
         ach = flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                    "traffic": None, "peak_source": how + " (sustained cuBLAS bf16)",
-                    "kernel": "conv_tc2_kernel + wgrad_tc_kernel / wgrad_halo_kernel (all contraction launches of one step)",
-                    "how": "CUDA events around every launch on its launching stream, in a profiling pass with the "
-                           "branch / weight-gradient stream overlap switched off (the timed steps run with it on)",
-                    "kernel_ms_per_step": gemm_ms, "launches_per_step": prof.get("n_gemm", 0) / prof_steps}
+        how_timed = ("CUDA events around every launch on its launching stream, in a profiling pass with the branch / "
+                     "weight-gradient stream overlap switched off (the timed steps run with it on)")
+        aggregate = {"achieved": ach, "frac": ach / tf_peak, "kernel_ms_per_step": gemm_ms,
+                     "launches_per_step": prof.get("n_gemm", 0) / prof_steps,
+                     "kernels": "every contraction launch of one step (conv_tc2 / wgrad_tc / wgrad_halo / stem kernels)"}
+        # per kernel INSTANCE (template arguments as launched, bvae_last_kernel): the dominant one is the roofline headline
+        kernels = prof.pop("kernels", {})
+        by_kernel, dom = {}, None
+        for name, kk in kernels.items():
+            tf = kk["flops"] / (kk["ms"] * 1e-3) / 1e12 if kk["ms"] > 0 else 0.0
+            by_kernel[name] = {"ms_per_step": kk["ms"] / prof_steps, "tflops": tf, "frac": tf / tf_peak,
+                               "launches_per_step": kk["launches"] / prof_steps}
+            if kk["flops"] > 0 and (dom is None or kk["ms"] > kernels[dom]["ms"]):
+                dom = name
+        traffic_tab, traffic_src = ncu_traffic_table()
+        if dom is not None:
+            kk = kernels[dom]
+            top_layer, (lms, lfl, ln) = max(kk["layers"].items(), key=lambda kv: kv[1][0])
+            tr = traffic_tab.get(dom)
+            roofline = {"bound": "tensor", "kernel": dom, "achieved": by_kernel[dom]["tflops"], "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": by_kernel[dom]["frac"],
+                        "traffic": tr.get("dram_bytes_per_launch") if isinstance(tr, dict) else None,
+                        "traffic_note": (dict(tr, source="profiles/" + traffic_src) if isinstance(tr, dict) else
+                                         "no ncu --set full capture of this kernel instance under profiles/"),
+                        "peak_source": how + " (sustained cuBLAS bf16)", "how": how_timed,
+                        "algorithmic_flops_per_launch": kk["flops"] / kk["launches"],
+                        "avg_launch_ms": kk["ms"] / kk["launches"], "launches_per_step": kk["launches"] / prof_steps,
+                        "ms_per_step": kk["ms"] / prof_steps,
+                        "share_of_step": kk["ms"] / max(prof.get("total_ms", 0.0), 1e-9),
+                        "top_layer": {"layer": top_layer, "ms_per_launch": lms / ln,
+                                      "tflops": lfl / (lms * 1e-3) / 1e12 if lms > 0 else 0.0},
+                        "all_contractions": aggregate, "by_kernel": by_kernel}
+        else:
+            roofline = dict(aggregate, bound="tensor", peak=tf_peak, unit="TFLOP/s", traffic=None,
+                            peak_source=how + " (sustained cuBLAS bf16)", how=how_timed)
         # the same launches split by their narrower channel count: FLOPs accounted per launch by engine.GemmLayer
         # (SURVEY.md section 8 convention), time = CUDA events around that launch
         try:
@@ -388,6 +499,15 @@ def main():
             roofline["flops_accounted_frac"] = sum(c[1] for c in classes.values()) / prof_steps / flops
         except Exception as exc:
             roofline["by_class"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+        # the HBM-bound half of the step: all norm-block launches against their ALGORITHMIC bytes
+        nb_bytes = NB_ALGO_BYTES_PER_BAR * B
+        nb_gbs = nb_bytes / (nb_ms * 1e-3) / 1e9 if nb_ms > 0 else 0.0
+        roofline_hbm = {"bound": "hbm", "kernel": "norm-block sweeps (all bvae_nb_forward / bvae_nb_backward launches)",
+                        "achieved": nb_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": nb_gbs / hbm_peak,
+                        "algorithmic_bytes_per_step": nb_bytes, "ms_per_step": nb_ms,
+                        "launches_per_step": (prof.get("n_nb_forward", 0) + prof.get("n_nb_backward", 0)) / prof_steps,
+                        "traffic": (traffic_tab.get("norm_blocks") or {}).get("dram_bytes_per_step"),
+                        "peak_source": how + " (copy bandwidth)", "how": how_timed}
         extra = {"normblock_ms_per_step": nb_ms, "step_ms_under_event_profiling": prof.get("total_ms", 0.0) / prof_steps,
                  "adam_gbs": None}
         # fused Adam alone: 28 B/param
@@ -408,10 +528,23 @@ def main():
         torch.cuda.synchronize()
         extra["repack_ms"] = e0.elapsed_time(e1) / 5
 
+    # BASELINE configs[4] in the same record, at every N: maker_bar sampling, 8192 songs per GPU, 2 phrases (8 bars/song)
+    if not args.no_decode:
+        try:
+            del dbatch
+            torch.cuda.empty_cache()
+            extra["decode"] = decode_measure(pkg, Model, dev, rank, world, args.songs, 2, model=model)
+            model.train()
+        except Exception as exc:
+            extra["decode"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
+    if world == 1 and not args.no_eager:
+        del trainer, model, flat
+        torch.cuda.empty_cache()
+        extra["torch_eager_gpu"] = torch_eager_gpu(dev, args.eager_bars)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         bars_s, dt, cores, threads, nst = cpu_reference_arm(args.cpu_batch, 3, 1, target_s=12.0)
@@ -426,7 +559,8 @@ def main():
                             "trainer.step_batch(batch).item() -- every step's H2D copy and loss read-back inside the "
                             "timed region, batch i+1's copy overlapping step i on a copy stream"},
             "e2e_sequential": e2e_seq,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
+            "cpu_baseline": cpu,
             "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "e2e_packed": e2e_packed, "extra": extra}
     emit(line)
     if world > 1:

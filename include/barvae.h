@@ -47,6 +47,16 @@ uint64_t bvae_launch_count(void);
 void bvae_launch_count_reset(void);
 /* 1 if the current device is sm_100 (B200); kernels refuse to run elsewhere */
 int bvae_device_ok(void);
+/* name (with template arguments) of the kernel the calling thread's last bvae_conv_gemm / bvae_wgrad_gemm call launched:
+ * lets bench.py attribute CUDA-event times to kernel instances ("conv_tc2_kernel<64,256,4,0>") for the per-kernel roofline */
+const char* bvae_last_kernel(void);
+/* Deterministic mode (default: env BVAE_DETERMINISTIC, else 0).  When on, every reduction of the FORWARD pass (InstanceNorm
+ * statistics, CBAM pooling, BCE loss) runs in a fixed order -- shared-memory accumulations warp by warp, no cross-CTA float
+ * atomics -- so two runs on the same inputs are bit-identical (slower; a diagnostic that separates summation-order noise from
+ * races).  Weight gradients use one split per output tile (one ordered accumulation per element); the norm-block BACKWARD
+ * reductions stay atomic. */
+void bvae_set_deterministic(int on);
+int bvae_deterministic(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution  (forward of Conv2d / ConvTranspose2d / Linear and their data gradients).

@@ -75,6 +75,9 @@ SYMBOLS = [
     ("bvae_launch_count", C.c_uint64, []),
     ("bvae_launch_count_reset", None, []),
     ("bvae_device_ok", C.c_int, []),
+    ("bvae_last_kernel", C.c_char_p, []),
+    ("bvae_set_deterministic", None, [C.c_int]),
+    ("bvae_deterministic", C.c_int, []),
     ("bvae_conv_gemm", C.c_int, [C.POINTER(ConvDesc), C.c_int, c_vp]),
     ("bvae_conv_stats_ok", C.c_int, [C.POINTER(ConvDesc)]),
     ("bvae_wgrad_gemm", C.c_int, [C.POINTER(WgradDesc), C.c_int, c_vp]),
@@ -146,3 +149,12 @@ def launch_count() -> int:
 
 def reset_launch_count():
     load().bvae_launch_count_reset()
+
+
+def set_deterministic(flag: bool):
+    """bvae_set_deterministic (include/barvae.h): fixed-order forward reductions, one split per weight-gradient tile"""
+    load().bvae_set_deterministic(1 if flag else 0)
+
+
+def last_kernel() -> str:
+    return load().bvae_last_kernel().decode()

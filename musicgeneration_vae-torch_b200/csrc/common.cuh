@@ -14,6 +14,8 @@ namespace bvae {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> BVAE_ERR_CUDA (+message), counts the launch
 void count_launch(int n = 1);
+void note_kernel(const char* fmt, ...);   // remembered per host thread for bvae_last_kernel()
+bool deterministic();                     // bvae_set_deterministic / BVAE_DETERMINISTIC
 
 #define BVAE_REQUIRE(cond, code, ...)            \
   do {                                           \

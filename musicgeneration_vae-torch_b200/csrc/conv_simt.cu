@@ -165,6 +165,7 @@ int conv_simt_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   const int64_t M = (int64_t)d->N * d->QH * d->QW;
   dim3 grid((unsigned)ceil_div64(M, SM_BM), ceil_div(d->Cout, SM_BN));
   conv_simt_kernel<<<grid, 256, 0, stream>>>(*d);
+  note_kernel("conv_simt_kernel");
   return check_launch("conv_simt");
 }
 
@@ -180,6 +181,7 @@ int wgrad_simt_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   splits = (int)ceil_div64(P, pps);
   dim3 grid(ceil_div(d->Ca, SM_BM), ceil_div(d->Cs, SM_BN), d->ntaps * splits);
   wgrad_simt_kernel<<<grid, 256, 0, stream>>>(*d, splits, pps);
+  note_kernel("wgrad_simt_kernel");
   return check_launch("wgrad_simt");
 }
 

@@ -1271,6 +1271,7 @@ static int launch_conv(const ConvTcParams& P, int grid, cudaStream_t stream) {
     attr_done = true;
   }
   conv_tc_kernel<KB, BN, STAGES><<<grid, 128, smem, stream>>>(P);
+  note_kernel("conv_tc_kernel<%d,%d,%d>", KB, BN, STAGES);
   return check_launch("conv_tc");
 }
 
@@ -1296,6 +1297,7 @@ static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t str
   }
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
   conv_tc2_kernel<KB, BN, STAGES, BRES><<<grid, 256, smem, stream>>>(P);
+  note_kernel("conv_tc2_kernel<%d,%d,%d,%d>%s", KB, BN, STAGES, (int)BRES, P.halo ? "+halo" : "");
   return check_launch("conv_tc2");
 }
 
@@ -1462,6 +1464,7 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
     attr_done = true;
   }
   wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
+  note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
   return check_launch("wgrad_tc");
 }
 
@@ -1485,6 +1488,7 @@ static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_til
     const double fill = (double)ctas / (double)(waves * 148);
     if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
   }
+  if (deterministic()) splits = 1;        // one CTA accumulates a whole output tile: one ordered addition per element
   P->chunks_per_split = ceil_div(P->nchunks, splits);
   P->splits = ceil_div(P->nchunks, P->chunks_per_split);
   // Reduction target.  Many pixel splits over a small weight (encoder front, decoder back): vector atomics into the
@@ -1570,6 +1574,7 @@ static int wgrad_halo_try(const bvae_wgrad_desc* d, const ViewPlan* vp, cudaStre
     attr_smem = smem;
   }
   wgrad_halo_kernel<<<(int)grid, 128, smem, stream>>>(P);
+  note_kernel("wgrad_halo_kernel");
   rc = check_launch("wgrad_halo");
   *done = 1;
   if (rc || !packed) return rc;

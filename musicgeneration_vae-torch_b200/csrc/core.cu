@@ -1,6 +1,7 @@
 // core.cu -- library state (errors, launch counter) and the small memory-bound kernels:
 // weight packing, column sums, fit2+sigmoid, BCE, reparameterise+KL, flat Adam.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "common.cuh"
 #include <vector>
@@ -15,6 +16,24 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+static thread_local char g_kernel[160] = "";
+static std::atomic<int> g_det{-1};
+
+void note_kernel(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_kernel, sizeof(g_kernel), fmt, ap);
+  va_end(ap);
+}
+bool deterministic() {
+  int v = g_det.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("BVAE_DETERMINISTIC");
+    v = (e && e[0] == '1') ? 1 : 0;
+    g_det.store(v, std::memory_order_relaxed);
+  }
+  return v == 1;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
@@ -353,6 +372,9 @@ int bvae_version(void) { return 100; }
 const char* bvae_last_error(void) { return bvae::g_err; }
 uint64_t bvae_launch_count(void) { return bvae::g_launches.load(); }
 void bvae_launch_count_reset(void) { bvae::g_launches.store(0); }
+const char* bvae_last_kernel(void) { return bvae::g_kernel; }
+void bvae_set_deterministic(int on) { bvae::g_det.store(on ? 1 : 0); }
+int bvae_deterministic(void) { return bvae::deterministic() ? 1 : 0; }
 
 int bvae_device_ok(void) {
   int dev = 0;
@@ -462,7 +484,8 @@ int bvae_fit_sigmoid_fwd(const void* x, int x_pitch, const float* w, int64_t row
 
 int bvae_bce_fwd(const float* recon, const float* target, int64_t rows, int smoothing, float* loss_out,
                  void* stream) {
-  bce_fwd_kernel<<<grid_for(rows, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(recon, target, rows, smoothing,
+  // deterministic mode: one CTA, so the two scalars are reduced in a fixed order (no float atomics across CTAs)
+  bce_fwd_kernel<<<deterministic() ? 1 : grid_for(rows, 256, 148 * 4), 256, 0, (cudaStream_t)stream>>>(recon, target, rows, smoothing,
                                                                                 1.f / (float)rows, loss_out);
   return check_launch("bce_fwd");
 }

@@ -17,6 +17,33 @@ enum { BN_DGC = 0, BN_S1 = 1, BN_S2 = 2, BN_DMX = 3, BN_W = 4 };
 // bwd_px layout
 enum { BP_DQ = 0, BP_DMEAN = 1, BP_DMAX = 2, BP_W = 4 };
 
+// Deterministic mode (bvae_set_deterministic): shared-memory float accumulations of the FORWARD kernels run warp by warp,
+// lane by lane, so their summation order is fixed.  All threads of the CTA must reach the call.
+__constant__ int c_det = 0;
+template <class F>
+__device__ __forceinline__ void ordered(F f) {
+  if (!c_det) { f(); return; }
+  const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = 0; i < nw; ++i) {
+    if (w == i) {
+      for (int l = 0; l < 32; ++l) {
+        if (lane == l) f();
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+}
+static bool sync_det() {
+  static int synced = -1;
+  const int v = deterministic() ? 1 : 0;
+  if (v != synced) {
+    cudaMemcpyToSymbol(c_det, &v, sizeof(int));
+    synced = v;
+  }
+  return v == 1;
+}
+
 template <bool F32>
 __device__ __forceinline__ void load8(const void* base, int64_t off, float* f) {
   if (F32) ldg8f((const float*)base + off, f);
@@ -96,17 +123,19 @@ __global__ void __launch_bounds__(256, 3) nb_stats_kernel(const void* __restrict
       }
     }
   }
-  if (grp == 0) {
+  ordered([&] {
+    if (grp == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[cl + i], sum[i]);
-      atomicAdd(&s_sq[cl + i], sq[i]);
-      if (EXT) {
-        atomicMax(&s_kmax[cl + i], kx[i]);
-        atomicMax(&s_kmin[cl + i], kn[i]);
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_sum[cl + i], sum[i]);
+        atomicAdd(&s_sq[cl + i], sq[i]);
+        if (EXT) {
+          atomicMax(&s_kmax[cl + i], kx[i]);
+          atomicMax(&s_kmin[cl + i], kn[i]);
+        }
       }
     }
-  }
+  });
   __syncthreads();
   if (threadIdx.x < Cc) {
     const int64_t o = (int64_t)n * C + blockIdx.x * 256 + threadIdx.x;
@@ -1669,13 +1698,15 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
         if (v[i] < vmn[i]) { vmn[i] = v[i]; imn[i] = p; }
       }
     }
+    ordered([&] {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_sum[c0 + i], sum[i]);
-      atomicAdd(&s_sq[c0 + i], sq[i]);
-      if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
-      if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
-    }
+      for (int i = 0; i < 8; ++i) {
+        atomicAdd(&s_sum[c0 + i], sum[i]);
+        atomicAdd(&s_sq[c0 + i], sq[i]);
+        if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
+        if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
+      }
+    });
   }
   __syncthreads();
   const float inv = 1.f / (float)HW;
@@ -1747,10 +1778,12 @@ __global__ void __launch_bounds__(256) nb_small_fwd_kernel(const bvae_nb_desc d)
         const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
         if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
       }
-      if (valid && (t & (G - 1)) == 0) {
-        atomicAdd(&s_psum[p], sum);
-        atomicMax(&s_pkey[p], make_key(mx, (uint32_t)mxc));     // max value, smallest channel index on ties
-      }
+      ordered([&] {
+        if (valid && (t & (G - 1)) == 0) {
+          atomicAdd(&s_psum[p], sum);
+          atomicMax(&s_pkey[p], make_key(mx, (uint32_t)mxc));     // max value, smallest channel index on ties
+        }
+      });
     }
   }
   if (!d.has_cbam) return;
@@ -2084,15 +2117,17 @@ __global__ void __launch_bounds__(CLT, 6) nb_cl_fwd_kernel(const bvae_nb_desc d,
         if (on < vmn[i] || (on == vmn[i] && oin < imn[i])) { vmn[i] = on; imn[i] = oin; }
       }
     }
-    if ((t & 31) < G) {
+    ordered([&] {
+      if ((t & 31) < G) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        atomicAdd(&s_sum[c0 + i], sum[i]);
-        atomicAdd(&s_sq[c0 + i], sq[i]);
-        if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
-        if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
+        for (int i = 0; i < 8; ++i) {
+          atomicAdd(&s_sum[c0 + i], sum[i]);
+          atomicAdd(&s_sq[c0 + i], sq[i]);
+          if (vmx[i] != -INFINITY) atomicMax(&s_kmax[c0 + i], make_key(vmx[i], (uint32_t)imx[i]));
+          if (vmn[i] != INFINITY) atomicMax(&s_kmin[c0 + i], make_key(-vmn[i], (uint32_t)imn[i]));
+        }
       }
-    }
+    });
   }
   if (CLn > 1) cl.sync(); else __syncthreads();
   const float inv = 1.f / (float)HW;
@@ -2173,10 +2208,12 @@ __global__ void __launch_bounds__(CLT, 6) nb_cl_fwd_kernel(const bvae_nb_desc d,
         const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
         if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
       }
-      if (valid && (t & (G - 1)) == 0) {
-        atomicAdd(&s_psum[lp], sum);
-        atomicMax(&s_pkey[lp], make_key(mx, (uint32_t)mxc));
-      }
+      ordered([&] {
+        if (valid && (t & (G - 1)) == 0) {
+          atomicAdd(&s_psum[lp], sum);
+          atomicMax(&s_pkey[lp], make_key(mx, (uint32_t)mxc));
+        }
+      });
     }
   }
   if (!d.has_cbam) return;
@@ -2821,6 +2858,7 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   int rc = validate(d, "nb_forward");
   if (rc) return rc;
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  const bool det = sync_det();
   BVAE_REQUIRE(!d->stats_fused || !(use_nb_cluster(d) || nb_small_ok(d)), BVAE_ERR_UNSUPPORTED,
                "nb_forward: fused statistics are only consumed by the tiled path (H*W > 128)");
   if (use_nb_cluster(d)) {
@@ -2872,7 +2910,7 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
     int psplit = ceil_div(148 * 8, N * cchunks);
     const int maxsplit = HW / 256 > 0 ? HW / 256 : 1;
     if (psplit > maxsplit) psplit = maxsplit;
-    if (psplit < 1) psplit = 1;
+    if (psplit < 1 || det) psplit = 1;           // deterministic mode: no float atomics across CTAs
     if (psplit > 1) {
       if (cudaMemsetAsync(d->stats, 0, NC * 24, st) != cudaSuccess) { set_error("nb_forward: memset failed"); return BVAE_ERR_CUDA; }
     }

@@ -179,6 +179,7 @@ int stem_fwd_launch(const bvae_conv_desc* d, cudaStream_t stream) {
   if (grid > 148 * 16) grid = 148 * 16;
   if (grid < 1) grid = 1;
   stem_fwd_kernel<4><<<(int)grid, 256, 0, stream>>>(*d);
+  note_kernel("stem_fwd_kernel<4>");
   return check_launch("stem_fwd");
 }
 
@@ -190,6 +191,7 @@ int stem_wgrad_eligible(const bvae_wgrad_desc* d) {
 
 int stem_wgrad_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   stem_wgrad_kernel<4><<<148 * 4, 256, 0, stream>>>(*d);
+  note_kernel("stem_wgrad_kernel<4>");
   return check_launch("stem_wgrad");
 }
 

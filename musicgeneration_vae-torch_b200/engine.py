@@ -177,7 +177,8 @@ def _timed(tag, fn, *args, detail=None, flops=0.0, cls=None):
     e0.record()
     rc = fn(*args)
     e1.record()
-    prof.setdefault(tag, []).append((e0, e1, detail, flops, cls))
+    kern = _lib.last_kernel() if cls is not None else None      # contraction launches: the kernel instance that ran
+    prof.setdefault(tag, []).append((e0, e1, detail, flops, cls, kern))
     return rc
 
 
@@ -193,10 +194,11 @@ def profile_end() -> dict:
     out = {"total_ms": prof.pop("_start").elapsed_time(end)}
     detail = {}
     classes = {}
+    kernels = {}
     for tag, evs in prof.items():
         out[tag] = sum(ev[0].elapsed_time(ev[1]) for ev in evs)
         out["n_" + tag] = len(evs)
-        for a, b, d, fl, cl in evs:
+        for a, b, d, fl, cl, kern in evs:
             ms = a.elapsed_time(b)
             if d is not None:
                 k = tag + ":" + d
@@ -207,8 +209,19 @@ def profile_end() -> dict:
                 c[0] += ms
                 c[1] += fl
                 c[2] += 1
+            if kern:
+                kk = kernels.setdefault(kern, {"ms": 0.0, "flops": 0.0, "launches": 0, "layers": {}})
+                kk["ms"] += ms
+                kk["flops"] += fl
+                kk["launches"] += 1
+                if d is not None:
+                    lay = kk["layers"].setdefault(d, [0.0, 0.0, 0])
+                    lay[0] += ms
+                    lay[1] += fl
+                    lay[2] += 1
     out["detail"] = detail
     out["classes"] = classes
+    out["kernels"] = kernels
     out["n_gemm"] = out.get("n_conv_gemm", 0) + out.get("n_wgrad_gemm", 0)
     return out
 

@@ -415,3 +415,43 @@ def test_decoder_branch_streams_agree(oracle, monkeypatch):
     e = (b - a).abs().mean().item() / upd
     report(test="decoder_branch_streams", floor=floor, forked_vs_default=e, losses=[l0, l1])
     assert e < 2 * floor + 0.05 and abs(l1 - l0) < 0.1 * abs(l0), (floor, e, l0, l1)
+
+
+def test_deterministic_mode_forward_is_bit_identical(oracle, monkeypatch):
+    """bvae_set_deterministic(1): every forward reduction runs in a fixed order (include/barvae.h), so recon / z / pf and the
+    loss are BIT-identical between runs and between the stream-overlapped and the serial schedule -- any difference would be a
+    race, not summation order.  The default mode's spread (fp32 atomics order, amplified layer by layer through bf16
+    re-rounding) is measured beside it and only reported."""
+    O = oracle
+    lib = pkg("_lib")
+    Model = pkg("graph.model").Model
+    Loss = pkg("graph.loss.bar_loss").Loss
+    sd = O.make_state_dict(O.generator_spec(), 11, "lively")
+    batch = tuple(t.cuda() for t in O.make_inputs(3, 21))
+    masks = tuple(m.cuda() for m in O.draw_dropout_masks(3, 77))
+    model = _load(Model(), sd).train()
+
+    def run(streams):
+        monkeypatch.setenv("BVAE_STREAMS", "1" if streams else "0")
+        with torch.no_grad():
+            gen, z, pre_z, pf = model(*batch, True, masks)
+            loss = Loss()(gen, batch[0], True)
+        torch.cuda.synchronize()
+        return gen.clone(), z.clone(), pf.clone(), loss.clone()
+
+    spread = []
+    base = run(True)
+    for _ in range(3):
+        r = run(True)
+        spread.append(max(float((a - b).abs().max()) for a, b in zip(base[:3], r[:3])))
+    lib.set_deterministic(True)
+    try:
+        ref = run(True)
+        for streams in (True, False, True, False):
+            r = run(streams)
+            for a, b in zip(ref, r):
+                assert torch.equal(a, b), "deterministic mode: forward results differ between runs (streams=%s)" % streams
+    finally:
+        lib.set_deterministic(False)
+    report(test="deterministic_forward", default_mode_maxabs_spread=spread, det_loss=float(ref[3]), default_loss=float(base[3]))
+    assert abs(float(ref[3]) - float(base[3])) < 2e-2 * abs(float(base[3]))

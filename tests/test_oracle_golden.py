@@ -158,7 +158,9 @@ def test_emulation_exact_mode_is_the_oracle(oracle):
         if n < 1e-6 * gnorm:
             assert float(eg[k].norm()) < 1e-6 * gnorm, k
             continue
-        assert float((eg[k] - v.grad).norm()) < 2e-2 * n, (k, float((eg[k] - v.grad).norm()) / n)
+        # (fp32 on the CPU is itself not reproducible across thread counts on the smallest tensors: absolute floor)
+        e = float((eg[k] - v.grad).norm())
+        assert e < 2e-2 * n or e < 2e-5 * gnorm, (k, e / n, e / gnorm)
     # and the rounded mode differs from the oracle only by bf16-sized forward changes
     l2, gen2, _, _ = E.train_grads(sd, batch, masks)
     assert float((gen2 - og.detach()).abs().max()) < 6e-2
