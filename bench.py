@@ -208,6 +208,8 @@ def torch_eager_gpu(dev, bars, steps=3):
     sd = O.make_state_dict(O.generator_spec(), 0, "reference")
     batch = tuple(t.to(dev) for t in O.make_inputs(bars, 1234))
     for name, autocast in (("fp32", False), ("bf16_autocast", True)):
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
         try:
             leaves = OrderedDict((k, v.to(dev).clone().requires_grad_(True)) for k, v in sd.items())
             opt = torch.optim.Adam(list(leaves.values()), lr=0.002)
@@ -292,7 +294,7 @@ def main():
     ap.add_argument("--songs", type=int, default=8192, help="decode: songs generated in lock-step per GPU")
     ap.add_argument("--no-decode", action="store_true", help="train mode: skip the extra.decode measurement")
     ap.add_argument("--no-eager", action="store_true", help="train mode: skip extra.torch_eager_gpu")
-    ap.add_argument("--eager-bars", type=int, default=64, help="bars per step of the PyTorch-eager comparator")
+    ap.add_argument("--eager-bars", type=int, default=256, help="bars per step of the PyTorch-eager comparator")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
