@@ -87,11 +87,15 @@ class BarGen(object):
             self.dataset = PackedNoteDataset(config.root_path, config)
         elif os.path.isdir(data_dir):
             self.dataset = NoteDataset(config.root_path, config)
+        elif getattr(config, "synthetic", False):
+            self.dataset = SyntheticBars(64, 4, self.batch_size)         # explicit opt-in only (config.synthetic)
         else:
-            self.dataset = SyntheticBars(64, 4, self.batch_size)
-        # DistributedSampler semantics of agent/barGen_horovod.py:49-50: each rank takes a disjoint shard
-        b, e = parallel.shard_range(len(self.dataset), self.rank, self.world)
-        self.indices = list(range(b, e))
+            # the reference raises from os.listdir (data/bar_dataset.py:12); a mistyped path must not train on noise
+            raise FileNotFoundError("no dataset directory %r (nor config.packed_array_path / packed_data_path); set "
+                                    "config.synthetic = True to train on random bars" % data_dir)
+        # DistributedSampler semantics of agent/barGen_horovod.py:49-50: every rank takes an equally long shard (padded by
+        # wrapping around), so all ranks run the same number of optimiser steps / all-reduces per epoch
+        self.indices = parallel.shard_indices(len(self.dataset), self.rank, self.world)
         if isinstance(self.dataset, PackedMemmapDataset):
             # flat memory-mapped bit arrays: whole batches gathered with three fancy-index reads in this process
             # (~0.5 M bars/s measured), no worker; batch_size counts BARS here (an .npz item holds several)
@@ -118,12 +122,25 @@ class BarGen(object):
         self.epoch = 0
         self.load_checkpoint(config.checkpoint_file)
         if self.reducer is not None:                      # rank 0's weights / optimiser state win (horovod :130-134)
-            self.reducer.broadcast_parameters(0)
+            self.reducer.broadcast_parameters(0, trainer=self.opt_gen1)
+            self.lr_gen1 = self.opt_gen1.lr
+            self._sync_host_state()
         self.summary = None
         if self.rank == 0:
             os.makedirs(os.path.join(config.root_path, config.summary_dir), exist_ok=True)
             self.summary = open(os.path.join(config.root_path, config.summary_dir, "scalars.jsonl"), "a")
             print("Number of generator parameters: {}".format(sum(p.numel() for p in self.generator.parameters())))
+
+    def _sync_host_state(self):
+        """epoch counter and LR-scheduler state of rank 0 (the only rank that is guaranteed to have read a checkpoint)"""
+        import torch.distributed as dist
+        st = self.scheduler_gen1
+        v = torch.tensor([float(self.epoch), st.best if st.best != float("inf") else -1.0, float(st.bad), float(st.cool)],
+                         dtype=torch.float64, device=self.device)
+        dist.broadcast(v, src=0)
+        self.epoch = int(v[0].item())
+        st.best = float("inf") if v[1].item() < 0 else float(v[1].item())
+        st.bad, st.cool = int(v[2].item()), int(v[3].item())
 
     def set_logger(self):
         logger = logging.getLogger("barGen")
@@ -164,6 +181,9 @@ class BarGen(object):
             self.opt_gen1.load_state_dict(opt)
             self.lr_gen1 = self.opt_gen1.lr
         self.epoch = ck.get("epoch", 0)
+        sch = ck.get("scheduler_gen1")                   # not in reference checkpoints (it never restores its schedulers)
+        if isinstance(sch, dict):
+            self.scheduler_gen1.best, self.scheduler_gen1.bad, self.scheduler_gen1.cool = sch["best"], sch["bad"], sch["cool"]
 
     def save_checkpoint(self, file_name, epoch):
         if self.rank != 0:
@@ -171,8 +191,14 @@ class BarGen(object):
         os.makedirs(self._ckpt_dir(), exist_ok=True)
         tmp_name = os.path.join(self._ckpt_dir(), "checkpoint_{}.pth.tar".format(epoch))
         gen_sd = {"module." + k: v.detach().clone() for k, v in self.generator.state_dict().items()}
-        state = {"epoch": self.epoch, "generator_state_dict": gen_sd, "gen_optimizer1": self.opt_gen1.state_dict(),
-                 "gen_optimizer2": self.opt_gen1.state_dict(), "lr_gen": self.lr_gen1}
+        # gen_optimizer1/2 in torch.optim.Adam.state_dict() form, as the reference stores them (agent/barGen.py:176-177): a
+        # reference-side torch.optim.Adam.load_state_dict accepts it.  This agent trains the generator alone, so the
+        # discriminator entries of the reference's dictionary (:178-186) are not written -- its load_checkpoint indexes
+        # them unconditionally and needs them added (agent/barGen_with_gan.py here writes all of them).
+        opt_sd = self.opt_gen1.torch_state_dict()
+        st = self.scheduler_gen1
+        state = {"epoch": self.epoch, "generator_state_dict": gen_sd, "gen_optimizer1": opt_sd, "gen_optimizer2": opt_sd,
+                 "lr_gen": self.lr_gen1, "scheduler_gen1": {"best": st.best, "bad": st.bad, "cool": st.cool}}
         torch.save(state, tmp_name)
         shutil.copyfile(tmp_name, os.path.join(self._ckpt_dir(), file_name))
 
@@ -200,8 +226,14 @@ class BarGen(object):
             self.iteration += 1
             dev_sum += self.opt_gen1.step_batch(batch)                                  # stays on the device
             n += 1
-        if n:
-            avg_gen_loss.update(float(dev_sum) / n, n)                                  # one D2H read per epoch
+        tot = torch.stack((dev_sum.double(), torch.tensor(float(n), dtype=torch.float64, device=self.device)))
+        if self.world > 1:
+            # every rank feeds the plateau scheduler the SAME epoch mean: with per-shard means the ranks cross the
+            # threshold / patience in different epochs, their learning rates diverge and the replicas drift apart
+            torch.distributed.all_reduce(tot)
+        tot = tot.tolist()                                                              # one D2H read per epoch
+        if tot[1] > 0:
+            avg_gen_loss.update(tot[0] / tot[1], int(tot[1]))
         self.lr_gen1 = self.opt_gen1.lr = self.scheduler_gen1.step(avg_gen_loss.val, self.opt_gen1.lr)
         if self.summary is not None:
             tag = "pre_train/Generator_loss" if self.opt_gen1.is_pretraining else "train/Generator_loss"

@@ -46,6 +46,16 @@ extern "C" int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream) {
       return BVAE_OK;
     }
     BVAE_REQUIRE(d->ntaps >= 1 && d->ntaps <= BVAE_MAX_TAPS, BVAE_ERR_SHAPE, "conv_gemm: ntaps=%d", d->ntaps);
+    // the same bounds the single-phase path checks below, per phase
+    BVAE_REQUIRE(d->N > 0 && d->C > 0 && d->Cout > 0, BVAE_ERR_SHAPE, "conv_gemm: empty problem");
+    BVAE_REQUIRE(d->sy >= 1 && d->sx >= 1 && d->osy >= 1 && d->osx >= 1, BVAE_ERR_SHAPE, "conv_gemm: bad strides");
+    BVAE_REQUIRE(d->w_pitch >= d->ntaps * d->C, BVAE_ERR_SHAPE, "conv_gemm: w_pitch too small");
+    for (int i = 0; i < d->nphase; ++i) {
+      BVAE_REQUIRE(d->ph_ntaps[i] >= 1 && d->ph_QH[i] >= 0 && d->ph_QW[i] >= 0, BVAE_ERR_SHAPE, "conv_gemm: bad phase %d", i);
+      if (d->ph_QH[i] == 0 || d->ph_QW[i] == 0) continue;
+      BVAE_REQUIRE((d->ph_QH[i] - 1) * d->osy + d->ph_ooy[i] < d->OH && (d->ph_QW[i] - 1) * d->osx + d->ph_oox[i] < d->OW,
+                   BVAE_ERR_SHAPE, "conv_gemm: grid of phase %d exceeds the output tensor", i);
+    }
     return conv_tc_launch(d, (cudaStream_t)stream);
   }
   BVAE_REQUIRE(d->ntaps >= 1 && d->ntaps <= BVAE_MAX_TAPS, BVAE_ERR_SHAPE, "conv_gemm: ntaps=%d", d->ntaps);

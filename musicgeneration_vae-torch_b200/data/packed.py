@@ -246,8 +246,12 @@ class PackedMemmapDataset(torch.utils.data.Dataset):
         the DistributedSampler semantics of agent/barGen_horovod.py:49-50"""
         n = len(self)
         order = np.random.RandomState(seed).permutation(n) if shuffle else np.arange(n)
-        per = (n + world - 1) // world
-        mine = order[rank * per:min(n, (rank + 1) * per)]
+        # every rank gets the same number of bars (hence of batches and of gradient all-reduces per epoch): the order is
+        # padded by wrapping around, as torch's DistributedSampler does (parallel.shard_indices)
+        per = (n + world - 1) // world if not drop_last else n // world
+        if n > 0 and per * world > n:
+            order = np.concatenate([order, order[np.arange(per * world - n) % n]])
+        mine = order[rank * per:(rank + 1) * per]
         for i in range(0, len(mine), batch_size):
             idx = mine[i:i + batch_size]
             if drop_last and len(idx) < batch_size:

@@ -36,10 +36,29 @@ def init_from_env(backend: Optional[str] = None) -> Tuple[int, int, int]:
 
 
 def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
-    """Contiguous shard [begin, end) of n_items for this rank (DistributedSampler without shuffling/padding)."""
+    """Contiguous shard [begin, end) of n_items for this rank (DistributedSampler without shuffling/padding).
+    Shards of unequal length make ranks run different numbers of optimiser steps; training loops use
+    ``shard_indices`` instead."""
     per = (n_items + world - 1) // world
     b = min(n_items, rank * per)
     return b, min(n_items, b + per)
+
+
+def shard_indices(n_items: int, rank: int, world: int, drop_last: bool = False) -> List[int]:
+    """This rank's item indices with EVERY rank getting the same count, as torch's DistributedSampler does
+    (agent/barGen_horovod.py:49-50): the index list is padded by wrapping around to ``world * ceil(n / world)`` entries
+    (``drop_last``: truncated to ``world * floor(n / world)``) and rank r takes the contiguous block r.  Equal counts
+    mean equal numbers of batches, hence equal numbers of collectives per epoch on every rank -- unequal shards pair
+    all-reduces of different steps and hang the longer ranks at the end of the epoch."""
+    if n_items <= 0:
+        return []
+    if drop_last:
+        per = n_items // world
+        order = list(range(per * world))
+    else:
+        per = (n_items + world - 1) // world
+        order = [i % n_items for i in range(per * world)]
+    return order[rank * per:(rank + 1) * per]
 
 
 class GradReducer:
@@ -70,13 +89,34 @@ class GradReducer:
         model.phrase_encoder.phrase_encoder._bvae_on_bwd_done = lambda: r.segment_ready("phrase_encoder")
         return r
 
-    def broadcast_parameters(self, root: int = 0):
-        """hvd.broadcast_parameters(state_dict, root_rank=0) (agent/barGen_horovod.py:130-134), one call."""
-        if self.world > 1:
-            dist.broadcast(self.flat.data, src=root, group=self.group)
-            if self.flat.exp_avg is not None:
-                dist.broadcast(self.flat.exp_avg, src=root, group=self.group)
-                dist.broadcast(self.flat.exp_avg_sq, src=root, group=self.group)
+    def broadcast_parameters(self, root: int = 0, trainer=None):
+        """hvd.broadcast_parameters(state_dict, root_rank=0) (agent/barGen_horovod.py:130-134) plus -- unlike the reference
+        -- the optimiser state.  Every rank issues the SAME collectives whatever it holds locally (only the root may have
+        read a checkpoint): a header [has_state, step_count, lr] goes first, ranks without moments allocate zeros.  The
+        bf16 GEMM operands packed from the old parameter values are invalidated and repacked."""
+        if self.world <= 1:
+            return
+        from . import engine
+        flat = self.flat
+        dev = flat.data.device
+        has = flat.exp_avg is not None
+        head = torch.tensor([1.0 if has else 0.0, float(trainer.step_count) if trainer is not None else 0.0,
+                             float(trainer.lr) if trainer is not None else 0.0], dtype=torch.float64, device=dev)
+        dist.broadcast(head, src=root, group=self.group)
+        dist.broadcast(flat.data, src=root, group=self.group)
+        if head[0].item() > 0:
+            if flat.exp_avg is None:
+                flat.exp_avg = torch.zeros_like(flat.data)
+                flat.exp_avg_sq = torch.zeros_like(flat.data)
+            dist.broadcast(flat.exp_avg, src=root, group=self.group)
+            dist.broadcast(flat.exp_avg_sq, src=root, group=self.group)
+        elif has:                                   # the root has no state: nobody keeps one
+            flat.exp_avg = flat.exp_avg_sq = None
+        if trainer is not None:
+            trainer.step_count, trainer.lr = int(head[1].item()), float(head[2].item())
+        engine.bump_param_epoch()                   # parameters are .data views: _version did not change
+        if flat.data.is_cuda:
+            engine.repack_weights(flat)
 
     def segment_ready(self, name: str):
         """Called right after a module's backward kernels were enqueued: all-reduce its gradient slice.
