@@ -188,7 +188,11 @@ def test_memmap_dataset_batches(tmp_path):
         for b in ds.batches(2, shuffle=True, seed=4, rank=rank, world=3):
             seen.extend(b.position.tolist())
             assert b.batch <= 2
-    assert sorted(seen) == sorted(cat("position").tolist())
+    # 10 bars over 3 ranks: every rank gets 4 (two bars are visited twice -- DistributedSampler's wrap-around padding,
+    # so that all ranks run the same number of steps), every bar is visited
+    from collections import Counter
+    have, need = Counter(seen), Counter(cat("position").tolist())
+    assert len(seen) == 12 and all(have[k] >= v for k, v in need.items())
     assert sum(b.batch for b in ds.batches(4, drop_last=True)) == 8
 
 
