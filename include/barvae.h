@@ -259,6 +259,42 @@ int bvae_unpack_bits(const void* bits, int64_t nbits, void* out_bf16, float* out
                      void* stream);
 int bvae_threshold_pack(const float* p, int64_t n, float threshold, void* bits, float* out_f32, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * nn.BatchNorm2d(C, eps, momentum, affine) (+ optional (Leaky)ReLU) on an NHWC tensor with few channels: the norm of the
+ * GAN-phase piano-roll discriminator (graph/bar_discriminator.py:19-23,69,113-114,153: BatchNorm2d(8..64, eps=1e-5,
+ * momentum=0.01), OnOffFeature's default-momentum BatchNorm2d(8)) and of the Refiner (graph/refiner.py:13,20,37,43).
+ * Replaces ATen's batch_norm / cudnn_batch_norm (+ relu) and their backward.
+ *   training != 0: statistics over all P = N*H*W pixels of THIS rank (the reference does not synchronise them across ranks,
+ *     SURVEY.md section 8e); running_mean / running_var (nullable) are updated with `momentum` and the unbiased variance.
+ *   training == 0: running statistics.
+ *   y = act(gamma * (x - mean) * rstd + beta);  backward: dx (bf16), dgamma += , dbeta += (both nullable).
+ * C is a power of two <= 64.  `save` holds 4*C floats (mean, rstd written by forward; two sums by backward), `scratch`
+ * bvae_bn_scratch_floats(C) floats.  Every reduction is two-stage with a fixed order: no float atomics, bit-reproducible.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct bvae_bn_desc {
+  int64_t P;                     /* pixels: N * H * W */
+  int32_t C, x_pitch, y_pitch, dy_pitch, dx_pitch;
+  int32_t x_f32, y_f32, dy_f32;  /* element types: 1 = fp32, 0 = bf16 (dx is always bf16) */
+  int32_t act;                   /* 1: (Leaky)ReLU with `slope` after the affine transform */
+  int32_t training;
+  float slope, eps, momentum;
+  const void* x;                 /* raw input (kept by the caller for backward) */
+  void* y;                       /* output; with act != 0 it must be bf16 (backward reads the mask from it) */
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  float* save;
+  float* scratch;
+  const void* dy;
+  void* dx;
+  float* dgamma;
+  float* dbeta;
+} bvae_bn_desc;
+int bvae_bn_scratch_floats(int C);
+int bvae_bn_forward(const bvae_bn_desc* d, void* stream);
+int bvae_bn_backward(const bvae_bn_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,16 @@ class NbDesc(C.Structure):
                 ("bwd_nc", c_vp), ("bwd_px", c_vp), ("bwd_h", c_vp)]
 
 
+class BnDesc(C.Structure):
+    """struct bvae_bn_desc."""
+    _fields_ = [("P", c_i64),
+                ("C", c_i32), ("x_pitch", c_i32), ("y_pitch", c_i32), ("dy_pitch", c_i32), ("dx_pitch", c_i32),
+                ("x_f32", c_i32), ("y_f32", c_i32), ("dy_f32", c_i32), ("act", c_i32), ("training", c_i32),
+                ("slope", c_f32), ("eps", c_f32), ("momentum", c_f32),
+                ("x", c_vp), ("y", c_vp), ("gamma", c_vp), ("beta", c_vp), ("running_mean", c_vp), ("running_var", c_vp),
+                ("save", c_vp), ("scratch", c_vp), ("dy", c_vp), ("dx", c_vp), ("dgamma", c_vp), ("dbeta", c_vp)]
+
+
 class PackJob(C.Structure):
     """mirror of bvae_pack_job (include/barvae.h)"""
     _fields_ = [("src", c_vp), ("dst", c_vp), ("R", c_i32), ("T", c_i32), ("Cc", c_i32), ("dst_pitch", c_i32),
@@ -100,6 +110,9 @@ SYMBOLS = [
     ("bvae_f32_to_bf16", C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     ("bvae_unpack_bits", C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     ("bvae_threshold_pack", C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),
+    ("bvae_bn_scratch_floats", C.c_int, [C.c_int]),
+    ("bvae_bn_forward", C.c_int, [C.POINTER(BnDesc), c_vp]),
+    ("bvae_bn_backward", C.c_int, [C.POINTER(BnDesc), c_vp]),
 ]
 
 

@@ -110,13 +110,15 @@ class BarGen(object):
         torch.cuda.manual_seed_all(self.manual_seed)
         random.seed(self.manual_seed)
 
-        self.generator = Model(vae_head=getattr(config, "vae_head", False)).to(self.device)
+        self.generator = Model(vae_head=getattr(config, "vae_head", False),
+                               refiner=getattr(config, "refiner", False)).to(self.device)
         flat = self.generator.flatten_parameters()
         self.reducer = None
         if self.world > 1:
             self.reducer = parallel.GradReducer.for_model(self.generator, flat, getattr(config, "bucket_mb", 64))
         self.lr_gen1 = config.learning_rate
-        self.opt_gen1 = GeneratorTrainer(self.generator, lr=self.lr_gen1, reducer=self.reducer)
+        self.opt_gen1 = GeneratorTrainer(self.generator, lr=self.lr_gen1, reducer=self.reducer,
+                                         micro_bars=getattr(config, "micro_bars", 0))
         self.scheduler_gen1 = _Plateau(factor=0.8, cooldown=6)
         self.iteration = 0
         self.epoch = 0
@@ -174,7 +176,8 @@ class BarGen(object):
                 print("No checkpoint exists from '{}'. Skipping...".format(self._ckpt_dir()))
             return
         sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["generator_state_dict"].items()}
-        sd = {k: v for k, v in sd.items() if not k.startswith("refiner.")}       # the reference's Refiner is not built
+        own = self.generator.state_dict()       # refiner.* only into Model(refiner=True) and only where shapes agree
+        sd = {k: v for k, v in sd.items() if not k.startswith("refiner.") or (k in own and tuple(own[k].shape) == tuple(v.shape))}
         self.generator.load_state_dict(sd, strict=False)
         opt = ck.get("gen_optimizer1")
         if isinstance(opt, dict) and ("exp_avg" in opt or "param_groups" in opt):   # ours, or torch.optim.Adam's (reference)

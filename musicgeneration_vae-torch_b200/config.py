@@ -28,4 +28,6 @@ class Config(object):
     packed_array_path = None  # directory of flat memory-mappable bit arrays (tools/pack_dataset.py --arrays); wins if it exists
     packed_data_path = None   # directory of bit-packed .npz items (tools/pack_dataset.py); used when it exists
     packed_input = False   # loader emits bit-packed batches (data/packed.py): 32x less host->device traffic
+    refiner = False        # graph/refiner.py with the one-line shape fix applied after the decoder (graph/model.py:31,41)
+    micro_bars = 0         # > 0: steps over more bars run as gradient-accumulated chunks of this size (trainer.py)
     synthetic = False      # explicit opt-in: train on random SyntheticBars when no dataset directory exists (smoke runs)

@@ -24,6 +24,9 @@ class _BCEFn(torch.autograd.Function):
                                            _lib.stream_ptr()), "bce_fwd")
         ctx.save_for_backward(p, t)
         ctx.smoothing, ctx.shape = int(smoothing), probs.shape
+        ctx.parts = with_count == 2
+        if ctx.parts:                        # [BCE mean, missed-note count] (micro-batched steps weight them differently)
+            return acc
         return acc[0] + acc[1] * 0.005 if with_count else acc[0]
 
     @staticmethod
@@ -32,12 +35,19 @@ class _BCEFn(torch.autograd.Function):
         d = torch.empty_like(p)
         _lib.check(_lib.lib().bvae_bce_bwd(p.data_ptr(), t.data_ptr(), p.numel(), ctx.smoothing, 1.0 / p.numel(),
                                            d.data_ptr(), _lib.stream_ptr()), "bce_bwd")
+        if ctx.parts:
+            g = g[0]                         # the count is not differentiable (graph/loss/bar_loss.py:31-32)
         return (d * g).view(ctx.shape), None, None, None
 
 
 class Loss(nn.Module):
     def forward(self, logits, labels, is_pretraining=False):
         return _BCEFn.apply(logits, labels, not is_pretraining, True)
+
+    def parts(self, logits, labels, is_pretraining=False):
+        """(BCE mean, missed-note count) of the same single-pass kernel: ``forward`` == parts[0] + 0.005 * parts[1]"""
+        acc = _BCEFn.apply(logits, labels, not is_pretraining, 2)
+        return acc[0], acc[1]
 
 
 class DLoss(nn.Module):

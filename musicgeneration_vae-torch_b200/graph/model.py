@@ -94,11 +94,18 @@ def _cat_bars(note, pre_note):
 
 
 class Model(nn.Module):
-    def __init__(self, vae_head: bool = False):
+    def __init__(self, vae_head: bool = False, refiner: bool = False):
         super().__init__()
         self.encoder = Encoder([64, 128, 256, 512, 1024])
         self.decoder = Decoder([1024, 512, 256, 128, 64])
         self.phrase_encoder = PhraseModel([64, 128, 256, 512, 1024])
+        # graph/model.py:18,31,41 applies a Refiner to the generated bar in both branches, but the reference's Refiner
+        # cannot execute (graph/refiner.py:12 vs :19); ``refiner=True`` adds it WITH the one-line shape fix (see
+        # graph/refiner.py here).  Off by default == the reference's runnable composition graph/model_with_gan.py.
+        self.refiner = None
+        if refiner:
+            from .refiner import Refiner
+            self.refiner = Refiner()
         self.vae_head = vae_head
         if vae_head:
             # log-variance head next to the mean head (= encoder.linear), as `var` sits next to `mean` in
@@ -169,8 +176,11 @@ class Model(nn.Module):
                 return recon, mu, logvar
             self._join_phrase()
             gen_note = self.decoder(z, pre_z, phrase_feature, position, dropout_masks)
+            if self.refiner is not None:
+                gen_note = self.refiner(gen_note)                       # graph/model.py:31
             return gen_note, z, pre_z, phrase_feature
         phrase_feature = self._phrase_branch(phrase)
         pre_z = self.encoder(pre_note)
         self._join_phrase()
-        return self.decoder(note, pre_z, phrase_feature, position, dropout_masks)
+        gen_note = self.decoder(note, pre_z, phrase_feature, position, dropout_masks)
+        return gen_note if self.refiner is None else self.refiner(gen_note)   # graph/model.py:41

@@ -26,6 +26,8 @@ def sample_songs(model, latents, music_length, return_first_probs=False, thresho
         for _ in range(4):
             pre_z = model.encoder(pre_bar)
             probs = model.decoder(latents[k], pre_z, phrase_feature, pos)
+            if getattr(model, "refiner", None) is not None:
+                probs = model.refiner(probs)                             # graph/model.py:41 (Model(refiner=True))
             if first is None:
                 first = probs.clone()
             pre_bar = (probs > threshold).float()                        # maker_bar.py:39
@@ -51,7 +53,11 @@ def load_generator(model, filename, device="cuda"):
     reference's Refiner entries are ignored (graph/refiner.py cannot execute)."""
     ck = torch.load(filename, map_location=device, weights_only=False)
     sd = {(k[len("module."):] if k.startswith("module.") else k): v for k, v in ck["generator_state_dict"].items()}
-    model.load_state_dict({k: v for k, v in sd.items() if not k.startswith("refiner.")}, strict=False)
+    own = model.state_dict()
+    # Refiner entries load only into Model(refiner=True), and only where the shapes agree: the reference's
+    # refiner.layer2.0.weight [8,1,4,4] IS its defect (graph/refiner.py:19)
+    sd = {k: v for k, v in sd.items() if not k.startswith("refiner.") or (k in own and tuple(own[k].shape) == tuple(v.shape))}
+    model.load_state_dict(sd, strict=False)
     return model
 
 

@@ -73,6 +73,7 @@ class GradReducer:
         self.comm_stream = torch.cuda.Stream() if flat.grad.is_cuda else None
         self._pending = []
         self._finishing = False
+        self.hold = False          # gradient accumulation: True while more backward passes of this step are to come
 
     @staticmethod
     def for_model(model, flat, bucket_mb: int = 64, group=None, overlap: bool = True) -> "GradReducer":
@@ -83,6 +84,11 @@ class GradReducer:
             b = min(p._bvae_off for p in ps)
             e = max(-(-(p._bvae_off + p.numel()) // flat.ALIGN) * flat.ALIGN for p in ps)
             segs.append((name, b, e))
+        ref = getattr(model, "refiner", None)
+        if ref is not None:                        # Model(refiner=True): no backward hook, reduced by finish()
+            ps = list(ref.parameters())
+            segs.append(("refiner", min(p._bvae_off for p in ps),
+                         max(-(-(p._bvae_off + p.numel()) // flat.ALIGN) * flat.ALIGN for p in ps)))
         r = GradReducer(flat, segs, bucket_mb, group, overlap)
         for name in ("encoder", "decoder"):
             getattr(model, name)._bvae_on_bwd_done = (lambda n=name: r.segment_ready(n))
@@ -122,7 +128,7 @@ class GradReducer:
         """Called right after a module's backward kernels were enqueued: all-reduce its gradient slice.
         With overlap=False (a module runs several backward passes per step, e.g. the GAN schedules) nothing happens
         here and finish() reduces everything."""
-        if self.world == 1 or (not self.overlap and not self._finishing):
+        if self.world == 1 or ((not self.overlap or self.hold) and not self._finishing):
             return
         if name in self._pending:
             raise RuntimeError("gradient segment %r was completed twice in one step; build the reducer with "

@@ -23,7 +23,7 @@ def test_struct_layouts_match_header(tmp_path):
     import subprocess
     lib = pkg("_lib")
     structs = {"bvae_conv_desc": lib.ConvDesc, "bvae_wgrad_desc": lib.WgradDesc, "bvae_nb_desc": lib.NbDesc,
-               "bvae_pack_job": lib.PackJob}
+               "bvae_pack_job": lib.PackJob, "bvae_bn_desc": lib.BnDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "barvae.h"', 'int main(void){']
     for cname, cls in structs.items():
         lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))

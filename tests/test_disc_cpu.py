@@ -69,3 +69,52 @@ def test_discriminator_mirrors_keep_reference_keys_and_refuse_cpu():
     assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == list(D.feature_disc_spec().items())
     G = pkg("graph.model_with_gan").Model()
     assert list(G.state_dict().keys()) == list(D.O.generator_spec().keys())
+
+
+@pytest.fixture(scope="module")
+def gc():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_conv_disc_v1.pt"), map_location="cpu", weights_only=False)
+
+
+def _run_conv(fwd, spec, seed, kind, x, training, D, target_ones):
+    sd = D.make_conv_state_dict(spec, seed, kind)
+    leaves = OrderedDict((k, (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()))
+                         for k, v in sd.items())
+    x = x.clone().requires_grad_(True)
+    out = fwd(x, leaves, training)
+    if target_ones:
+        loss = F.binary_cross_entropy(out, torch.ones_like(out))
+    else:
+        loss = (out * torch.linspace(0.5, 1.5, out.numel()).view_as(out)).mean()
+    loss.backward()
+    return out.detach(), loss.detach(), x.grad, leaves
+
+
+@pytest.mark.parametrize("net", ["bar_disc", "refiner"])
+@pytest.mark.parametrize("kind,seed", [("lively", 0), ("reference", 1)])
+@pytest.mark.parametrize("training", [True, False])
+def test_conv_disc_and_refiner_oracle_vs_reference_golden(gc, net, kind, seed, training):
+    """oracle/disc_oracle.py bar_disc_forward / refiner_forward against the reference's BarDiscriminator (unmodified) and its
+    Refiner with the in-memory layer2 fix (oracle/gen_golden_conv_disc.py): outputs, loss, input gradient, every parameter
+    gradient and the BatchNorm buffers after the call, in training (batch statistics) and eval (running statistics) mode."""
+    import disc_oracle as D
+    if net == "bar_disc":
+        spec, fwd, x, seed = D.bar_disc_spec(), D.bar_disc_forward, gc["disc_x"], 7 + seed
+    else:
+        spec, fwd, x, seed = D.refiner_spec(), D.refiner_forward, gc["refiner_x"], 9 + seed
+    out, loss, dx, leaves = _run_conv(fwd, spec, seed, kind, x, training, D, net == "bar_disc")
+    want = gc["%s/%s/%s" % (net, kind, "train" if training else "eval")]
+    assert torch.allclose(out, want["out"], rtol=2e-4, atol=1e-5), float((out - want["out"]).abs().max())
+    assert torch.allclose(loss, want["loss"], rtol=2e-4, atol=1e-6)
+    tol = lambda w: dict(rtol=2e-3, atol=2e-4 * float(w.abs().max() + 1e-30))
+    assert torch.allclose(dx, want["dx"], **tol(want["dx"]))
+    for k, w in want["grads"].items():
+        if w is None:
+            assert leaves[k].grad is None, k
+        else:
+            assert torch.allclose(leaves[k].grad, w, **tol(w)), (k, float((leaves[k].grad - w).abs().max()), float(w.abs().max()))
+    dg = __import__("barvae_oracle").grad_digest(OrderedDict((k, leaves[k].grad) for k in want["grad_digest"]))
+    for k, w in want["grad_digest"].items():                                  # the tensors too large to store whole
+        assert torch.allclose(dg[k], w, rtol=2e-3, atol=2e-4 * float(w.abs().max() + 1e-30)), k
+    for k, w in want["buffers_after"].items():
+        assert torch.allclose(leaves[k].float(), w.float(), rtol=1e-4, atol=1e-5), k

@@ -1,0 +1,112 @@
+"""GPU: the convolutional BarDiscriminator (graph/bar_discriminator.py) and the Refiner (graph/refiner.py, with the layer2
+fix) through libbarvae.so -- bvae_conv_gemm / bvae_wgrad_gemm + bvae_bn_forward / bvae_bn_backward -- against the CPU oracle
+(oracle/disc_oracle.py, pinned to the reference classes' own outputs by tests/test_disc_cpu.py) and against the committed
+reference goldens directly.
+Arithmetic: bf16 GEMM operands / stored activations, fp32 accumulation, fp32 raw conv outputs in front of every BatchNorm,
+fp32 statistics.  Tolerances ("lively" weights): output probability |err| <= 2e-2, loss 2e-2 rel, input gradient and every
+parameter gradient <= 6e-2 rel-Frobenius (measured values go to gpurun_out/parity_report.jsonl; 8-16 bf16 layers deep);
+BatchNorm running statistics after the call 2e-3.  Reference-init weights (N(-1,1) everywhere, BatchNorm gammas included):
+forward only."""
+import os
+from collections import OrderedDict
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import ROOT, pkg, rel_fro, report
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gc():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "golden_conv_disc_v1.pt"), map_location="cpu", weights_only=False)
+
+
+def _oracle(fwd, sd, x, training, ones):
+    leaves = OrderedDict((k, (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()))
+                         for k, v in sd.items())
+    x = x.clone().requires_grad_(True)
+    out = fwd(x, leaves, training)
+    loss = F.binary_cross_entropy(out, torch.ones_like(out)) if ones else \
+        (out * torch.linspace(0.5, 1.5, out.numel()).view_as(out)).mean()
+    loss.backward()
+    return out.detach(), float(loss), x.grad, leaves
+
+
+@pytest.mark.parametrize("net", ["bar_disc", "refiner"])
+@pytest.mark.parametrize("training", [True, False])
+def test_conv_nets_forward_backward_vs_oracle(gc, net, training):
+    import disc_oracle as D
+    if net == "bar_disc":
+        cls, spec, fwd, x, seed = pkg("graph.bar_discriminator").BarDiscriminator, D.bar_disc_spec(), D.bar_disc_forward, gc["disc_x"], 7
+    else:
+        cls, spec, fwd, x, seed = pkg("graph.refiner").Refiner, D.refiner_spec(), D.refiner_forward, gc["refiner_x"], 9
+    sd = D.make_conv_state_dict(spec, seed, "lively")
+    want_out, want_loss, want_dx, leaves = _oracle(fwd, sd, x, training, net == "bar_disc")
+    gold = gc["%s/lively/%s" % (net, "train" if training else "eval")]
+    m = cls()
+    assert list(m.state_dict().keys()) == list(spec.keys())                 # the reference's parameter AND buffer names
+    m.load_state_dict(sd)
+    m = m.cuda().train(training)
+    xg = x.cuda().requires_grad_(True)
+    out = m(xg)
+    if net == "bar_disc":
+        loss = pkg("graph.loss.bar_loss").DLoss()(out, torch.ones_like(out))
+    else:
+        loss = (out * torch.linspace(0.5, 1.5, out.numel(), device="cuda").view_as(out)).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    errs = {"out_maxabs": float((out.detach().cpu() - want_out).abs().max()),
+            "out_vs_reference_golden": float((out.detach().cpu() - gold["out"]).abs().max()),
+            "loss_rel": abs(float(loss) - want_loss) / abs(want_loss), "dx": rel_fro(xg.grad, want_dx)}
+    worst = 0.0
+    for k, p in m.named_parameters():
+        if leaves[k].grad is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k    # ConvModule.bn1 of the isBasic block: unused
+            continue
+        errs[k] = rel_fro(p.grad, leaves[k].grad)
+        worst = max(worst, errs[k])
+    bufs = {k: v for k, v in m.state_dict().items() if "running" in k}
+    berr = max(float((v.cpu() - leaves[k]).abs().max() / (leaves[k].abs().max() + 1e-6)) for k, v in bufs.items())
+    nbt = all(int(v) == int(leaves[k]) for k, v in m.state_dict().items() if "tracked" in k)
+    report(test="conv_net", net=net, training=training, out_maxabs=errs["out_maxabs"], out_vs_golden=errs["out_vs_reference_golden"],
+           loss_rel=errs["loss_rel"], dx=errs["dx"], worst_param_grad=worst, running_stats=berr)
+    assert errs["out_maxabs"] < 2e-2 and errs["out_vs_reference_golden"] < 2e-2 and errs["loss_rel"] < 2e-2, errs
+    assert errs["dx"] < 6e-2 and worst < 6e-2, {k: v for k, v in errs.items() if isinstance(v, float) and v > 3e-2}
+    assert berr < 2e-3 and nbt, berr
+
+
+@pytest.mark.parametrize("net", ["bar_disc", "refiner"])
+def test_conv_nets_reference_init_forward(gc, net):
+    import disc_oracle as D
+    if net == "bar_disc":
+        cls, spec, x, seed = pkg("graph.bar_discriminator").BarDiscriminator, D.bar_disc_spec(), gc["disc_x"], 8
+    else:
+        cls, spec, x, seed = pkg("graph.refiner").Refiner, D.refiner_spec(), gc["refiner_x"], 10
+    for training in (True, False):
+        m = cls()
+        m.load_state_dict(D.make_conv_state_dict(spec, seed, "reference"))
+        m = m.cuda().train(training)
+        with torch.no_grad():
+            out = m(x.cuda())
+        want = gc["%s/reference/%s" % (net, "train" if training else "eval")]["out"]
+        e = float((out.cpu() - want).abs().max())
+        report(test="conv_net_reference_init", net=net, training=training, out_maxabs=e)
+        assert e < 3e-2, (net, training, e)
+
+
+def test_frozen_discriminator_still_propagates_input_gradient(gc):
+    """agent/barGen_with_gan.py:506-528: the generator step runs the discriminator with requires_grad=False on all of its
+    parameters and backpropagates into the generated bar"""
+    import disc_oracle as D
+    m = pkg("graph.bar_discriminator").BarDiscriminator()
+    m.load_state_dict(D.make_conv_state_dict(D.bar_disc_spec(), 7, "lively"))
+    m = m.cuda().train()
+    for p in m.parameters():
+        p.requires_grad = False
+    x = gc["disc_x"].cuda().requires_grad_(True)
+    F.binary_cross_entropy(m(x), torch.ones(5, 1, device="cuda")).backward()
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0
+    assert all(p.grad is None for p in m.parameters())
