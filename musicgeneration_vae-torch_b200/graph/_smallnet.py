@@ -20,13 +20,13 @@ from .encodingBlock import gemm_of
 
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, layer, act, slope, out_f32, use_bias, *params):
+    def forward(ctx, x, layer, act, slope, out_f32, use_bias, bias_grad, *params):
         N, H, W, Cin = x.shape
         xa = Act(x.detach(), N, H, W, Cin)
         oh, ow = layer.out_hw(H, W)
         y = Act.empty(N, oh, ow, layer.Cout, dtype=torch.float32 if out_f32 else BF16, device=x.device)
         layer.forward(xa, y, act=act, slope=slope, use_bias=use_bias)
-        ctx.layer, ctx.act, ctx.slope, ctx.use_bias = layer, act, slope, use_bias
+        ctx.layer, ctx.act, ctx.slope, ctx.use_bias, ctx.bias_grad = layer, act, slope, use_bias, bias_grad
         ctx.save_for_backward(x.detach(), y.t if act else None)
         return y.t
 
@@ -42,24 +42,29 @@ class _ConvFn(torch.autograd.Function):
         dya = Act(d, d.shape[0], d.shape[1], d.shape[2], d.shape[3])
         xa = Act(x, N, H, W, Cin)
         layer.wgrad(xa, dya)
-        if ctx.use_bias:
+        if ctx.use_bias and ctx.bias_grad:
             layer.bias_grad(dya)
+        elif ctx.use_bias:
+            layer.zero_bias_grad()      # bias in front of a batch-statistics norm: the gradient is analytically zero
         dx = None
         if ctx.needs_input_grad[0]:
             dxa = Act.empty(N, H, W, Cin, device=x.device)
             layer.dgrad(dya, dxa)
             dx = dxa.t
-        return (dx, None, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 6)
+        return (dx, None, None, None, None, None, None) + (None,) * (len(ctx.needs_input_grad) - 7)
 
 
-def conv(x, module, act=False, slope=0.0, out_f32=True, use_bias=True):
+def conv(x, module, act=False, slope=0.0, out_f32=True, use_bias=True, bias_grad=True):
     """x: [N,H,W,Cin] (any float dtype; stored as bf16 for the GEMM).  Returns [N,OH,OW,Cout] fp32 (raw output in front
-    of a BatchNorm) or bf16 (with the activation fused in the epilogue)."""
+    of a BatchNorm) or bf16 (with the activation fused in the epilogue).  ``bias_grad=False``: the bias feeds a BatchNorm
+    running on batch statistics, which removes any per-channel constant -- its gradient is exactly zero (the reference
+    yields ~1e-9 of fp32 noise there; summing the bf16-stored BatchNorm gradient would give 1e-2 of rounding noise, which
+    Adam's normalisation would turn into a random walk of the bias)."""
     if not x.is_cuda:
         raise RuntimeError("the B200 path needs CUDA tensors; there is no CPU fallback")
     layer = gemm_of(module)
     params = [p for p in (module.weight, module.bias) if p is not None]
-    return _ConvFn.apply(x.to(BF16).contiguous(), layer, act, slope, out_f32, use_bias, *params)
+    return _ConvFn.apply(x.to(BF16).contiguous(), layer, act, slope, out_f32, use_bias, bias_grad, *params)
 
 
 def linear(x, module, act=False):

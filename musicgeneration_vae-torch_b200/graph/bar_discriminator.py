@@ -1,7 +1,7 @@
 """Convolutional piano-roll discriminator of the adversarial phase (reference: graph/bar_discriminator.py:7-217): three
 feature towers over the two-bar roll ``cat((pre_note, note), dim=2)`` [B,1,192,60] -- chord (pitch classes summed over
 octaves), on/off (per-step note count) and a generic tower -- each ending in a 64-vector, concatenated into one logit.
-Same sub-module / parameter / buffer names as the reference (state_dict interchangeable, 112 keys).  Convolutions run
+Same sub-module / parameter / buffer names as the reference (state_dict interchangeable: 87 keys, BatchNorm buffers included).  Convolutions run
 through bvae_conv_gemm / bvae_wgrad_gemm, every nn.BatchNorm2d (batch statistics of THIS rank in training mode, as the
 reference: no SyncBN) through bvae_bn_forward / bvae_bn_backward (graph/_smallnet.py).
 

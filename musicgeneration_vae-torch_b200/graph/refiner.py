@@ -40,8 +40,9 @@ class Refiner(nn.Module):
             raise RuntimeError("the B200 path needs CUDA tensors; there is no CPU fallback")
         B = x.shape[0]
         xh = x.reshape(B, 96, 60, 1)
-        x_2 = self._pool(batch_norm(conv(xh, self.layer1[0]), self.layer1[1], act=True, slope=0.2))       # [B,48,30,2]
-        x_8 = self._pool(batch_norm(conv(x_2, self.layer2[0]), self.layer2[1], act=True, slope=0.2))      # [B,24,15,8]
+        bg = not self.layer1[1].training        # conv biases in front of a batch-statistics BatchNorm: zero gradient
+        x_2 = self._pool(batch_norm(conv(xh, self.layer1[0], bias_grad=bg), self.layer1[1], act=True, slope=0.2))   # [B,48,30,2]
+        x_8 = self._pool(batch_norm(conv(x_2, self.layer2[0], bias_grad=bg), self.layer2[1], act=True, slope=0.2))  # [B,24,15,8]
         flat = x_8.permute(0, 3, 1, 2).reshape(B, 2880)         # the reference flattens NCHW (:52)
         f = linear(linear(flat, self.layer3[0], act=True), self.layer4[0], act=True)
         x_8_t = x_8.float() + f.float().view(B, 8, 24, 15).permute(0, 2, 3, 1)

@@ -169,55 +169,68 @@ def batch_norm(x, sd, p, training, momentum, eps=1e-5):
                         momentum, eps)
 
 
-def bar_disc_forward(x, sd, training=True):
+class _Ident:
+    """precision policy of the fp32 oracle: nothing is rounded.  tests/test_gpu_convdisc.py passes barvae_emul's q / gq / wq
+    (value+gradient, gradient-only, value-only bf16 rounding) to evaluate the SAME functions at the CUDA path's storage
+    precision: bf16 GEMM operands and stored activations, fp32 raw conv outputs in front of a BatchNorm, bf16 gradients."""
+    q = gq = wq = staticmethod(lambda t: t)
+
+
+def bar_disc_forward(x, sd, training=True, prec=_Ident):
     """graph/bar_discriminator.py:199-217.  Note OnOffFeature.forward (:84-85): ``x[:, :-1]`` slices the CHANNEL axis of a
     one-channel tensor (empty) and the pad restores one channel of zeros, so ``x - onoff_x`` is x itself: the on/off
     feature is the per-step sum over pitches (replicated, not repaired)."""
+    q, gq, wq = prec.q, prec.gq, prec.wq
     x = x.view(-1, 1, 192, 60)
-    bn = lambda t, p, m: batch_norm(t, sd, p, training, m)
+    bn = lambda t, p, m: q(F.relu(batch_norm(gq(t), sd, p, training, m)))            # raw conv output fp32 -> BN+ReLU -> bf16
+    cv = lambda t, k, **kw: F.conv2d(t, wq(sd[k]), **kw)
+    rl = lambda t: q(F.relu(t))                                                      # ReLU fused in the conv epilogue -> bf16
     # ChordFeature :29-58
-    c = x.view(-1, 1, 192, 12, 5).sum(4, keepdim=True).view(-1, 1, 192, 12)
-    c = F.relu(bn(F.conv2d(c, sd["chord.chord_conv1.weight"], stride=(2, 1), padding=(1, 0)), "chord.batch_norm1.", 0.01))
-    c = F.relu(bn(F.conv2d(c, sd["chord.chord_conv2.weight"], stride=(2, 1), padding=(1, 0)), "chord.batch_norm2.", 0.01))
-    c = F.relu(bn(F.conv2d(c, sd["chord.chord_fit.weight"]), "chord.batch_norm3.", 0.01))
-    c = F.relu(bn(F.conv2d(c, sd["chord.chord_conv3.weight"], stride=2, padding=1), "chord.batch_norm4.", 0.01))
-    c = F.relu(bn(F.conv2d(c, sd["chord.chord_conv4.weight"], stride=2, padding=1), "chord.batch_norm5.", 0.01))
+    c = q(x.view(-1, 1, 192, 12, 5).sum(4, keepdim=True).view(-1, 1, 192, 12))
+    c = bn(cv(c, "chord.chord_conv1.weight", stride=(2, 1), padding=(1, 0)), "chord.batch_norm1.", 0.01)
+    c = bn(cv(c, "chord.chord_conv2.weight", stride=(2, 1), padding=(1, 0)), "chord.batch_norm2.", 0.01)
+    c = bn(cv(c, "chord.chord_fit.weight"), "chord.batch_norm3.", 0.01)
+    c = bn(cv(c, "chord.chord_conv3.weight", stride=2, padding=1), "chord.batch_norm4.", 0.01)
+    c = bn(cv(c, "chord.chord_conv4.weight", stride=2, padding=1), "chord.batch_norm5.", 0.01)
     c = F.avg_pool2d(c, (12, 3))
     # OnOffFeature :83-100
     shifted = F.pad(x[:, :-1], (0, 0, 0, 0, 1, 0))
-    o = torch.sum(x - shifted, 3, keepdim=True)
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_conv1.weight"], stride=(2, 1), padding=1))
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_conv2.weight"], stride=(2, 1), padding=1))
-    o = bn(o, "onoff.batch_norm2.", 0.1)
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_conv3.weight"], stride=(2, 1), padding=1))
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_conv4.weight"], stride=(2, 1), padding=1))
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_fit.weight"]))
-    o = F.relu(F.conv2d(o, sd["onoff.onoff_conv5.weight"], stride=(2, 1), padding=1))
+    o = q(torch.sum(x - shifted, 3, keepdim=True))
+    o = rl(cv(o, "onoff.onoff_conv1.weight", stride=(2, 1), padding=1))
+    o = rl(cv(o, "onoff.onoff_conv2.weight", stride=(2, 1), padding=1))
+    o = q(batch_norm(o, sd, "onoff.batch_norm2.", training, 0.1))
+    o = rl(cv(o, "onoff.onoff_conv3.weight", stride=(2, 1), padding=1))
+    o = rl(cv(o, "onoff.onoff_conv4.weight", stride=(2, 1), padding=1))
+    o = rl(cv(o, "onoff.onoff_fit.weight"))
+    o = rl(cv(o, "onoff.onoff_conv5.weight", stride=(2, 1), padding=1))
     o = F.avg_pool2d(o, (6, 1))
     # BasicFeature :163-183
-    pitch = F.relu(F.conv2d(x, sd["basic.pitch1.weight"], stride=(1, 2), padding=(0, 1)))
-    pitch = F.relu(F.conv2d(pitch, sd["basic.pitch2.weight"], stride=(2, 1), padding=(1, 0)))
-    time = F.relu(F.conv2d(x, sd["basic.time1.weight"], stride=(2, 1), padding=(1, 0)))
-    time = F.relu(F.conv2d(time, sd["basic.time2.weight"], stride=(1, 2), padding=(0, 1)))
+    xq = q(x)
+    pitch = rl(cv(xq, "basic.pitch1.weight", stride=(1, 2), padding=(0, 1)))
+    pitch = rl(cv(pitch, "basic.pitch2.weight", stride=(2, 1), padding=(1, 0)))
+    time = rl(cv(xq, "basic.time1.weight", stride=(2, 1), padding=(1, 0)))
+    time = rl(cv(time, "basic.time2.weight", stride=(1, 2), padding=(0, 1)))
     b = torch.cat((pitch, time), 1)
-    b = F.relu(bn(F.conv2d(b, sd["basic.fit.weight"]), "basic.bn.", 0.01))
+    b = bn(cv(b, "basic.fit.weight"), "basic.bn.", 0.01)
     for i, basic in enumerate((False, False, True)):                        # ConvModule.forward :122-134
-        q = "basic.layers.%d." % i
+        p = "basic.layers.%d." % i
         if not basic:
-            b = F.relu(bn(F.conv2d(b, sd[q + "conv1.weight"], padding=1), q + "bn1.", 0.01))
-        b = F.relu(bn(F.conv2d(b, sd[q + "conv2.weight"], stride=2, padding=1), q + "bn2.", 0.01))
+            b = bn(cv(b, p + "conv1.weight", padding=1), p + "bn1.", 0.01)
+        b = bn(cv(b, p + "conv2.weight", stride=2, padding=1), p + "bn2.", 0.01)
     b = F.avg_pool2d(b, (12, 4))
     out = torch.cat((c, o, b), 1).view(-1, 192)
     return torch.sigmoid(F.linear(out, sd["linear.weight"]))
 
 
-def refiner_forward(x, sd, training=True):
+def refiner_forward(x, sd, training=True, prec=_Ident):
     """graph/refiner.py:49-58 (with the layer2 fix of refiner_spec)"""
-    bn = lambda t, p: batch_norm(t, sd, p, training, 0.1)
-    x2 = F.max_pool2d(F.leaky_relu(bn(F.conv2d(x, sd["layer1.0.weight"], sd["layer1.0.bias"], padding=2), "layer1.1."), 0.2), 2)
-    x8 = F.max_pool2d(F.leaky_relu(bn(F.conv2d(x2, sd["layer2.0.weight"], sd["layer2.0.bias"], padding=2), "layer2.1."), 0.2), 2)
-    f = F.relu(F.linear(x8.reshape(-1, 2880), sd["layer3.0.weight"], sd["layer3.0.bias"]))
-    f = F.relu(F.linear(f, sd["layer4.0.weight"], sd["layer4.0.bias"]))
+    q, gq, wq = prec.q, prec.gq, prec.wq
+    bn = lambda t, p: batch_norm(gq(t), sd, p, training, 0.1)
+    x2 = F.max_pool2d(q(F.leaky_relu(bn(F.conv2d(q(x), wq(sd["layer1.0.weight"]), sd["layer1.0.bias"], padding=2), "layer1.1."), 0.2)), 2)
+    x8 = F.max_pool2d(q(F.leaky_relu(bn(F.conv2d(x2, wq(sd["layer2.0.weight"]), sd["layer2.0.bias"], padding=2), "layer2.1."), 0.2)), 2)
+    f = q(F.relu(F.linear(x8.reshape(-1, 2880), wq(sd["layer3.0.weight"]), sd["layer3.0.bias"])))
+    f = q(F.relu(F.linear(f, wq(sd["layer4.0.weight"]), sd["layer4.0.bias"])))
     x8t = x8 + f.view(-1, 8, 24, 15)
-    x2t = x2 + F.relu(bn(F.conv_transpose2d(x8t, sd["layer5.0.weight"], stride=2, padding=1), "layer5.1."))
-    return (x + torch.sigmoid(bn(F.conv_transpose2d(x2t, sd["layer6.0.weight"], stride=2, padding=1), "layer6.1."))) * 0.5
+    x2t = x2 + q(F.relu(bn(F.conv_transpose2d(q(x8t), wq(sd["layer5.0.weight"]), stride=2, padding=1), "layer5.1.")))
+    y = q(bn(F.conv_transpose2d(q(x2t), wq(sd["layer6.0.weight"]), stride=2, padding=1), "layer6.1."))
+    return (x + torch.sigmoid(y)) * 0.5
