@@ -254,6 +254,70 @@ def ncu_traffic_table():
     return {}, None
 
 
+def gan_bench(args, pkg, dev, rank, world):
+    """BASELINE configs[3]: the adversarial step of agent/barGen_with_gan.py on N GPUs -- per iteration a discriminator
+    step (generator frozen: forward only, incl. the re-encode of the thresholded bar) + a generator step, for both phases:
+    train_wae (z discriminators; generator step = BCE + 3 adversarial terms) and train_gan (conv BarDiscriminator + feature
+    discriminator; generator step from noise).  Whole-job bars/s = bars per iteration / time per iteration."""
+    import torch
+    import torch.distributed as dist
+    Config = importlib.import_module(PKG + ".config").Config
+    G = importlib.import_module(PKG + ".agent.barGen_with_gan")
+    SyntheticBars = importlib.import_module(PKG + ".data.bar_dataset").SyntheticBars
+    import tempfile
+
+    class Cfg(Config):
+        root_path = tempfile.mkdtemp(prefix="bvae_gan_bench_")
+        batch_size = 1
+        pretraining_step_size = 0
+
+    agent = G.BarGen(Cfg(), dataset=SyntheticBars(world, 1, 1))
+    B = args.batch
+    batch = synthetic_batch(B, 1234 + rank, dev)
+    valid, fake = torch.ones(B, device=dev), torch.zeros(B, device=dev)
+    sink = lambda loss: None
+    agent.epoch = 1
+
+    def it_wae():
+        agent.train_wae(*batch, sink, sink, sink, fake, valid, 0)       # (epoch + curr_it) % 2 == 1: discriminator step too
+
+    def it_gan():
+        agent.train_gan(*batch, sink, sink, sink, fake, valid, 0)
+
+    out = {}
+    for name, fn in (("wae", it_wae), ("gan", it_gan)):
+        for _ in range(max(2, args.warmup)):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n0 = pkg.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        out[name] = {"ms_per_iteration": ms, "bars_per_sec": B * world / (ms * 1e-3),
+                     "gpu_launches_per_iteration": (pkg.launch_count() - n0) / args.steps}
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    emit({"metric": "gan_step_bars_per_sec", "value": out["gan"]["bars_per_sec"], "unit": "bars/s", "n_gpus": world,
+          "steps": args.steps, "warmup": max(2, args.warmup), "ms_per_step": out["gan"]["ms_per_iteration"],
+          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+          "config": {"workload": "barGen_with_gan adversarial iteration (discriminator step + generator step), %d bars/GPU, "
+                                 "reference-init weights; value = train_gan phase, extra.wae = train_wae phase" % B,
+                     "bars_per_gpu": B, "parallelism": "dp%d" % world},
+          "gpu_launches": int(out["gan"]["gpu_launches_per_iteration"] * args.steps), "extra": out})
+
+
 _JSON_OUT = None
 
 
@@ -289,7 +353,10 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=16, help="bars per step of the CPU arm (BASELINE configs[0])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "decode"],
+    ap.add_argument("--micro-bars", type=int, default=0,
+                    help="train: run the step as gradient-accumulated chunks of this many bars (BASELINE configs[2]: "
+                         "--gpus 2 --batch 2048 --micro-bars 512 is global batch 4096)")
+    ap.add_argument("--mode", default="train", choices=["train", "decode", "gan"],
                     help="train = BASELINE configs[1] (the driver's default); decode = configs[4], maker_bar sampling")
     ap.add_argument("--songs", type=int, default=8192, help="decode: songs generated in lock-step per GPU")
     ap.add_argument("--no-decode", action="store_true", help="train mode: skip the extra.decode measurement")
@@ -340,13 +407,18 @@ def main():
     torch.manual_seed(0)
     if args.mode == "decode":
         return decode_bench(args, pkg, Model, dev, rank, world)
+    if args.mode == "gan":
+        return gan_bench(args, pkg, dev, rank, world)
     model = Model().to(dev).train()          # reference initialisation (graph/weights_initializer.py semantics)
     flat = model.flatten_parameters()
     reducer = None
     if world > 1:
         reducer = par.GradReducer.for_model(model, flat)
         reducer.broadcast_parameters(0)
-    trainer = Trainer(model, lr=0.002, reducer=reducer)
+    trainer = Trainer(model, lr=0.002, reducer=reducer, micro_bars=args.micro_bars)
+    if args.micro_bars:
+        cfg["micro_bars"] = args.micro_bars
+        cfg["workload"] += " (gradient-accumulated in chunks of %d bars)" % args.micro_bars
 
     dbatch = synthetic_batch(B, 1234 + rank, dev)
     hbatch = synthetic_batch(B, 4321 + rank, None, pin=True)
