@@ -240,6 +240,16 @@ int bvae_reparam_kl_bwd(const float* mu, const float* logvar, const float* eps, 
  * pre-multiplied by grad_scale (1/world_size when the bucket holds an NCCL sum).  16 B read + 12 B written/param. */
 int bvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
                    int step, float grad_scale, void* stream);
+/* The same update with the step-dependent scalars read from DEVICE memory, so that a captured CUDA graph of the whole
+ * training step can be replayed unchanged: bvae_adam_hyper (host, no device work) fills out6 = {lr/(1-b1^t),
+ * 1/sqrt(1-b2^t), b1, b2, eps, grad_scale}; the caller copies those 6 floats to hyper_dev on the stream before the launch
+ * (or before the graph replay). */
+void bvae_adam_hyper(float lr, float b1, float b2, float eps, int step, float grad_scale, float* out6);
+/* ... or in one call: a one-thread kernel writes them (launch parameters are captured at launch time, so the host may run
+ * any number of steps ahead of the device) */
+int bvae_adam_hyper_upload(float lr, float b1, float b2, float eps, int step, float grad_scale, float* hyper_dev,
+                           void* stream);
+int bvae_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_dev, void* stream);
 
 /* fp32 -> bf16 cast of a contiguous buffer (piano-roll inputs: [N,1,H,W] with C == 1 is already NHWC) */
 int bvae_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -107,6 +107,9 @@ SYMBOLS = [
     ("bvae_reparam_kl_fwd", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     ("bvae_reparam_kl_bwd", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, c_i64, c_vp]),
     ("bvae_adam_step", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_f32, C.c_int, c_f32, c_vp]),
+    ("bvae_adam_hyper", None, [c_f32, c_f32, c_f32, c_f32, C.c_int, c_f32, c_vp]),
+    ("bvae_adam_step_dev", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    ("bvae_adam_hyper_upload", C.c_int, [c_f32, c_f32, c_f32, c_f32, C.c_int, c_f32, c_vp, c_vp]),
     ("bvae_f32_to_bf16", C.c_int, [c_vp, c_vp, c_i64, c_vp]),
     ("bvae_unpack_bits", C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     ("bvae_threshold_pack", C.c_int, [c_vp, c_i64, c_f32, c_vp, c_vp, c_vp]),

@@ -328,7 +328,10 @@ __global__ void reparam_kl_bwd_kernel(const float* __restrict__ mu, const float*
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n4,
                                                    int64_t n, float b1, float b2, float eps, float step_size,
-                                                   float inv_sqrt_bc2, float gscale) {
+                                                   float inv_sqrt_bc2, float gscale, const float* __restrict__ hyp) {
+  if (hyp) {      // step-dependent scalars from device memory: lets a captured CUDA graph replay the launch unchanged
+    step_size = hyp[0]; inv_sqrt_bc2 = hyp[1]; b1 = hyp[2]; b2 = hyp[3]; eps = hyp[4]; gscale = hyp[5];
+  }
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -531,7 +534,38 @@ int bvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
   const float inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
   const int64_t n4 = n / 4;
   adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n4, n, b1, b2, eps, step_size, inv_sqrt_bc2,
-                                                        grad_scale);
+                                                        grad_scale, nullptr);
+  return check_launch("adam");
+}
+
+void bvae_adam_hyper(float lr, float b1, float b2, float eps, int step, float grad_scale, float* out6);
+}  // extern "C" (reopened below: a kernel cannot have C linkage)
+__global__ void adam_hyper_kernel(float* out, float a, float b, float c, float d, float e, float f) {
+  out[0] = a; out[1] = b; out[2] = c; out[3] = d; out[4] = e; out[5] = f;
+}
+extern "C" {
+
+int bvae_adam_hyper_upload(float lr, float b1, float b2, float eps, int step, float grad_scale, float* hyper_dev,
+                           void* stream) {
+  BVAE_REQUIRE(step >= 1 && hyper_dev, BVAE_ERR_SHAPE, "adam_hyper_upload: step must be >= 1, hyper_dev non-NULL");
+  float h[6];
+  bvae_adam_hyper(lr, b1, b2, eps, step, grad_scale, h);
+  adam_hyper_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper_dev, h[0], h[1], h[2], h[3], h[4], h[5]);
+  return check_launch("adam_hyper");
+}
+
+void bvae_adam_hyper(float lr, float b1, float b2, float eps, int step, float grad_scale, float* out6) {
+  const double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
+  out6[0] = (float)(lr / bc1);
+  out6[1] = (float)(1.0 / sqrt(bc2));
+  out6[2] = b1; out6[3] = b2; out6[4] = eps; out6[5] = grad_scale;
+}
+
+int bvae_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper_dev, void* stream) {
+  BVAE_REQUIRE(hyper_dev != nullptr, BVAE_ERR_SHAPE, "adam_dev: hyper_dev is NULL");
+  BVAE_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, BVAE_ERR_ALIGN,
+               "adam: buffers must be 16-byte aligned");
+  adam_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n / 4, n, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, hyper_dev);
   return check_launch("adam");
 }
 

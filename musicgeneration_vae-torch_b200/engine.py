@@ -785,3 +785,27 @@ def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: f
     bump_param_epoch()
     if repack:
         repack_weights(flat)
+
+
+def adam_step_dev(flat: FlatParams, hyper_dev: torch.Tensor, repack: bool = True):
+    """adam_step with the step-dependent scalars read from device memory (bvae_adam_step_dev): the launch is identical
+    every step, so it can live inside a captured CUDA graph; ``adam_hyper_upload`` sets the scalars before each replay."""
+    if flat.exp_avg is None:
+        flat.exp_avg = torch.zeros_like(flat.data)
+        flat.exp_avg_sq = torch.zeros_like(flat.data)
+    _lib.check(_lib.lib().bvae_adam_step_dev(flat.data.data_ptr(), flat.grad.data_ptr(), flat.exp_avg.data_ptr(),
+                                             flat.exp_avg_sq.data_ptr(), flat.numel, hyper_dev.data_ptr(),
+                                             _lib.stream_ptr()), "adam_dev")
+    bump_param_epoch()
+    if repack:
+        repack_weights(flat)
+
+
+def adam_hyper_upload(hyper_dev: torch.Tensor, lr: float, step: int, betas=(0.9, 0.999), eps: float = 1e-8,
+                      grad_scale: float = 1.0):
+    _lib.check(_lib.lib().bvae_adam_hyper_upload(lr, betas[0], betas[1], eps, step, grad_scale, hyper_dev.data_ptr(),
+                                                 _lib.stream_ptr()), "adam_hyper_upload")
+
+
+def capturing() -> bool:
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()

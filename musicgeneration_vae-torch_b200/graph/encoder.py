@@ -24,7 +24,7 @@ class _TrunkFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         cur0 = torch.cuda.current_stream()
-        if cur0 != torch.cuda.default_stream(cur0.device):
+        if cur0 != torch.cuda.default_stream(cur0.device) and not torch.cuda.is_current_stream_capturing():
             dz.record_stream(cur0)       # produced on the decoder's stream, dropped by autograd when this node returns
         with async_wgrad():
             ctx.module._bwd(ctx.saved, dz)

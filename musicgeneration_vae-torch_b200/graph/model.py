@@ -139,7 +139,8 @@ class Model(nn.Module):
         main = torch.cuda.current_stream()
         side = self.side_stream(phrase.device)
         side.wait_stream(main)
-        phrase.record_stream(side)      # the caller may drop its input right after the call (one block per step)
+        if not torch.cuda.is_current_stream_capturing():      # (graph capture: the inputs are the graph's static buffers)
+            phrase.record_stream(side)  # the caller may drop its input right after the call (one block per step)
         with torch.cuda.stream(side):
             pf = self.phrase_encoder(phrase)
         self._phrase_join = (main, side, pf)

@@ -3,6 +3,9 @@ function: zero gradients (one memset of the flat bucket), forward, Loss, backwar
 NCCL as they complete), fused flat Adam."""
 from __future__ import annotations
 
+import os
+import warnings
+
 import torch
 
 from . import engine
@@ -101,13 +104,19 @@ class HostPrefetcher:
 
 class GeneratorTrainer:
     def __init__(self, model, lr: float = 0.002, betas=(0.9, 0.999), eps: float = 1e-8, reducer=None,
-                 is_pretraining: bool = True, micro_bars: int = 0):
+                 is_pretraining: bool = True, micro_bars: int = 0, use_graph=None):
         """``micro_bars`` > 0: a step over more bars than that is run as ceil(B / micro_bars) forward/backward passes
         whose gradients accumulate in the flat bucket before ONE all-reduce and ONE Adam step (exactly equivalent: the
         generator has no batch-coupled op and BCE-mean over the batch is the size-weighted mean of the chunk means).
         BASELINE config 3 (global batch 4096 on 2 / 4 GPUs = 2048 / 1024 bars per GPU) runs this way: the activations
         saved for backward are ~25 MB per bar."""
         self.micro_bars = int(micro_bars)
+        # CUDA-graph replay of the whole step (zero-grad memset, forward, loss, backward on all streams, NCCL all-reduces,
+        # Adam, operand repack: ~520 launches) -- see _graph_step.  BVAE_GRAPH=0 or use_graph=False keeps every step eager.
+        self.use_graph = (os.environ.get("BVAE_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
+        self.graph_after = 3               # eager steps per input signature before capturing (kernel attributes, pack plan,
+        self._graphs, self._graph_seen = {}, {}      # allocator warm-up all happen there)
+        self._hyper_dev = None
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.flat = model.flatten_parameters()
         self.reducer = reducer
@@ -117,7 +126,73 @@ class GeneratorTrainer:
 
     def step(self, note, pre_note, pre_phrase, position, dropout_masks=None, target=None):
         """One optimisation step; returns the (device) loss tensor without synchronising.  ``target`` (default: ``note``)
-        is the fp32 BCE target when ``note`` itself arrives as bf16 (bit-packed input path)."""
+        is the fp32 BCE target when ``note`` itself arrives as bf16 (bit-packed input path).  After ``graph_after`` eager
+        steps with the same input signature the step is captured once as a CUDA graph and replayed from then on."""
+        if self.use_graph and note.is_cuda and not engine.profiling():
+            loss = self._graph_step(note, pre_note, pre_phrase, position, dropout_masks, target)
+            if loss is not None:
+                return loss
+        return self._eager_step(note, pre_note, pre_phrase, position, dropout_masks, target)
+
+    # ---- CUDA-graph replay --------------------------------------------------------------------------------------
+    def _graph_step(self, note, pre_note, pre_phrase, position, dropout_masks, target):
+        """The reference's loop (agent/barGen.py:302-335) enqueues ~2000 ATen kernels per step from Python; this path's eager
+        step still issues ~520 launches through ctypes (~25 ms of host time per 42 ms step at 512 bars, the limiter at
+        smaller batches).  Everything in the step is stream-ordered device work with fixed shapes, so it is captured ONCE
+        per input signature -- forward and backward on the branch / weight-gradient streams (fork/join inside the
+        capture), the NCCL all-reduces of the gradient segments, the fused Adam (step-dependent scalars read from device
+        memory: bvae_adam_step_dev) and the operand repack -- and replayed with one cudaGraphLaunch.  Inputs are copied
+        into the graph's static buffers (D2D, ~20 us for 70 MB); dropout masks are drawn inside the graph by torch's
+        graph-safe Philox generator (a fresh mask every replay), injected masks are copied like inputs."""
+        ins = [note, pre_note, pre_phrase, position] + list(dropout_masks or ()) + ([target] if target is not None else [])
+        key = (tuple((tuple(t.shape), t.dtype) for t in ins), dropout_masks is not None, target is not None,
+               self.is_pretraining, self.model.training, self.micro_bars)
+        ent = self._graphs.get(key)
+        if ent is None:
+            seen = self._graph_seen.get(key, 0)
+            if seen < self.graph_after:
+                self._graph_seen[key] = seen + 1
+                return None
+            ent = self._capture(key, ins, dropout_masks is not None, target is not None)
+            if ent is None:
+                return None
+        graph, static, loss = ent
+        for s, t in zip(static, ins):
+            if s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self.step_count += 1
+        scale = 1.0 / self.reducer.world if self.reducer is not None and self.reducer.world > 1 else 1.0
+        engine.adam_hyper_upload(self._hyper_dev, self.lr, self.step_count, self.betas, self.eps, scale)
+        graph.replay()
+        return loss.clone()          # the static loss buffer is overwritten by the next replay
+
+    def _capture(self, key, ins, has_masks, has_target):
+        dev = self.flat.data.device
+        if self._hyper_dev is None:
+            self._hyper_dev = torch.zeros(8, dtype=torch.float32, device=dev)
+        static = [torch.empty_like(t).copy_(t) for t in ins]
+        n_m = 2 if has_masks else 0
+        masks = tuple(static[4:4 + n_m]) if has_masks else None
+        target = static[4 + n_m] if has_target else None
+        # the capture itself performs one real step: give it this step's scalars
+        scale = 1.0 / self.reducer.world if self.reducer is not None and self.reducer.world > 1 else 1.0
+        engine.adam_hyper_upload(self._hyper_dev, self.lr, self.step_count + 1, self.betas, self.eps, scale)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph):
+                loss = self._eager_step(static[0], static[1], static[2], static[3], masks, target, hyper_dev=self._hyper_dev)
+        except Exception as exc:                  # loud, and the eager path keeps working
+            self.use_graph = False
+            warnings.warn("CUDA-graph capture of the training step failed (%s: %s); continuing with eager steps"
+                          % (type(exc).__name__, exc))
+            return None
+        # capturing does not execute: the step this call stands for is the first replay (done by the caller)
+        self.step_count -= 1
+        ent = self._graphs[key] = (graph, static, loss)
+        return ent
+
+    def _eager_step(self, note, pre_note, pre_phrase, position, dropout_masks=None, target=None, hyper_dev=None):
         self.flat.attach_grads(zero=True)
         B = note.shape[0]
         if self.micro_bars and B > self.micro_bars:
@@ -128,7 +203,10 @@ class GeneratorTrainer:
             loss.backward()
         scale = self.reducer.finish() if self.reducer is not None else 1.0
         self.step_count += 1
-        engine.adam_step(self.flat, self.lr, self.step_count, self.betas, self.eps, scale)
+        if hyper_dev is not None:
+            engine.adam_step_dev(self.flat, hyper_dev)
+        else:
+            engine.adam_step(self.flat, self.lr, self.step_count, self.betas, self.eps, scale)
         return loss.detach()
 
     def _accumulate(self, note, pre_note, pre_phrase, position, dropout_masks, target):

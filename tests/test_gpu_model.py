@@ -455,3 +455,43 @@ def test_deterministic_mode_forward_is_bit_identical(oracle, monkeypatch):
         lib.set_deterministic(False)
     report(test="deterministic_forward", default_mode_maxabs_spread=spread, det_loss=float(ref[3]), default_loss=float(base[3]))
     assert abs(float(ref[3]) - float(base[3])) < 2e-2 * abs(float(base[3]))
+
+
+def test_graph_replayed_step_matches_eager_steps(oracle):
+    """GeneratorTrainer with CUDA-graph replay (the default after 3 eager steps per input signature; forced after 1 here):
+    four steps -- one eager, one that captures, two replays -- must leave the same parameters as four eager steps, within the
+    run-to-run floor of the eager path (the replay runs exactly the captured launches: forward + backward on all streams,
+    Adam with its step-dependent scalars read from device memory, operand repack), and the replayed losses must follow
+    the eager ones.  Injected dropout masks make the two runs comparable."""
+    O = oracle
+    Model = pkg("graph.model").Model
+    Trainer = pkg("trainer").GeneratorTrainer
+    sd = O.make_state_dict(O.generator_spec(), 21, "lively")
+    batch = tuple(t.cuda() for t in O.make_inputs(4, 9))
+    masks = tuple(m.cuda() for m in O.draw_dropout_masks(4, 5))
+
+    def run(graph):
+        model = Model()
+        model.load_state_dict(sd)
+        tr = Trainer(model.cuda().train(), lr=0.002, use_graph=graph)
+        tr.graph_after = 1
+        start = tr.flat.data.clone()
+        losses = [float(tr.step(*batch, masks)) for _ in range(4)]
+        torch.cuda.synchronize()
+        return tr.flat.data.clone(), start, losses, tr
+
+    a, start, la, _ = run(False)
+    a2, _, _, _ = run(False)
+    b, _, lb, tr = run(True)
+    assert len(tr._graphs) == 1 and tr.use_graph and tr.step_count == 4           # captured once, replayed, counter in step
+    upd = (a - start).abs().mean().item()
+    floor = (a2 - a).abs().mean().item() / upd
+    e = (b - a).abs().mean().item() / upd
+    report(test="graph_step", floor=floor, graph_vs_eager=e, losses_eager=la, losses_graph=lb)
+    assert e < 2 * floor + 0.05, (floor, e)
+    assert all(abs(x - y) < 0.1 * abs(x) for x, y in zip(la, lb)), (la, lb)
+    # a different batch size is a different signature: eager again, then its own graph
+    small = tuple(t[:2] for t in batch)
+    for _ in range(3):
+        tr.step(*small, tuple(m[:2] for m in masks))
+    assert len(tr._graphs) == 2
