@@ -457,7 +457,13 @@ def main():
         for db in trainer.prefetch(batch for _ in range(k)):
             trainer.step_batch(db).item()
 
-    for _ in range(max(3, args.warmup)):
+    # untimed warm-up: W (>= 3) eager steps, then -- with CUDA-graph replay on (the default) -- the step that captures the
+    # graph and one replay, so that the timed region below contains replays only
+    n_warm = max(3, args.warmup)
+    if trainer.use_graph:
+        trainer.graph_after = n_warm
+        n_warm += 2
+    for _ in range(n_warm):
         step_resident()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -485,7 +491,7 @@ def main():
     try:
         Packed = importlib.import_module(PKG + ".data.packed").PackedBatch
         pbatch = Packed.from_arrays(*hbatch, pin=True)
-        loop_e2e(pbatch, 2)
+        loop_e2e(pbatch, 2 + (trainer.graph_after + 1 if trainer.use_graph else 0))   # (its own input signature / graph)
         ms_p = timed(lambda: loop_e2e(pbatch, args.steps), 1)
         e2e_packed = {"value": B * world * args.steps / (ms_p * 1e-3), "unit": "bars/s",
                       "h2d_bytes_per_step": pbatch.nbytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_p / args.steps}
@@ -611,6 +617,7 @@ def main():
             model.train()
         except Exception as exc:
             extra["decode"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    trainer.release_graphs()            # graphs that captured NCCL kernels must go before the process group does
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -625,7 +632,7 @@ def main():
         cpu = {"value": bars_s, "unit": "bars/s", "cores": threads, "kind": "port",
                "sample": "%d steps of %d bars (fwd+bwd+Adam) of the oracle port, %.1f s/step" % (nst, args.cpu_batch, dt)}
     line = {"metric": "train_bars_per_sec", "value": value, "unit": "bars/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg,
             "e2e": {"value": e2e, "unit": "bars/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,

@@ -45,6 +45,9 @@ const char* bvae_last_error(void);
 /* number of kernels launched by this library since load / since the last reset (bench.py's gpu_launches) */
 uint64_t bvae_launch_count(void);
 void bvae_launch_count_reset(void);
+/* kernels of this library launched by REPLAYING a captured CUDA graph do not pass through the entry points: the caller
+ * that replays adds the number of launches it counted while capturing */
+void bvae_launch_count_add(uint64_t n);
 /* 1 if the current device is sm_100 (B200); kernels refuse to run elsewhere */
 int bvae_device_ok(void);
 /* name (with template arguments) of the kernel the calling thread's last bvae_conv_gemm / bvae_wgrad_gemm call launched:

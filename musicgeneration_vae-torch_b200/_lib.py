@@ -84,6 +84,7 @@ SYMBOLS = [
     ("bvae_last_error", C.c_char_p, []),
     ("bvae_launch_count", C.c_uint64, []),
     ("bvae_launch_count_reset", None, []),
+    ("bvae_launch_count_add", None, [C.c_uint64]),
     ("bvae_device_ok", C.c_int, []),
     ("bvae_last_kernel", C.c_char_p, []),
     ("bvae_set_deterministic", None, [C.c_int]),

@@ -375,6 +375,7 @@ int bvae_version(void) { return 100; }
 const char* bvae_last_error(void) { return bvae::g_err; }
 uint64_t bvae_launch_count(void) { return bvae::g_launches.load(); }
 void bvae_launch_count_reset(void) { bvae::g_launches.store(0); }
+void bvae_launch_count_add(uint64_t n) { bvae::g_launches.fetch_add(n); }
 const char* bvae_last_kernel(void) { return bvae::g_kernel; }
 void bvae_set_deterministic(int on) { bvae::g_det.store(on ? 1 : 0); }
 int bvae_deterministic(void) { return bvae::deterministic() ? 1 : 0; }

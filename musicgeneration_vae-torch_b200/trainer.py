@@ -8,7 +8,7 @@ import warnings
 
 import torch
 
-from . import engine
+from . import _lib, engine
 from .graph.loss.bar_loss import Loss
 
 
@@ -113,7 +113,15 @@ class GeneratorTrainer:
         self.micro_bars = int(micro_bars)
         # CUDA-graph replay of the whole step (zero-grad memset, forward, loss, backward on all streams, NCCL all-reduces,
         # Adam, operand repack: ~520 launches) -- see _graph_step.  BVAE_GRAPH=0 or use_graph=False keeps every step eager.
-        self.use_graph = (os.environ.get("BVAE_GRAPH", "1") != "0") if use_graph is None else bool(use_graph)
+        # Default: on for single-process training; OFF under torch.distributed unless BVAE_GRAPH=1 / use_graph=True asks for
+        # it: capturing the NCCL all-reduces works (measured: 2 GPUs, 23.8 k bars/s, same as eager), but a process that
+        # still holds such a graph when the process group is destroyed hangs in NCCL teardown until the watchdog aborts it
+        # (measured: 16 minutes) -- call release_graphs() before dist.destroy_process_group().
+        env = os.environ.get("BVAE_GRAPH")
+        multi = reducer is not None and getattr(reducer, "world", 1) > 1
+        self.use_graph = ((env == "1") if (env is not None or multi) else True) if use_graph is None else bool(use_graph)
+        if env == "0":
+            self.use_graph = False
         self.graph_after = 3               # eager steps per input signature before capturing (kernel attributes, pack plan,
         self._graphs, self._graph_seen = {}, {}      # allocator warm-up all happen there)
         self._hyper_dev = None
@@ -156,7 +164,7 @@ class GeneratorTrainer:
             ent = self._capture(key, ins, dropout_masks is not None, target is not None)
             if ent is None:
                 return None
-        graph, static, loss = ent
+        graph, static, loss, n_launch = ent
         for s, t in zip(static, ins):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
@@ -164,7 +172,17 @@ class GeneratorTrainer:
         scale = 1.0 / self.reducer.world if self.reducer is not None and self.reducer.world > 1 else 1.0
         engine.adam_hyper_upload(self._hyper_dev, self.lr, self.step_count, self.betas, self.eps, scale)
         graph.replay()
+        _lib.load().bvae_launch_count_add(n_launch)     # the replay launches what the capture recorded
         return loss.clone()          # the static loss buffer is overwritten by the next replay
+
+    def release_graphs(self):
+        """drop every captured graph (and its private memory pool); required before dist.destroy_process_group() when the
+        graphs contain NCCL collectives"""
+        if self._graphs:
+            torch.cuda.synchronize()
+            self._graphs.clear()
+            self._graph_seen.clear()
+            torch.cuda.synchronize()
 
     def _capture(self, key, ins, has_masks, has_target):
         dev = self.flat.data.device
@@ -179,6 +197,7 @@ class GeneratorTrainer:
         engine.adam_hyper_upload(self._hyper_dev, self.lr, self.step_count + 1, self.betas, self.eps, scale)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
         try:
             with torch.cuda.graph(graph):
                 loss = self._eager_step(static[0], static[1], static[2], static[3], masks, target, hyper_dev=self._hyper_dev)
@@ -189,7 +208,9 @@ class GeneratorTrainer:
             return None
         # capturing does not execute: the step this call stands for is the first replay (done by the caller)
         self.step_count -= 1
-        ent = self._graphs[key] = (graph, static, loss)
+        n_launch = _lib.launch_count() - n0
+        _lib.load().bvae_launch_count_add(-n_launch & 0xFFFFFFFFFFFFFFFF)      # recorded, not executed
+        ent = self._graphs[key] = (graph, static, loss, n_launch)
         return ent
 
     def _eager_step(self, note, pre_note, pre_phrase, position, dropout_masks=None, target=None, hyper_dev=None):
@@ -244,6 +265,8 @@ class GeneratorTrainer:
         else:
             with torch.cuda.stream(side):
                 phrase_d = pre_phrase.to(dev, non_blocking=True)
+            if self.use_graph:          # a graph replay reads its inputs on the main stream (copy into static buffers)
+                torch.cuda.current_stream().wait_stream(side)
         return self.step(note_d, pre_d, phrase_d, pos_d, dropout_masks)
 
     def prefetch(self, host_batches):
@@ -266,6 +289,8 @@ class GeneratorTrainer:
         dev = self.flat.data.device
         side = self.model.side_stream(dev) if hasattr(self.model, "side_stream") else None
         note_f32, bars, phrase, pos, dbits = packed.to_device(dev, side)
+        if self.use_graph and side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         B = packed.batch
         loss = self.step(bars[:B], bars[B:], phrase, pos, dropout_masks, target=note_f32)
         del dbits        # held until here: the main stream has joined the phrase stream inside the step
