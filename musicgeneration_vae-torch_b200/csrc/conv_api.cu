@@ -13,6 +13,10 @@ int stem_fwd_eligible(const bvae_conv_desc* d);
 int stem_fwd_launch(const bvae_conv_desc* d, cudaStream_t stream);
 int stem_wgrad_eligible(const bvae_wgrad_desc* d);
 int stem_wgrad_launch(const bvae_wgrad_desc* d, cudaStream_t stream);
+int conv_small_eligible(const bvae_conv_desc* d);
+int conv_small_launch(const bvae_conv_desc* d, cudaStream_t stream);
+int wgrad_small_eligible(const bvae_wgrad_desc* d);
+int wgrad_small_launch(const bvae_wgrad_desc* d, cudaStream_t stream);
 }  // namespace bvae
 
 using namespace bvae;
@@ -68,6 +72,7 @@ extern "C" int bvae_conv_gemm(const bvae_conv_desc* d, int impl, void* stream) {
                "conv_gemm: statistics fusion is not available for this problem (check bvae_conv_stats_ok)");
   if (impl == BVAE_IMPL_SIMT) return conv_simt_launch(d, (cudaStream_t)stream);
   if (impl == BVAE_IMPL_AUTO && stem_fwd_eligible(d)) return stem_fwd_launch(d, (cudaStream_t)stream);
+  if (impl == BVAE_IMPL_AUTO && conv_small_eligible(d)) return conv_small_launch(d, (cudaStream_t)stream);
   const int ok = conv_tc_eligible(d);
   if (impl == BVAE_IMPL_TC) {
     BVAE_REQUIRE(ok, BVAE_ERR_UNSUPPORTED, "conv_gemm: shape not eligible for the tcgen05 kernel (C=%d Cout=%d)", d->C, d->Cout);
@@ -96,6 +101,7 @@ extern "C" int bvae_wgrad_gemm(const bvae_wgrad_desc* d, int impl, void* stream)
   BVAE_REQUIRE(d->N > 0 && d->AH > 0 && d->AW > 0 && d->Ca > 0 && d->Cs > 0, BVAE_ERR_SHAPE, "wgrad_gemm: empty problem");
   if (impl == BVAE_IMPL_SIMT) return wgrad_simt_launch(d, (cudaStream_t)stream);
   if (impl == BVAE_IMPL_AUTO && stem_wgrad_eligible(d)) return stem_wgrad_launch(d, (cudaStream_t)stream);
+  if (impl == BVAE_IMPL_AUTO && wgrad_small_eligible(d)) return wgrad_small_launch(d, (cudaStream_t)stream);
   const int ok = wgrad_tc_eligible(d);
   if (impl == BVAE_IMPL_TC) {
     BVAE_REQUIRE(ok, BVAE_ERR_UNSUPPORTED, "wgrad_gemm: shape not eligible for the tcgen05 kernel (Ca=%d Cs=%d)", d->Ca, d->Cs);

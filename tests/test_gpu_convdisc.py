@@ -136,3 +136,100 @@ def test_frozen_discriminator_still_propagates_input_gradient(gc):
     F.binary_cross_entropy(m(x), torch.ones(5, 1, device="cuda")).backward()
     assert x.grad is not None and float(x.grad.abs().sum()) > 0
     assert all(p.grad is None for p in m.parameters())
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+
+
+_SMALL_CONVS = [(1, 8, (3, 1), (2, 1), (1, 0), 192, 12), (8, 16, (3, 1), (2, 1), (1, 0), 96, 12), (16, 16, 1, 1, 0, 48, 12),
+                (16, 32, 3, 2, 1, 48, 12), (32, 64, 3, 2, 1, 24, 6), (1, 8, 3, (2, 1), 1, 192, 1), (8, 8, 3, (2, 1), 1, 96, 1),
+                (1, 8, (1, 4), (1, 2), (0, 1), 192, 60), (8, 8, (4, 1), (2, 1), (1, 0), 192, 30), (16, 8, 1, 1, 0, 96, 30),
+                (8, 8, 3, 1, 1, 96, 30), (8, 16, 3, 2, 1, 96, 30), (1, 2, 4, 1, 2, 96, 60), (2, 8, 4, 1, 2, 48, 30),
+                (32, 32, 1, 1, 0, 12, 1)]
+
+
+@pytest.mark.parametrize("spec", _SMALL_CONVS, ids=lambda s: "%dto%d_k%s_s%s" % (s[0], s[1], s[2], s[3]))
+@pytest.mark.parametrize("act", [False, True])
+def test_small_channel_conv_ops_vs_torch(spec, act):
+    """every convolution shape of the BarDiscriminator / Refiner through graph/_smallnet.conv (forward, weight gradient,
+    data gradient: csrc/conv_small.cu for < 32 channels, the tcgen05 kernels otherwise) against torch.nn.functional on the
+    same bf16-representable operands: fp32 outputs 1e-5, bf16 outputs / gradients 4e-3 (one bf16 rounding)"""
+    import torch.nn as nn
+    S = pkg("graph._smallnet")
+    cin, cout, k, s, p, H, W = spec
+    torch.manual_seed(1)
+    m = nn.Conv2d(cin, cout, k, s, p, bias=False).cuda()
+    x = torch.randn(3, cin, H, W, device="cuda").to(torch.bfloat16).float().requires_grad_(True)
+    with torch.no_grad():
+        m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    ref = m(x)
+    if act:
+        ref = F.relu(ref)
+    g = torch.randn_like(ref).to(torch.bfloat16).float()
+    ref.backward(g)
+    rw, rx = m.weight.grad.clone(), x.grad.clone()
+    m.weight.grad = None
+    x2 = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    out = S.conv(x2, m, act=act, out_f32=not act)
+    out.backward(g.permute(0, 2, 3, 1).contiguous().to(out.dtype))
+    e = (_rel(out.permute(0, 3, 1, 2).float(), ref), _rel(m.weight.grad, rw), _rel(x2.grad.permute(0, 3, 1, 2), rx))
+    assert e[0] < (4e-3 if act else 1e-5) and e[1] < 1e-4 and e[2] < 4e-3, e
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(8, 2, 24, 15), (2, 1, 48, 30)])
+def test_small_channel_transposed_conv_vs_torch(cin, cout, H, W):
+    import torch.nn as nn
+    S = pkg("graph._smallnet")
+    torch.manual_seed(2)
+    m = nn.ConvTranspose2d(cin, cout, 4, 2, 1, bias=False).cuda()
+    x = torch.randn(3, cin, H, W, device="cuda").to(torch.bfloat16).float().requires_grad_(True)
+    with torch.no_grad():
+        m.weight.copy_(m.weight.to(torch.bfloat16).float())
+    ref = m(x)
+    g = torch.randn_like(ref).to(torch.bfloat16).float()
+    ref.backward(g)
+    rw, rx = m.weight.grad.clone(), x.grad.clone()
+    m.weight.grad = None
+    x2 = x.detach().permute(0, 2, 3, 1).contiguous().requires_grad_(True)
+    out = S.conv(x2, m)
+    out.backward(g.permute(0, 2, 3, 1).contiguous())
+    e = (_rel(out.permute(0, 3, 1, 2).float(), ref), _rel(m.weight.grad, rw), _rel(x2.grad.permute(0, 3, 1, 2), rx))
+    assert e[0] < 1e-5 and e[1] < 1e-4 and e[2] < 4e-3, e
+
+
+@pytest.mark.parametrize("C", [1, 2, 8, 16, 64])
+@pytest.mark.parametrize("act,training,xf32", [(False, True, True), (True, True, True), (True, False, True), (False, True, False)])
+def test_batch_norm_op_vs_torch(C, act, training, xf32):
+    """bvae_bn_forward / bvae_bn_backward against nn.BatchNorm2d (+ReLU): output and dx within one bf16 rounding, dgamma /
+    dbeta and the updated running statistics to fp32 precision"""
+    import copy
+    import torch.nn as nn
+    S = pkg("graph._smallnet")
+    torch.manual_seed(3)
+    bn = nn.BatchNorm2d(C, momentum=0.01).cuda().train(training)
+    with torch.no_grad():
+        bn.weight.normal_(1, 0.3)
+        bn.bias.normal_(0, 0.3)
+        bn.running_mean.normal_(0, 0.2)
+        bn.running_var.uniform_(0.5, 1.5)
+    bn2 = copy.deepcopy(bn)
+    x = torch.randn(4, C, 24, 15, device="cuda") * 2 + 3
+    if not xf32:
+        x = x.to(torch.bfloat16).float()
+    x.requires_grad_(True)
+    ref = bn(x)
+    if act:
+        ref = F.relu(ref)
+    g = torch.randn_like(ref).to(torch.bfloat16).float()
+    ref.backward(g)
+    x2 = x.detach().permute(0, 2, 3, 1).contiguous()
+    if not xf32:
+        x2 = x2.to(torch.bfloat16)
+    x2.requires_grad_(True)
+    out = S.batch_norm(x2, bn2, act=act)
+    out.backward(g.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))
+    assert _rel(out.permute(0, 3, 1, 2).float(), ref) < 4e-3 and _rel(x2.grad.permute(0, 3, 1, 2).float(), x.grad) < 4e-3
+    assert _rel(bn2.weight.grad, bn.weight.grad) < 1e-4 and _rel(bn2.bias.grad, bn.bias.grad) < 1e-4
+    assert _rel(bn2.running_mean, bn.running_mean) < 1e-5 and _rel(bn2.running_var, bn.running_var) < 1e-5
+    assert int(bn2.num_batches_tracked) == int(bn.num_batches_tracked)

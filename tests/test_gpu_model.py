@@ -384,12 +384,10 @@ def test_trainer_stream_and_segment_paths_agree(oracle, monkeypatch):
     assert abs(l1 - l0) < 0.1 * abs(l0) and abs(l2 - l0) < 0.1 * abs(l0), (l0, l1, l2)
 
 
-@pytest.mark.skipif(os.environ.get("BVAE_TEST_EXPERIMENTAL") != "1",
-                    reason="engine.fork (decoder branches on a companion stream) ships disabled: written after the round's "
-                           "last GPU minute; run with BVAE_TEST_EXPERIMENTAL=1 before enabling BVAE_DEC_STREAMS")
 def test_decoder_branch_streams_agree(oracle, monkeypatch):
-    """BVAE_DEC_STREAMS=1 must give the same parameters after two steps as the default path, within the run-to-run
-    floor of the default path (same protocol as test_trainer_stream_and_segment_paths_agree)"""
+    """decoder branches on a companion stream (engine.fork, the default) must give the same parameters after two steps as
+    the one-stream launch order (BVAE_DEC_STREAMS=0), within the run-to-run floor of the latter (same protocol as
+    test_trainer_stream_and_segment_paths_agree)"""
     O = oracle
     Model = pkg("graph.model").Model
     Trainer = pkg("trainer").GeneratorTrainer
