@@ -89,6 +89,8 @@ SYMBOLS = [
     ("bvae_last_kernel", C.c_char_p, []),
     ("bvae_set_deterministic", None, [C.c_int]),
     ("bvae_deterministic", C.c_int, []),
+    ("bvae_set_option", None, [C.c_char_p, C.c_int]),
+    ("bvae_get_option", C.c_int, [C.c_char_p, C.c_int]),
     ("bvae_conv_gemm", C.c_int, [C.POINTER(ConvDesc), C.c_int, c_vp]),
     ("bvae_conv_stats_ok", C.c_int, [C.POINTER(ConvDesc)]),
     ("bvae_wgrad_gemm", C.c_int, [C.POINTER(WgradDesc), C.c_int, c_vp]),
@@ -175,3 +177,18 @@ def set_deterministic(flag: bool):
 
 def last_kernel() -> str:
     return load().bvae_last_kernel().decode()
+
+
+class option:
+    """``with option("BVAE_NB_FAST", 0): ...`` -- a kernel-variant switch (bvae_set_option) for the duration of the block"""
+
+    def __init__(self, name: str, value: int):
+        self.name, self.value = name.encode(), int(value)
+
+    def __enter__(self):
+        load().bvae_set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        load().bvae_set_option(self.name, -1)
+        return False

@@ -16,6 +16,7 @@ int check_launch(const char* what);   // cudaGetLastError -> BVAE_ERR_CUDA (+mes
 void count_launch(int n = 1);
 void note_kernel(const char* fmt, ...);   // remembered per host thread for bvae_last_kernel()
 bool deterministic();                     // bvae_set_deterministic / BVAE_DETERMINISTIC
+int option(const char* name, int dflt);   // bvae_set_option override, else getenv(name), else dflt (kernel-variant switches)
 
 #define BVAE_REQUIRE(cond, code, ...)            \
   do {                                           \

@@ -1163,9 +1163,7 @@ static int make_w_map(CUtensorMap* m, const void* base, int K, int rows, int pit
 }
 
 static bool use_conv_v1_flag() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  return option("BVAE_CONV_V1", 0) == 1;
 }
 
 static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
@@ -1312,16 +1310,12 @@ static int launch_conv2(const ConvTcParams& P, long tiles, cudaStream_t stream) 
 // outputs (measured slower on the masked data gradients: 0.79 vs 0.65 ms on 64->64 3x3, the mask rows are already
 // prefetched there and the extra barriers cost more than the store requests save)
 static int conv_tma_store_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_CONV_TMA_STORE"); v = e ? atoi(e) : 1; }
-  return v;
+  return option("BVAE_CONV_TMA_STORE", 1);
 }
 
 // BVAE_CONV_HALO: 0 = off, 1 = on (default)
 static int conv_halo_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_CONV_HALO"); v = e ? atoi(e) : 1; }
-  return v;
+  return option("BVAE_CONV_HALO", 1);
 }
 
 // Halo mode applies to single-phase stride-1 layers whose weights stay resident (see launch_conv2): the output tile is
@@ -1362,9 +1356,7 @@ static int plan_halo(const bvae_conv_desc* d, ConvTcParams* P, int KB, int BN) {
 }
 
 static bool use_conv_v1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_CONV_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
+  return option("BVAE_CONV_V1", 0) == 1;
 }
 
 int conv_tc_launch(const bvae_conv_desc* d, cudaStream_t stream) {
@@ -1470,9 +1462,7 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
 
 // BVAE_WGRAD_HALO: 0 = off, 1 = on (default)
 static int wgrad_halo_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_WGRAD_HALO"); v = e ? atoi(e) : 1; }
-  return v;
+  return option("BVAE_WGRAD_HALO", 1);
 }
 
 static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_tiles, bool* packed_) {

@@ -5,6 +5,9 @@
 #include <atomic>
 #include "common.cuh"
 #include <vector>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 
 namespace bvae {
 
@@ -34,6 +37,18 @@ bool deterministic() {
     g_det.store(v, std::memory_order_relaxed);
   }
   return v == 1;
+}
+// kernel-variant switches: bvae_set_option overrides, else the environment variable of the same name, else the default
+static std::mutex g_opt_mu;
+static std::unordered_map<std::string, int> g_opts;
+int option(const char* name, int dflt) {
+  {
+    std::lock_guard<std::mutex> g(g_opt_mu);
+    auto it = g_opts.find(name);
+    if (it != g_opts.end()) return it->second;
+  }
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
@@ -378,6 +393,12 @@ void bvae_launch_count_reset(void) { bvae::g_launches.store(0); }
 void bvae_launch_count_add(uint64_t n) { bvae::g_launches.fetch_add(n); }
 const char* bvae_last_kernel(void) { return bvae::g_kernel; }
 void bvae_set_deterministic(int on) { bvae::g_det.store(on ? 1 : 0); }
+void bvae_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> g(bvae::g_opt_mu);
+  if (value < 0) bvae::g_opts.erase(name);
+  else bvae::g_opts[name] = value;
+}
+int bvae_get_option(const char* name, int dflt) { return bvae::option(name, dflt); }
 int bvae_deterministic(void) { return bvae::deterministic() ? 1 : 0; }
 
 int bvae_device_ok(void) {

@@ -2741,8 +2741,7 @@ __global__ void __launch_bounds__(256) nb_mlp_bwd_kernel(int N, int HW, int C, i
 // the >= 512-channel small maps (measured: C1024 backward -15 %, C512 neutral, C256 and every forward slower because
 // each extra stage pays the partial second wave of 512 CTAs again); 2 batches it everywhere (forward too)
 static bool nb_mlp_batched(const bvae_nb_desc* d, int CLn, bool backward) {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_NB_MLP"); v = e ? atoi(e) : 1; }
+  const int v = option("BVAE_NB_MLP", 1);
   if (v == 0 || CLn != 1 || !d->has_cbam || d->C < 128) return false;
   return v == 2 || (backward && d->C >= 512);
 }
@@ -2779,9 +2778,7 @@ static int nb_cl_launch(K kernel, const bvae_nb_desc* d, size_t smem, cudaStream
 //               1 = cluster kernels everywhere (4..16 CTAs per sample; halves HBM traffic but is latency bound:
 //                   measured 1.2-1.5x slower than the tiled kernels on the 96x60 maps);  2 = tiled / nb_small only.
 static int nb_mode() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_NB_MODE"); v = e ? atoi(e) : 0; }
-  return v;
+  return option("BVAE_NB_MODE", 0);
 }
 static bool use_nb_cluster(const bvae_nb_desc* d) {
   const int m = nb_mode();
@@ -2803,16 +2800,12 @@ static int pick_ppc(int HW, int N, int G) {
 
 // BVAE_NB_SPLIT=0 keeps the two full reduction sweeps (nbf_bwd1 + nbf_bwd2) on the CBAM sites
 static bool nb_split_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_NB_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  return option("BVAE_NB_SPLIT", 1) != 0;
 }
 
 // BVAE_NB_FAST=0 selects the generic tiled backward kernels (kept as the reference implementation of the fast ones)
 static bool nb_fast_enabled() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("BVAE_NB_FAST"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1;
+  return option("BVAE_NB_FAST", 1) != 0;
 }
 
 static int launch_bwd_w(const bvae_nb_desc* d, cudaStream_t st) {

@@ -88,7 +88,7 @@ class _UpBlock(nn.Module):
             return (g, nb, nb.forward(y, cat.slice(i * Cc, Cc), stats=st))
 
         b0, b1 = self._branches()
-        if fork_enabled():                      # EXPERIMENTAL (engine.fork): second branch on the companion stream
+        if fork_enabled():                      # engine.fork: second branch on the companion stream
             with fork() as f:
                 c1 = branch(1, *b1)
             bctx = [branch(0, *b0), c1]
@@ -120,7 +120,7 @@ class _UpBlock(nn.Module):
                 g.zero_bias_grad()          # bias feeds an InstanceNorm: gradient is identically zero
                 g.dgrad(dy, dx, addend=dx if i > 0 else None)
             return dx
-        # EXPERIMENTAL (engine.fork): norm-block backward of the second branch on the companion stream; its weight /
+        # engine.fork: norm-block backward of the second branch on the companion stream; its weight /
         # data gradients follow after the join (no weight-gradient launch inside a fork)
         dys = [None, None]
         with fork() as f:
@@ -248,7 +248,7 @@ class Decoder(nn.Module):
         else:
             keep, x = None, lin
         hcat = Act.empty(B, 6, 3, 2048)                     # torch.cat((pitch, time), 1)
-        if fork_enabled():                      # EXPERIMENTAL (engine.fork): the two head stems are independent
+        if fork_enabled():                      # engine.fork: the two head stems are independent
             with fork() as f:
                 c_t = self.time.fwd(x, hcat.slice(1024, 1024))
             c_p = self.pitch.fwd(x, hcat.slice(0, 1024))

@@ -160,6 +160,46 @@ def test_norm_block(C, H, W, mode, raw):
     mask flip on the 3x2 maps is already 0.7 %)."""
     if raw == "bf16" and (C, H, W) not in [(64, 12, 8), (128, 24, 15)]:
         pytest.skip("bf16 raw input covered on two shapes")
+    _run_norm_block(C, H, W, mode, raw)
+
+
+# ---- every kernel-variant switch that ships (include/barvae.h: bvae_set_option) gets the same parity treatment ----------
+CONV_VARIANTS = [("BVAE_CONV_V1", 1), ("BVAE_CONV_TMA_STORE", 0), ("BVAE_CONV_TMA_STORE", 2), ("BVAE_CONV_HALO", 0),
+                 ("BVAE_WGRAD_HALO", 0)]
+
+
+@pytest.mark.parametrize("opt", CONV_VARIANTS, ids=lambda o: "%s=%d" % o)
+def test_kernel_variants_contractions(opt):
+    """the first tcgen05 kernel (one tile per CTA), the direct-store / TMA-store epilogues and the non-halo paths of the
+    64-channel layers: same layers, same tolerances as the defaults"""
+    lib = pkg("_lib")
+    with lib.option(*opt):
+        assert lib.load().bvae_get_option(opt[0].encode(), -7) == opt[1]
+        for spec in LAYERS:
+            if spec[1] == 1:
+                continue                                     # C_in = 1: stem kernels, no variant
+            _run_gemm_layer(spec, "tc", 3)
+        for spec in BIG_LAYERS[-6:]:                         # the 64 / 32-channel layers incl. all halo-mode shapes
+            _run_gemm_layer(spec[:9], "tc", spec[9])
+    assert lib.load().bvae_get_option(opt[0].encode(), -7) == -7
+
+
+NB_VARIANTS = [("BVAE_NB_MLP", 0), ("BVAE_NB_MLP", 2), ("BVAE_NB_MODE", 1), ("BVAE_NB_MODE", 2), ("BVAE_NB_SPLIT", 0),
+               ("BVAE_NB_FAST", 0)]
+
+
+@pytest.mark.parametrize("opt", NB_VARIANTS, ids=lambda o: "%s=%d" % o)
+def test_kernel_variants_norm_blocks(opt):
+    """channel MLP inside / outside the per-sample kernels, cluster and per-sample kernels on every map size, unsplit
+    reduction sweeps, the generic (non-restructured) sweeps: all shapes and residual modes of test_norm_block"""
+    lib = pkg("_lib")
+    with lib.option(*opt):
+        for C, H, W in [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60)]:
+            for mode in ("plain", "self", "ext"):
+                _run_norm_block(C, H, W, mode, "f32")
+
+
+def _run_norm_block(C, H, W, mode, raw):
     eng = pkg("engine")
     torch.manual_seed(C + H)
     B = 3
