@@ -608,6 +608,20 @@ def main():
         torch.cuda.synchronize()
         extra["repack_ms"] = e0.elapsed_time(e1) / 5
 
+    # a 64-bar/GPU point: with the step replayed as one CUDA graph the host is out of the picture, what
+    # remains is the device-side latency of ~520 small launches
+    if not args.no_profile and not args.micro_bars:
+        try:
+            sb = synthetic_batch(64, 99 + rank, dev)
+            for _ in range(trainer.graph_after + 3 if trainer.use_graph else 4):
+                trainer.step(*sb)
+            ms64 = timed(lambda: trainer.step(*sb), 10) / 10
+            extra["small_batch"] = {"bars_per_gpu": 64, "ms_per_step": ms64, "bars_per_sec": 64 * world / (ms64 * 1e-3),
+                                    "per_bar_rate_vs_%d_bars" % B: (64 * world / (ms64 * 1e-3)) / value,
+                                    "graph_replay": bool(trainer.use_graph)}
+            del sb
+        except Exception as exc:
+            extra["small_batch"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
     # BASELINE configs[4] in the same record, at every N: maker_bar sampling, 8192 songs per GPU, 2 phrases (8 bars/song)
     if not args.no_decode:
         try:
@@ -617,6 +631,7 @@ def main():
             model.train()
         except Exception as exc:
             extra["decode"] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    trainer_used_graph = bool(trainer._graphs)
     trainer.release_graphs()            # graphs that captured NCCL kernels must go before the process group does
     if rank != 0:
         if world > 1:
@@ -642,7 +657,8 @@ def main():
             "e2e_sequential": e2e_seq,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_hbm": roofline_hbm,
             "cpu_baseline": cpu,
-            "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "e2e_packed": e2e_packed, "extra": extra}
+            "tflops_end_to_end": GFLOP_PER_BAR_TRAIN * 1e9 * value / 1e12, "e2e_packed": e2e_packed,
+            "graph_replay": bool(trainer_used_graph), "extra": extra}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -17,7 +17,8 @@ def install_dropin():
     for name in ("graph", "graph.model", "graph.encoder", "graph.decoder", "graph.phrase_encoder", "graph.cbam",
                  "graph.encodingBlock", "graph.weights_initializer", "graph.loss", "graph.loss.bar_loss",
                  "graph.model_with_gan", "graph.z_discriminator", "graph.bar_discriminator_with_feature",
-                 "data", "data.bar_dataset", "config", "agent", "agent.barGen", "maker_bar"):
+                 "graph.bar_discriminator", "graph.refiner",
+                 "data", "data.bar_dataset", "config", "agent", "agent.barGen", "agent.barGen_with_gan", "maker_bar"):
         try:
             sys.modules[name] = importlib.import_module(pkg + "." + name)
         except ImportError:

@@ -2027,7 +2027,8 @@ static size_t nb_small_bwd_smem(int C) { return (size_t)(12 * C) * 4 + SMALL_HW 
 // the 2nd and 3rd sweeps of the forward (and of the backward) hit L2 instead of HBM.
 // ---------------------------------------------------------------------------------------------------
 namespace cg = cooperative_groups;
-constexpr int CLT = 128;   // threads per CTA
+constexpr int CLT = 128;   // threads per CTA (256 with 3 CTAs per SM measured no faster in round 2: 22.9 vs 22.7 ms of norm blocks per step)
+constexpr int CL_MINB = 6; // CTAs per SM the launch bounds ask for
 
 __device__ __forceinline__ float cl_sum(cg::cluster_group& cl, float* s_arr, int c, int CLn) {
   float v = 0.f;
@@ -2043,7 +2044,7 @@ __device__ __forceinline__ u64 cl_max(cg::cluster_group& cl, u64* s_arr, int c, 
 // stage 0 = the whole forward; 1 = statistics + coefficients only (the channel MLP then runs BATCHED over samples in
 // nb_mlp_fwd_kernel); 2 = everything after the MLP, coefficients re-read from d.nc
 template <bool F32>
-__global__ void __launch_bounds__(CLT, 6) nb_cl_fwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
+__global__ void __launch_bounds__(CLT, CL_MINB) nb_cl_fwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ float sm[];
   const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV;
@@ -2268,7 +2269,7 @@ __global__ void __launch_bounds__(CLT, 6) nb_cl_fwd_kernel(const bvae_nb_desc d,
 
 // stage 0 = the whole backward; 1 = the reduction sweeps (totals of dgc, S1, S2 and the per-pixel spatial gradients go to
 // d.bwd_nc / d.bwd_px; the channel-MLP backward then runs BATCHED in nb_mlp_bwd_kernel); 2 = the final dy sweep
-__global__ void __launch_bounds__(CLT, 6) nb_cl_bwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
+__global__ void __launch_bounds__(CLT, CL_MINB) nb_cl_bwd_kernel(const bvae_nb_desc d, int CLn, int slice, int stage) {
   cg::cluster_group cl = cg::this_cluster();
   extern __shared__ float sm[];
   const int C = d.C, H = d.H, W = d.W, HW = H * W, NV = C / 8, PL = CLT / NV, Cr = d.Cr;
