@@ -204,7 +204,11 @@ def torch_eager_gpu(dev, bars, steps=3):
     import barvae_oracle as O
     out = {"bars_per_step": bars, "steps": steps,
            "what": "oracle port of the reference modules on cuda through PyTorch eager (cuDNN/cuBLAS/ATen), fwd+bwd+"
-                   "torch.optim.Adam; TF32 off (fp32 row), torch.autocast(bfloat16) (bf16 row)"}
+                   "torch.optim.Adam; fp32 row = fp32 storage with TF32 tensor-core convolutions and matmuls allowed "
+                   "(the faster setting), bf16 row = torch.autocast(bfloat16)"}
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True          # as the reference sets it (agent/barGen.py:26)
     sd = O.make_state_dict(O.generator_spec(), 0, "reference")
     batch = tuple(t.to(dev) for t in O.make_inputs(bars, 1234))
     for name, autocast in (("fp32", False), ("bf16_autocast", True)):
