@@ -25,7 +25,7 @@ BF16 = torch.bfloat16
 _PARAM_EPOCH = [0]          # bumped whenever libbarvae itself rewrites parameters (fused Adam)
 _IMPL = [_lib.IMPL_AUTO]    # contraction implementation selector (tests flip it to compare SIMT vs tcgen05)
 _RAW_F32 = [True]           # dtype of raw conv outputs feeding an InstanceNorm (see DESIGN.md "Parity tolerances")
-_FUSE_STATS = [False]       # opt-in: let the conv epilogue accumulate the InstanceNorm statistics of its output
+_FUSE_STATS = [os.environ.get("BVAE_FUSE_STATS", "0") == "1"]   # opt-in: let the conv epilogue accumulate the InstanceNorm statistics of its output
                             # (measured: the extra epilogue work costs the small-channel layers what the saved
                             # statistics pass gains -- 56.6 vs 54.4 ms/step -- so it is off by default)
 
