@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbarvae.so")
+LIB_PATH = os.environ.get("BVAE_LIB_PATH") or os.path.join(_HERE, "libbarvae.so")    # (override: A/B builds of the library)
 MAX_TAPS = 16
 MAX_PHASES = 6
 IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2

@@ -2543,7 +2543,10 @@ __global__ void __launch_bounds__(CLT, CL_MINB) nb_cl_bwd_kernel(const bvae_nb_d
 // 30-50 % of their time; here a CTA owns MLP_NS samples, so every weight element fetched is used MLP_NS times and the
 // loads of one row are all in flight together.
 // ---------------------------------------------------------------------------------------------------
-constexpr int MLP_NS = 4;
+#ifndef BVAE_MLP_NS
+#define BVAE_MLP_NS 4
+#endif
+constexpr int MLP_NS = BVAE_MLP_NS;
 
 // hidden pre-activations: ha[j] = W1[j,:] . beta (the average pool of an instance-normalised map is beta),
 // hm[s][j] = W1[j,:] . mx[s,:].  warp per hidden unit, lanes over channels.
@@ -2738,11 +2741,13 @@ __global__ void __launch_bounds__(256) nb_mlp_bwd_kernel(int N, int HW, int C, i
   }
 }
 
-// BVAE_NB_MLP: 0 keeps the channel MLP inside the per-sample kernels; 1 (default) batches it in the backward pass of
-// the >= 512-channel small maps (measured: C1024 backward -15 %, C512 neutral, C256 and every forward slower because
-// each extra stage pays the partial second wave of 512 CTAs again); 2 batches it everywhere (forward too)
+// BVAE_NB_MLP: 0 keeps the channel MLP inside the per-sample kernels; 1 batches it in the backward pass of the >= 512-channel
+// small maps; 2 (default since round 2) batches it everywhere (forward too).  Round 1 measured 1 fastest kernel by kernel
+// (every extra stage pays the partial second wave of the per-sample CTAs again); on the final multi-stream step 2 wins end to
+// end: 40.91 ms per 512-bar step against 41.3 (1) and 42.08 (0) -- the staged kernels are shorter and leave more of the SMs to
+// the other branch's stream.
 static bool nb_mlp_batched(const bvae_nb_desc* d, int CLn, bool backward) {
-  const int v = option("BVAE_NB_MLP", 1);
+  const int v = option("BVAE_NB_MLP", 2);
   if (v == 0 || CLn != 1 || !d->has_cbam || d->C < 128) return false;
   return v == 2 || (backward && d->C >= 512);
 }
