@@ -365,8 +365,13 @@ class GemmLayer:
 
     # ---- packed operands ------------------------------------------------------------------------------
     def _key(self):
+        """identity of the fp32 master the packed operands were made from: the global epoch (anything that rewrote
+        parameters behind autograd's back: load, broadcast) and the epoch of the weight's own flat bucket (its fused Adam
+        step) -- per bucket, so that stepping ONE module (a discriminator, another model replica) does not make every other
+        module re-pack its operands"""
         w = self.weight
-        return (w.data_ptr(), w._version, _PARAM_EPOCH[0])
+        flat = getattr(w, "_bvae_flat", None)
+        return (w.data_ptr(), w._version, _PARAM_EPOCH[0], flat.epoch if flat is not None else 0)
 
     def _pack(self, rows: int, cc: int, src, perm) -> torch.Tensor:
         T = len(perm)
@@ -665,6 +670,7 @@ class FlatParams:
             self.offsets.append(off)
             off += -(-p.numel() // self.ALIGN) * self.ALIGN
         self.numel = off
+        self.epoch = 0             # bumped by every fused Adam step on this bucket (GemmLayer._key)
         self.data = torch.zeros(off, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
         self.exp_avg = self.exp_avg_sq = None
@@ -783,7 +789,7 @@ def adam_step(flat: FlatParams, lr: float, step: int, betas=(0.9, 0.999), eps: f
     _lib.check(_lib.lib().bvae_adam_step(flat.data.data_ptr(), flat.grad.data_ptr(), flat.exp_avg.data_ptr(),
                                          flat.exp_avg_sq.data_ptr(), flat.numel, lr, betas[0], betas[1], eps, step,
                                          grad_scale, _lib.stream_ptr()), "adam")
-    bump_param_epoch()
+    flat.epoch += 1
     if repack:
         repack_weights(flat)
 
@@ -797,7 +803,7 @@ def adam_step_dev(flat: FlatParams, hyper_dev: torch.Tensor, repack: bool = True
     _lib.check(_lib.lib().bvae_adam_step_dev(flat.data.data_ptr(), flat.grad.data_ptr(), flat.exp_avg.data_ptr(),
                                              flat.exp_avg_sq.data_ptr(), flat.numel, hyper_dev.data_ptr(),
                                              _lib.stream_ptr()), "adam_dev")
-    bump_param_epoch()
+    flat.epoch += 1
     if repack:
         repack_weights(flat)
 

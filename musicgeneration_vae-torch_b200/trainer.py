@@ -124,6 +124,10 @@ class GeneratorTrainer:
             self.use_graph = False
         self.graph_after = 3               # eager steps per input signature before capturing (kernel attributes, pack plan,
         self._graphs, self._graph_seen = {}, {}      # allocator warm-up all happen there)
+        # every captured graph keeps its own memory pool (~25 MB of saved activations per bar): a loader whose batches vary
+        # in size (the reference's .npz items hold different numbers of bars, agent/barGen.py:134-141) must not collect one
+        # graph per size -- only the first `max_graphs` signatures that recur are captured, everything else stays eager
+        self.max_graphs = 4
         self._hyper_dev = None
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.flat = model.flatten_parameters()
@@ -158,7 +162,7 @@ class GeneratorTrainer:
         ent = self._graphs.get(key)
         if ent is None:
             seen = self._graph_seen.get(key, 0)
-            if seen < self.graph_after:
+            if seen < self.graph_after or len(self._graphs) >= self.max_graphs:
                 self._graph_seen[key] = seen + 1
                 return None
             ent = self._capture(key, ins, dropout_masks is not None, target is not None)
