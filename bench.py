@@ -461,12 +461,11 @@ def main():
         for db in trainer.prefetch(batch for _ in range(k)):
             trainer.step_batch(db).item()
 
-    # untimed warm-up: W (>= 3) eager steps, then -- with CUDA-graph replay on (the default) -- the step that captures the
-    # graph and one replay, so that the timed region below contains replays only
+    # untimed warm-up: W (>= 3) steps; with CUDA-graph replay on (the default) the last two of them are the step that captures
+    # the graph and one replay, so that the timed region below contains replays only
     n_warm = max(3, args.warmup)
     if trainer.use_graph:
-        trainer.graph_after = n_warm
-        n_warm += 2
+        trainer.graph_after = n_warm - 2          # eager steps, then the capturing step, then one replay: W untimed steps
     for _ in range(n_warm):
         step_resident()
     sampler = ClockSampler(local)
