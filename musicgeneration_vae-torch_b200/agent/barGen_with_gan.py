@@ -11,6 +11,12 @@ per-iteration schedules:
 and the phase flipping of ``train_epoch`` (:297-305: 50 WAE epochs, then 100 GAN epochs, alternating).  Label conventions
 are the reference's (real -> fake_target, generated -> valid_target in the discriminator steps).
 
+``config.gan_schedule = "horovod"`` selects the per-iteration schedule of agent/barGen_horovod.py instead (:312-324):
+EVERY iteration a ``train_discriminator`` step of all four discriminators on one frozen-generator forward (:380-432), then a
+generator step -- ``train_wae_only`` (:510-553: the generator half of train_wae) or, in the GAN phase, ``train_add_gan``
+(:555-607: BCE x 1.1 + the three z terms + 0.8 x the two from-noise adversarial terms, two generator forwards, ONE backward
+through both) -- with its 40 / 160-epoch phase lengths (:336-341).
+
 B200 mapping: every module's parameters live in one flat fp32 bucket (engine.FlatParams) -> one fused Adam launch per
 optimiser; one process per GPU, gradients of whichever module trained are all-reduced over NCCL before its Adam step
 (``GradReducer(overlap=False)`` for the generator: its encoder runs up to three backward passes per step here, so the
@@ -35,7 +41,6 @@ from ..graph.loss.bar_loss import DLoss, Loss
 from ..graph.model_with_gan import Model
 from ..graph.z_discriminator import BarZDiscriminator, PhraseZDiscriminator
 from ..maker_bar import sample_songs
-from ..metrics import AverageMeter
 from .barGen import _Plateau
 
 
@@ -229,6 +234,7 @@ class BarGen(object):
         if self.epoch > self.pretraining_step_size:
             self.train_count += 1
         dev = self.device
+        horovod = getattr(self.config, "gan_schedule", "with_gan") == "horovod"
         meters = {k: [torch.zeros((), device=dev), 0] for k in self._opts}     # running loss sums stay on the device
 
         def upd(name):
@@ -245,6 +251,14 @@ class BarGen(object):
             fake_target = torch.zeros(note.size(0), device=dev)
             if self.epoch <= self.pretraining_step_size:
                 self.train_pretrain(note, pre_note, pre_phrase, position, upd("generator"))
+            elif horovod:                                   # agent/barGen_horovod.py:312-324
+                self.train_discriminator(note, pre_note, pre_phrase, position, upd("z_discriminator_bar"),
+                                         upd("z_discriminator_phrase"), upd("discriminator"),
+                                         upd("discriminator_feature"), fake_target, valid_target)
+                if self.flag_gan:
+                    self.train_add_gan(note, pre_note, pre_phrase, position, upd("generator"), valid_target)
+                else:
+                    self.train_wae_only(note, pre_note, pre_phrase, position, upd("generator"), valid_target)
             elif self.flag_gan:
                 self.train_gan(note, pre_note, pre_phrase, position, upd("generator"), upd("discriminator"),
                                upd("discriminator_feature"), fake_target, valid_target, curr_it)
@@ -252,9 +266,10 @@ class BarGen(object):
                 self.train_wae(note, pre_note, pre_phrase, position, upd("generator"), upd("z_discriminator_bar"),
                                upd("z_discriminator_phrase"), fake_target, valid_target, curr_it)
 
-        if self.flag_gan and self.train_count >= 100:
+        gan_len, wae_len = (160, 40) if horovod else (100, 50)      # barGen_horovod.py:336-341 / barGen_with_gan.py:297-305
+        if self.flag_gan and self.train_count >= gan_len:
             self.flag_gan, self.train_count = not self.flag_gan, 0
-        elif not self.flag_gan and self.train_count >= 50:
+        elif not self.flag_gan and self.train_count >= wae_len:
             self.flag_gan, self.train_count = not self.flag_gan, 0
 
         # epoch means, identical on every rank (one all-reduce of 10 numbers), then the plateau schedulers (:337-342)
@@ -369,6 +384,78 @@ class BarGen(object):
         d_note_fake = self.discriminator(torch.cat((pre_note, gen_note), dim=2)).view(-1)
         loss = self.loss_disc(d_note_fake, valid_target)
         loss = loss + self.loss_disc(self.discriminator_feature(gen_z).view(-1), valid_target)
+        loss.backward()
+        self.opt_generator.step()
+        avg_generator_loss(loss)
+        return gen_note[:3]
+
+    # ---- the per-iteration schedule of agent/barGen_horovod.py ------------------------------------------------
+    def train_discriminator(self, note, pre_note, pre_phrase, position, avg_barZ_disc_loss, avg_phraseZ_disc_loss,
+                            avg_discriminator_loss, avg_feature_discriminator_loss, fake_target, valid_target):
+        """agent/barGen_horovod.py:380-432: one frozen-generator forward feeds all four discriminators"""
+        self._modes(set(self._opts))
+        dev = note.device
+        discs = (self.discriminator, self.discriminator_feature, self.z_discriminator_bar, self.z_discriminator_phrase)
+        opts = (self.opt_discriminator, self.opt_discriminator_feature, self.opt_Zdiscriminator_bar,
+                self.opt_Zdiscriminator_phrase)
+        for o in opts:
+            o.zero_grad()
+        for m in discs:
+            free(m)
+        frozen(self.generator)
+        gen_note, z, pre_z, phrase_feature, gen_z = self.generator(note, pre_note, pre_phrase, position)
+        phrase_fake = torch.randn(phrase_feature.size(0), phrase_feature.size(1), device=dev) * self.config.sigma
+        phraseZ = self.loss_phrase(self.z_discriminator_phrase(phrase_feature).view(-1), fake_target) + \
+            self.loss_phrase(self.z_discriminator_phrase(phrase_fake).view(-1), valid_target)
+        bar_fake = torch.randn(z.size(0), z.size(1), device=dev) * self.config.sigma
+        barZ = self.loss_bar(self.z_discriminator_bar(z).view(-1), fake_target) + \
+            self.loss_bar(self.z_discriminator_bar(bar_fake).view(-1), valid_target)
+        note_loss = self.loss_disc(self.discriminator(torch.cat((pre_note, note), dim=2)).view(-1), fake_target) + \
+            self.loss_disc(self.discriminator(torch.cat((pre_note, gen_note), dim=2)).view(-1), valid_target)
+        feat_loss = self.loss_disc(self.discriminator_feature(z).view(-1), fake_target) + \
+            self.loss_disc(self.discriminator_feature(gen_z).view(-1), valid_target)
+        for l in (phraseZ, barZ, note_loss, feat_loss):
+            l.backward()
+        for o in (self.opt_Zdiscriminator_bar, self.opt_Zdiscriminator_phrase, self.opt_discriminator,
+                  self.opt_discriminator_feature):
+            o.step()
+        avg_barZ_disc_loss(barZ)
+        avg_phraseZ_disc_loss(phraseZ)
+        avg_discriminator_loss(note_loss)
+        avg_feature_discriminator_loss(feat_loss)
+
+    def _generator_wae_terms(self, note, pre_note, pre_phrase, position, valid_target, bce_weight):
+        gen_note, z, pre_z, phrase_feature, _ = self.generator(note, pre_note, pre_phrase, position)
+        loss = self.loss_phrase(self.z_discriminator_phrase(phrase_feature).view(-1), valid_target)
+        loss = loss + self.loss_bar(self.z_discriminator_bar(z).view(-1), valid_target) + \
+            self.loss_bar(self.z_discriminator_bar(pre_z).view(-1), valid_target)
+        return gen_note, loss + self.loss_generator(gen_note, note, False) * bce_weight
+
+    def _generator_step_modes(self):
+        self._modes({"generator", "z_discriminator_bar", "z_discriminator_phrase"})       # :511-516,556-561
+        self.opt_generator.zero_grad()
+        free(self.generator)
+        for m in (self.z_discriminator_bar, self.z_discriminator_phrase, self.discriminator, self.discriminator_feature):
+            frozen(m)
+
+    def train_wae_only(self, note, pre_note, pre_phrase, position, avg_generator_loss, valid_target):
+        """agent/barGen_horovod.py:510-553"""
+        self._generator_step_modes()
+        gen_note, loss = self._generator_wae_terms(note, pre_note, pre_phrase, position, valid_target, 1.0)
+        loss.backward()
+        self.opt_generator.step()
+        avg_generator_loss(loss)
+        return gen_note[:3]
+
+    def train_add_gan(self, note, pre_note, pre_phrase, position, avg_generator_loss, valid_target):
+        """agent/barGen_horovod.py:555-607: reconstruction + latent terms AND the from-noise adversarial terms in one
+        backward pass through two generator forwards"""
+        self._generator_step_modes()
+        _, loss = self._generator_wae_terms(note, pre_note, pre_phrase, position, valid_target, 1.1)
+        noise = torch.randn(note.size(0), 1152, device=note.device) * 1.5
+        gen_note, gen_z = self.generator(noise, pre_note, pre_phrase, position, False)
+        loss = loss + self.loss_disc(self.discriminator(torch.cat((pre_note, gen_note), dim=2)).view(-1), valid_target) * 0.8
+        loss = loss + self.loss_disc(self.discriminator_feature(gen_z).view(-1), valid_target) * 0.8
         loss.backward()
         self.opt_generator.step()
         avg_generator_loss(loss)

@@ -30,4 +30,5 @@ class Config(object):
     packed_input = False   # loader emits bit-packed batches (data/packed.py): 32x less host->device traffic
     refiner = False        # graph/refiner.py with the one-line shape fix applied after the decoder (graph/model.py:31,41)
     micro_bars = 0         # > 0: steps over more bars run as gradient-accumulated chunks of this size (trainer.py)
+    gan_schedule = 'with_gan'   # agent.barGen_with_gan: 'with_gan' (agent/barGen_with_gan.py) or 'horovod' (agent/barGen_horovod.py)
     synthetic = False      # explicit opt-in: train on random SyntheticBars when no dataset directory exists (smoke runs)

@@ -78,7 +78,29 @@ def test_gan_agent_schedules_and_checkpoint(tmp_path):
     m = _moved(_snap(agent), s0)
     assert m["generator"] > 0 and m["discriminator"] == 0 and m["discriminator_feature"] == 0, m
 
+    # the per-iteration schedule of agent/barGen_horovod.py: all four discriminators every iteration, then the generator --
+    # in the GAN phase with two forwards and one backward (train_add_gan)
+    s0 = _snap(agent)
+    agent.train_discriminator(*batch, rec("h_barz"), rec("h_phrasez"), rec("h_disc"), rec("h_feat"), fake, valid)
+    m = _moved(_snap(agent), s0)
+    assert m["generator"] == 0 and all(m[k] > 0 for k in m if k != "generator"), m
+    s0 = _snap(agent)
+    agent.train_add_gan(*batch, rec("h_gen_gan"), valid)
+    m = _moved(_snap(agent), s0)
+    assert m["generator"] > 0 and all(m[k] == 0 for k in m if k != "generator"), m
+    s0 = _snap(agent)
+    agent.train_wae_only(*batch, rec("h_gen_wae"), valid)
+    m = _moved(_snap(agent), s0)
+    assert m["generator"] > 0 and all(m[k] == 0 for k in m if k != "generator"), m
+    assert all(v == v and abs(v) < 1e4 for v in losses.values()), losses
+    report(test="gan_agent_horovod_schedule", losses={k: v for k, v in losses.items() if k.startswith("h_")})
+
     means = agent.train_epoch()                        # a whole epoch through the dispatcher (:284-296)
+    agent.config.gan_schedule = "horovod"
+    agent.epoch = 3
+    means_h = agent.train_epoch()                      # and through the other one (barGen_horovod.py:312-324)
+    assert set(means_h) == set(agent._opts) and all(v == v for v in means_h.values())
+    agent.config.gan_schedule = "with_gan"
     assert set(means) == set(agent._opts)
     agent.save_checkpoint(Cfg.checkpoint_file, 3)
     ck = torch.load(os.path.join(str(tmp_path), Cfg.checkpoint_dir, "checkpoint.pth.tar"), weights_only=False)
