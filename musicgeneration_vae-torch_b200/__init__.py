@@ -18,7 +18,7 @@ def install_dropin():
                  "graph.encodingBlock", "graph.weights_initializer", "graph.loss", "graph.loss.bar_loss",
                  "graph.model_with_gan", "graph.z_discriminator", "graph.bar_discriminator_with_feature",
                  "graph.bar_discriminator", "graph.refiner",
-                 "data", "data.bar_dataset", "config", "agent", "agent.barGen", "agent.barGen_with_gan", "maker_bar"):
+                 "data", "data.bar_dataset", "config", "agent", "agent.barGen", "agent.barGen_with_gan", "maker_bar", "main"):
         try:
             sys.modules[name] = importlib.import_module(pkg + "." + name)
         except ImportError:

@@ -54,3 +54,22 @@ def test_make_batch_layouts():
     packed_items = [P.pack_item(ds[0]), P.pack_item(ds[2])]
     pb2 = B.make_batch(s, packed_items)                       # items already stored as bits
     assert torch.equal(pb2.bits, pb.bits) and torch.equal(pb2.position, pb.position)
+
+
+def test_main_entry_overrides_and_missing_dataset(tmp_path, monkeypatch):
+    """main.py (reference main.py:7-12): Config overrides from the command line; a missing dataset directory is an error
+    unless synthetic data is asked for explicitly -- checked up to the point where a GPU would be needed"""
+    import pytest
+    main = pkg("main")
+    with pytest.raises(SystemExit):
+        main.main(["--set", "no_such_attribute=1"])
+    BarGen = pkg("agent.barGen").BarGen
+    Config = pkg("config").Config
+
+    class Cfg(Config):
+        root_path = str(tmp_path)
+
+    import torch
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    with pytest.raises(FileNotFoundError):
+        BarGen(Cfg())
