@@ -2741,6 +2741,598 @@ __global__ void __launch_bounds__(256) nb_mlp_bwd_kernel(int N, int HW, int C, i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Small maps, round 3: "wide" kernels (nbs_*) for H*W <= 128 and C = 256 / 512 / 1024 with fp32 raw input.
+// The per-sample nb_cl_* kernels above are latency bound on these sites (ncu: 60-75 % of the warp samples wait on
+// the long scoreboard with 14-24 resident warps per SM, 3-15 % of the DRAM peak): one 128-thread CTA walks a sample
+// through five barrier-separated phases, each a chain of dependent L2 round trips, with shared-memory atomics (64-bit
+// CAS loops for the arg-max keys) in between.  Here
+//   * a thread owns FOUR channels (one 16-byte fp32 / 8-byte bf16 access per pixel) whose per-channel constants live
+//     in registers; a warp covers 128 consecutive channels of one pixel; the 8 warps of a CTA are CW = C/128 channel
+//     warps x 8/CW pixel lanes, and every pixel loop issues the loads of 2-4 pixels before the first use;
+//   * per-pixel reductions over channels are one warp shuffle tree plus CW partials in shared memory, per-channel
+//     reductions over pixels are registers plus one partial per pixel lane in shared memory -- every slot has exactly
+//     one writer and the partials are summed in a fixed order: no atomics, deterministic by construction;
+//   * the statistics kernel is not per sample at all: a CTA owns (sample, 128 channels), its warps split the pixels.
+// Scratch layouts (nc, nc_idx, sa, cidx, gs, bwd_nc, bwd_px, bwd_h) are those of the nb_cl_* kernels, so the batched
+// channel MLP (nb_mlp_fwd / nb_mlp_bwd), the MLP weight-gradient kernels and the tests' state readers are unchanged.
+// ---------------------------------------------------------------------------------------------------
+constexpr int NBS_T = 256;
+
+__device__ __forceinline__ void nbs_unpack4(const uint2 r, float* f) {
+  f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+  f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+__device__ __forceinline__ uint2 nbs_ld4(const bf16* p) { return *reinterpret_cast<const uint2*>(p); }
+__device__ __forceinline__ void nbs_st4(bf16* p, const float* f) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
+}
+
+// forward 1: InstanceNorm statistics and coefficients.  grid (C/128, N), block 256: warp w sweeps pixels w, w+8, ...
+// EXT = false (sites without CBAM): no extrema, the pooled value is reported as the mean like nb_coef_kernel does.
+template <bool EXT>
+__global__ void __launch_bounds__(NBS_T) nbs_stats_kernel(const float* __restrict__ y, int y_pitch, int HW, int C,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float eps, float* __restrict__ nc, int32_t* __restrict__ nc_idx) {
+  __shared__ float4 s_sum[8][32], s_sq[8][32];
+  __shared__ ulonglong2 s_kx[EXT ? 8 : 1][64], s_kn[EXT ? 8 : 1][64];
+  const int n = blockIdx.y, cb = blockIdx.x * 128;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* base = y + (int64_t)n * HW * y_pitch + cb + lane * 4;
+  const float4 sh4 = __ldg(reinterpret_cast<const float4*>(base));          // pixel 0: the shift of the shifted sums
+  const float sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+  float sum[4], sq[4], vmx[4], vmn[4];
+  int imx[4], imn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
+  for (int p0 = w; p0 < HW; p0 += 32) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + 8 * u;
+      if (p < HW) v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * y_pitch));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + 8 * u;
+      if (p < HW) {
+        const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float dl = f[i] - sh[i];
+          sum[i] += dl; sq[i] += dl * dl;
+          if (EXT) {
+            if (f[i] > vmx[i]) { vmx[i] = f[i]; imx[i] = p; }      // p ascends inside a thread: strict > keeps the first
+            if (f[i] < vmn[i]) { vmn[i] = f[i]; imn[i] = p; }
+          }
+        }
+      }
+    }
+  }
+  s_sum[w][lane] = make_float4(sum[0], sum[1], sum[2], sum[3]);
+  s_sq[w][lane] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+  if (EXT) {
+    u64 kx[4], kn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {       // warps that saw no pixel contribute the neutral key 0
+      kx[i] = vmx[i] == -INFINITY ? 0ull : make_key(vmx[i], (uint32_t)imx[i]);
+      kn[i] = vmn[i] == INFINITY ? 0ull : make_key(-vmn[i], (uint32_t)imn[i]);
+    }
+    s_kx[w][lane * 2] = make_ulonglong2(kx[0], kx[1]); s_kx[w][lane * 2 + 1] = make_ulonglong2(kx[2], kx[3]);
+    s_kn[w][lane * 2] = make_ulonglong2(kn[0], kn[1]); s_kn[w][lane * 2 + 1] = make_ulonglong2(kn[2], kn[3]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int cl = threadIdx.x, c = cb + cl;
+    float tsum = 0.f, tsq = 0.f;
+    u64 kx = 0, kn = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {                                         // fixed order: deterministic
+      tsum += reinterpret_cast<const float*>(&s_sum[ww][0])[cl];
+      tsq += reinterpret_cast<const float*>(&s_sq[ww][0])[cl];
+      if (EXT) {
+        const u64 a = reinterpret_cast<const u64*>(&s_kx[ww][0])[cl], b = reinterpret_cast<const u64*>(&s_kn[ww][0])[cl];
+        kx = a > kx ? a : kx;
+        kn = b > kn ? b : kn;
+      }
+    }
+    const float inv = 1.f / (float)HW;
+    const float shift = __ldg(y + (int64_t)n * HW * y_pitch + c);
+    const float md = tsum * inv;
+    const float mean = shift + md;
+    const float var = fmaxf(tsq * inv - md * md, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma[c], b0 = beta[c];
+    const float a = g * rstd, b = b0 - mean * a;
+    float yext = mean;
+    uint32_t idx = 0;
+    if (EXT) {
+      if (a >= 0.f) { yext = key_val(kx); idx = key_idx(kx); }
+      else { yext = -key_val(kn); idx = key_idx(kn); }
+    }
+    const float ext_uhat = (yext - mean) * rstd;
+    const float ext_u = g * ext_uhat + b0;
+    const int64_t o = (int64_t)n * C + c;
+    float4* q = reinterpret_cast<float4*>(nc + o * NC_W);
+    q[0] = make_float4(mean, rstd, a, b);
+    q[1] = make_float4(1.f, ext_u, ext_uhat, 0.f);                           // {gc, ext_u, ext_uhat, -}
+    nc_idx[o] = (int32_t)idx;
+  }
+}
+
+// 3x3 attention conv on the [mean, max] map held in shared memory (zero padding), one pixel; same order as sa_conv
+__device__ __forceinline__ float nbs_sa_conv(const float2* s_sa, const float* s_w, int H, int W, int py, int px) {
+  float q = 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int yy = py + ky - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int xx = px + kx - 1;
+      if (xx < 0 || xx >= W) continue;
+      const float2 v = s_sa[yy * W + xx];
+      q += s_w[ky * 3 + kx] * v.x + s_w[9 + ky * 3 + kx] * v.y;
+    }
+  }
+  return q;
+}
+
+// forward 2 (after the batched channel MLP on CBAM sites): one CTA per sample.
+//   without CBAM: uhat, out = act(u) in one sweep.
+//   with CBAM:    sweep 1 writes uhat and the per-pixel mean / max / arg-max over channels of u*gc; the 3x3 gate conv
+//                 runs from shared memory; sweep 2 re-reads the raw tile (L1/L2) and writes out = act(r + u*gc*gs).
+// MODE = res_mode of the CBAM sites (1 self, 2 external, 3 none); ignored without CBAM.
+template <bool CBAM, int MODE>
+__global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d) {
+  __shared__ float s_ps[CBAM ? 128 : 1][8];
+  __shared__ u64 s_pk[CBAM ? 128 : 1][8];
+  __shared__ float2 s_sa[CBAM ? 128 : 1];
+  __shared__ float s_gs[CBAM ? 128 : 1];
+  __shared__ float s_w[18];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, CW = C >> 7, PLn = 8 / CW;
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  float h_r[4], h_nm[4], h_a[4], h_b[4], h_gc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4* q = reinterpret_cast<const float4*>(d.nc + ((int64_t)n * C + c + i) * NC_W);
+    const float4 lo = __ldg(q);                                              // {mean, rstd, a, b}
+    h_r[i] = lo.y; h_nm[i] = -lo.x * lo.y; h_a[i] = lo.z; h_b[i] = lo.w;
+    h_gc[i] = CBAM ? __ldg(q + 1).x : 1.f;
+  }
+  if (CBAM && t < 18) s_w[t] = d.wsp[t];
+  const float slope = d.slope;
+  const int y_pitch = d.y_pitch, out_pitch = d.out_pitch;
+  const float* yb = (const float*)d.y + (int64_t)n * HW * y_pitch + c;
+  bf16* ub = d.uhat != nullptr ? (bf16*)d.uhat + (int64_t)n * HW * C + c : nullptr;
+  bf16* ob = (bf16*)d.out + (int64_t)n * HW * out_pitch + c;
+
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) v[u] = __ldg(reinterpret_cast<const float4*>(yb + (int64_t)p * y_pitch));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;                     // warp-uniform: the shuffles below are safe inside the branch
+      if (p < HW) {
+        const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float uh[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) uh[i] = fmaf(f[i], h_r[i], h_nm[i]);
+        if (ub != nullptr) nbs_st4(ub + (int64_t)p * C, uh);                 // inference: nothing is saved
+        if (CBAM) {
+          float sum = 0.f, mx = -INFINITY;
+          int mxc = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float u1 = fmaf(h_a[i], f[i], h_b[i]) * h_gc[i];
+            sum += u1;
+            if (u1 > mx) { mx = u1; mxc = c + i; }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+            if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+          }
+          if (lane == 0) { s_ps[p][cwi] = sum; s_pk[p][cwi] = make_key(mx, (uint32_t)mxc); }
+        } else {
+          float o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] = act_fwd(fmaf(h_a[i], f[i], h_b[i]), slope);
+          nbs_st4(ob + (int64_t)p * out_pitch, o);
+        }
+      }
+    }
+  }
+  if (!CBAM) return;
+  __syncthreads();
+  if (t < HW) {
+    float s = 0.f;
+    u64 k = 0;
+    for (int j = 0; j < CW; ++j) { s += s_ps[t][j]; const u64 o = s_pk[t][j]; k = o > k ? o : k; }
+    const float2 v = make_float2(s / (float)C, key_val(k));
+    s_sa[t] = v;
+    const int64_t o = (int64_t)n * HW + t;
+    reinterpret_cast<float2*>(d.sa)[o] = v;
+    d.cidx[o] = (int32_t)key_idx(k);
+  }
+  __syncthreads();
+  if (t < HW) {
+    const float g = 1.f / (1.f + expf(-nbs_sa_conv(s_sa, s_w, H, W, t / W, t % W)));
+    s_gs[t] = g;
+    d.gs[(int64_t)n * HW + t] = g;
+  }
+  __syncthreads();
+  const int res_pitch = d.res_pitch;
+  const bf16* rb = MODE == 2 ? (const bf16*)d.res + (int64_t)n * HW * res_pitch + c : nullptr;
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    float4 v[4];
+    uint2 rr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(yb + (int64_t)p * y_pitch));
+        if (MODE == 2) rr[u] = nbs_ld4(rb + (int64_t)p * res_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        const float g = s_gs[p];
+        float r[4], o[4];
+        if (MODE == 2) nbs_unpack4(rr[u], r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float uu = fmaf(h_a[i], f[i], h_b[i]);
+          const float k = h_gc[i] * g;
+          const float tt = MODE == 1 ? fmaf(uu, k, uu) : (MODE == 2 ? fmaf(uu, k, r[i]) : uu * k);
+          o[i] = act_fwd(tt, slope);
+        }
+        nbs_st4(ob + (int64_t)p * out_pitch, o);
+      }
+    }
+  }
+}
+
+// backward 1 (CBAM sites): the reduction sweeps of one sample.  Sweep 1: dgs[p] = sum_c ds*u*gc, dgc[c] += sum_p ds*u*gs;
+// then dq, the 3x3 transpose conv (dmean, dmax) and the attention-conv weight gradient from shared memory; sweep 2:
+// S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u, dres.  Output: bwd_nc = {dgc, S1, S2, 0}, bwd_px = {dq, dmean/C, dmax, 0}
+// (consumed by nb_mlp_bwd_kernel and nbs_bwd2_kernel).
+template <int MODE>
+__global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d) {
+  __shared__ float s_pp[128][8];
+  __shared__ float4 s_red[3][256];              // [sum][pixel lane * (C/4) + channel quad]: PLn * C/4 == 256
+  __shared__ float s_gs[128], s_dq[128], s_dmean[128], s_dmax[128];
+  __shared__ int s_cidx[128];
+  __shared__ float s_w[18], s_dw[18];
+  const int C = d.C, H = d.H, W = d.W, HW = H * W, CW = C >> 7, PLn = 8 / CW;
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const float slope = d.slope;
+  float h_g[4], h_b[4], h_gc[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h_g[i] = __ldg(d.gamma + c + i); h_b[i] = __ldg(d.beta + c + i);
+    h_gc[i] = __ldg(d.nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
+  }
+  if (t < HW) { s_gs[t] = d.gs[(int64_t)n * HW + t]; s_cidx[t] = d.cidx[(int64_t)n * HW + t]; }
+  if (t < 18) { s_w[t] = d.wsp[t]; s_dw[t] = 0.f; }
+  __syncthreads();
+  const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dres_pitch = d.dres_pitch;
+  const bf16* ub = (const bf16*)d.uhat + (int64_t)n * HW * C + c;
+  const bf16* ob = (const bf16*)d.out + (int64_t)n * HW * out_pitch + c;
+  const bf16* db = (const bf16*)d.dout + (int64_t)n * HW * dout_pitch + c;
+  bf16* rb = (MODE == 2 && d.dres != nullptr) ? (bf16*)d.dres + (int64_t)n * HW * dres_pitch + c : nullptr;
+
+  float acc[4], a1[4], a2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { acc[i] = 0.f; a1[i] = 0.f; a2[i] = 0.f; }
+  // ---- sweep 1
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    uint2 ru[4], ro[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        ru[u] = nbs_ld4(ub + (int64_t)p * C);
+        ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
+        rd[u] = nbs_ld4(db + (int64_t)p * dout_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;                     // warp-uniform
+      if (p < HW) {
+        float uh[4], o[4], dd[4];
+        nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
+        const float g = s_gs[p];
+        float dgs = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          const float tt = ds * fmaf(h_g[i], uh[i], h_b[i]);
+          dgs += tt * h_gc[i];
+          acc[i] += tt * g;
+        }
+        dgs = warp_sum(dgs);
+        if (lane == 0) s_pp[p][cwi] = dgs;
+      }
+    }
+  }
+  __syncthreads();
+  if (t < HW) {
+    float dgs = 0.f;
+    for (int j = 0; j < CW; ++j) dgs += s_pp[t][j];
+    const float g = s_gs[t];
+    s_dq[t] = dgs * g * (1.f - g);
+  }
+  __syncthreads();
+  // ---- 3x3 transpose conv of dq and the attention-conv weight gradient (warps 0..3 take part in the warp sums)
+  if (t < 128) {
+    float part[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) part[i] = 0.f;
+    if (t < HW) {
+      const float* sa_n = d.sa + (int64_t)n * HW * 2;
+      const int py = t / W, px = t % W;
+      const float dq = s_dq[t];
+      float dmean = 0.f, dmax = 0.f;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = py - (ky - 1), xx = px - (kx - 1);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const float dqq = s_dq[yy * W + xx];
+            dmean += s_w[ky * 3 + kx] * dqq;
+            dmax += s_w[9 + ky * 3 + kx] * dqq;
+          }
+          const int y2 = py + ky - 1, x2 = px + kx - 1;
+          if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W) {
+            const float2 v = *reinterpret_cast<const float2*>(sa_n + ((int64_t)y2 * W + x2) * 2);
+            part[ky * 3 + kx] += dq * v.x;
+            part[9 + ky * 3 + kx] += dq * v.y;
+          }
+        }
+      dmean /= (float)C;
+      s_dmean[t] = dmean;
+      s_dmax[t] = dmax;
+      reinterpret_cast<float4*>(d.bwd_px)[(int64_t)n * HW + t] = make_float4(dq, dmean, dmax, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+      const float v = warp_sum(part[i]);
+      if (lane == 0 && v != 0.f) atomicAdd(&s_dw[i], v);
+    }
+  }
+  __syncthreads();
+  if (t < 18) atomicAdd(d.dwsp + t, s_dw[t]);
+  // ---- sweep 2 (the sample's tensors come back from L1 / L2)
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    uint2 ru[4], ro[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        ru[u] = nbs_ld4(ub + (int64_t)p * C);
+        ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
+        rd[u] = nbs_ld4(db + (int64_t)p * dout_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        float uh[4], o[4], dd[4], dsv[4];
+        nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
+        const float g = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
+        const int ci = s_cidx[p];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          dsv[i] = ds;
+          const float dsp = dm + ((c + i) == ci ? dx : 0.f);           // grad wrt u*gc from the spatial branch
+          const float v = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * g + dsp * h_gc[i];
+          a1[i] += v;
+          a2[i] += v * uh[i];
+          acc[i] += dsp * fmaf(h_g[i], uh[i], h_b[i]);
+        }
+        if (rb != nullptr) nbs_st4(rb + (int64_t)p * dres_pitch, dsv);
+      }
+    }
+  }
+  const int slot = pl * (C >> 2) + (c >> 2);
+  s_red[0][slot] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  s_red[1][slot] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+  s_red[2][slot] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+  __syncthreads();
+  for (int cc = t; cc < C; cc += NBS_T) {
+    float dgc = 0.f, S1 = 0.f, S2 = 0.f;
+    for (int j = 0; j < PLn; ++j) {                                     // fixed order
+      dgc += reinterpret_cast<const float*>(&s_red[0][0])[j * C + cc];
+      S1 += reinterpret_cast<const float*>(&s_red[1][0])[j * C + cc];
+      S2 += reinterpret_cast<const float*>(&s_red[2][0])[j * C + cc];
+    }
+    *reinterpret_cast<float4*>(d.bwd_nc + ((int64_t)n * C + cc) * BN_W) = make_float4(dgc, S1, S2, 0.f);
+  }
+}
+
+// backward 2 (CBAM sites, after nb_mlp_bwd_kernel): dy = a*du + [p == argmax] a*d_mx - a*m1 - uhat*(a*m2)
+template <int MODE>
+__global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d) {
+  __shared__ float s_gs[128], s_dmean[128], s_dmax[128];
+  __shared__ int s_cidx[128];
+  const int C = d.C, HW = d.H * d.W, CW = C >> 7, PLn = 8 / CW;
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const float slope = d.slope;
+  float h_gc[4], h_a[4], h_m1[4], h_m2[4], h_dmx[4];
+  int h_idx[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t o = (int64_t)n * C + c + i;
+    const float4* q = reinterpret_cast<const float4*>(d.nc + o * NC_W);
+    h_a[i] = __ldg(q).z; h_gc[i] = __ldg(q + 1).x;
+    const float4 bw = *reinterpret_cast<const float4*>(d.bwd_nc + o * BN_W);     // {dv, a*m1, a*m2, a*d_mx}
+    h_m1[i] = bw.y; h_m2[i] = bw.z; h_dmx[i] = bw.w;
+    h_idx[i] = d.nc_idx[o];
+  }
+  if (t < HW) {
+    const int64_t o = (int64_t)n * HW + t;
+    s_gs[t] = d.gs[o]; s_cidx[t] = d.cidx[o];
+    const float4 v = reinterpret_cast<const float4*>(d.bwd_px)[o];               // {dq, dmean / C, dmax, -}
+    s_dmean[t] = v.y; s_dmax[t] = v.z;
+  }
+  __syncthreads();
+  const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dy_pitch = d.dy_pitch;
+  const bf16* ub = (const bf16*)d.uhat + (int64_t)n * HW * C + c;
+  const bf16* ob = (const bf16*)d.out + (int64_t)n * HW * out_pitch + c;
+  const bf16* db = (const bf16*)d.dout + (int64_t)n * HW * dout_pitch + c;
+  bf16* yb = (bf16*)d.dy + (int64_t)n * HW * dy_pitch + c;
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    uint2 ru[4], ro[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        ru[u] = nbs_ld4(ub + (int64_t)p * C);
+        ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
+        rd[u] = nbs_ld4(db + (int64_t)p * dout_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        float uh[4], o[4], dd[4], r[4];
+        nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
+        const float g = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
+        const int ci = s_cidx[p];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          const float dsp = dm + ((c + i) == ci ? dx : 0.f);
+          const float du = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * g + dsp * h_gc[i];
+          const float extra = (p == h_idx[i]) ? h_dmx[i] : 0.f;
+          r[i] = h_a[i] * du + extra - h_m1[i] - uh[i] * h_m2[i];
+        }
+        nbs_st4(yb + (int64_t)p * dy_pitch, r);
+      }
+    }
+  }
+}
+
+// backward of a site without CBAM, one CTA per sample: S1 = sum du, S2 = sum du*uhat (du = dout * act'), dgamma / dbeta,
+// then dy = a*(du - S1/HW - uhat*S2/HW) from the re-read tile.
+__global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_desc d) {
+  __shared__ float4 s_red[2][256];
+  __shared__ float s_m1[1024], s_m2[1024];
+  const int C = d.C, HW = d.H * d.W, CW = C >> 7, PLn = 8 / CW;
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const float slope = d.slope;
+  const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dy_pitch = d.dy_pitch;
+  const bf16* ub = (const bf16*)d.uhat + (int64_t)n * HW * C + c;
+  const bf16* ob = (const bf16*)d.out + (int64_t)n * HW * out_pitch + c;
+  const bf16* db = (const bf16*)d.dout + (int64_t)n * HW * dout_pitch + c;
+  bf16* yb = (bf16*)d.dy + (int64_t)n * HW * dy_pitch + c;
+  float a1[4], a2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    uint2 ru[4], ro[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        ru[u] = nbs_ld4(ub + (int64_t)p * C);
+        ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
+        rd[u] = nbs_ld4(db + (int64_t)p * dout_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        float uh[4], o[4], dd[4];
+        nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float du = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          a1[i] += du;
+          a2[i] += du * uh[i];
+        }
+      }
+    }
+  }
+  const int slot = pl * (C >> 2) + (c >> 2);
+  s_red[0][slot] = make_float4(a1[0], a1[1], a1[2], a1[3]);
+  s_red[1][slot] = make_float4(a2[0], a2[1], a2[2], a2[3]);
+  __syncthreads();
+  const float inv = 1.f / (float)HW;
+  for (int cc = t; cc < C; cc += NBS_T) {
+    float S1 = 0.f, S2 = 0.f;
+    for (int j = 0; j < PLn; ++j) {
+      S1 += reinterpret_cast<const float*>(&s_red[0][0])[j * C + cc];
+      S2 += reinterpret_cast<const float*>(&s_red[1][0])[j * C + cc];
+    }
+    atomicAdd(d.dbeta + cc, S1);
+    atomicAdd(d.dgamma + cc, S2);
+    const float a = d.nc[((int64_t)n * C + cc) * NC_W + NC_A];
+    s_m1[cc] = a * S1 * inv;
+    s_m2[cc] = a * S2 * inv;
+  }
+  __syncthreads();
+  float h_a[4], h_m1[4], h_m2[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h_a[i] = d.nc[((int64_t)n * C + c + i) * NC_W + NC_A];
+    h_m1[i] = s_m1[c + i]; h_m2[i] = s_m2[c + i];
+  }
+  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+    uint2 ru[4], ro[4], rd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        ru[u] = nbs_ld4(ub + (int64_t)p * C);
+        ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
+        rd[u] = nbs_ld4(db + (int64_t)p * dout_pitch);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int p = p0 + u * PLn;
+      if (p < HW) {
+        float uh[4], o[4], dd[4], r[4];
+        nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float du = dd[i] * (o[i] > 0.f ? 1.f : slope);
+          r[i] = h_a[i] * du - h_m1[i] - uh[i] * h_m2[i];
+        }
+        nbs_st4(yb + (int64_t)p * dy_pitch, r);
+      }
+    }
+  }
+}
+
+// BVAE_NB_SMALL (default 1): the nbs_* kernels on the small maps they cover.  Any non-default BVAE_NB_MODE / BVAE_NB_MLP
+// selects the per-sample nb_cl_* / nb_small_* kernels there, which stay as their reference implementation.
+static bool nbs_enabled(const bvae_nb_desc* d) {
+  if (option("BVAE_NB_SMALL", 1) == 0 || option("BVAE_NB_MODE", 0) != 0 || option("BVAE_NB_MLP", 2) != 2) return false;
+  return d->H * d->W <= 128 && (d->C == 256 || d->C == 512 || d->C == 1024);
+}
+
 // BVAE_NB_MLP: 0 keeps the channel MLP inside the per-sample kernels; 1 batches it in the backward pass of the >= 512-channel
 // small maps; 2 (default since round 2) batches it everywhere (forward too).  Round 1 measured 1 fastest kernel by kernel
 // (every extra stage pays the partial second wave of the per-sample CTAs again); on the final multi-stream step 2 wins end to
@@ -2860,6 +3452,29 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
   const bool det = sync_det();
   BVAE_REQUIRE(!d->stats_fused || !(use_nb_cluster(d) || nb_small_ok(d)), BVAE_ERR_UNSUPPORTED,
                "nb_forward: fused statistics are only consumed by the tiled path (H*W > 128)");
+  if (nbs_enabled(d) && d->y_f32 && !d->stats_fused) {
+    // small maps: statistics + coefficients -> batched channel MLP -> one per-sample kernel for everything else
+    dim3 gs(C / 128, N);
+    if (d->has_cbam)
+      nbs_stats_kernel<true><<<gs, NBS_T, 0, st>>>((const float*)d->y, d->y_pitch, HW, C, d->gamma, d->beta, d->eps, d->nc,
+                                                   d->nc_idx);
+    else
+      nbs_stats_kernel<false><<<gs, NBS_T, 0, st>>>((const float*)d->y, d->y_pitch, HW, C, d->gamma, d->beta, d->eps, d->nc,
+                                                    d->nc_idx);
+    if ((rc = check_launch("nbs_stats"))) return rc;
+    if (!d->has_cbam) {
+      nbs_fwd_kernel<false, 0><<<N, NBS_T, 0, st>>>(*d);
+      return check_launch("nbs_fwd");
+    }
+    BVAE_REQUIRE(d->res_mode >= 1 && d->res_mode <= 3, BVAE_ERR_SHAPE, "nb_forward: CBAM needs res_mode 1..3");
+    nb_mlp_fwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + MLP_NS) * C * sizeof(float), st>>>(N, C, d->Cr, d->w1, d->w2,
+                                                                                                 d->beta, d->nc);
+    if ((rc = check_launch("nb_mlp_fwd"))) return rc;
+    if (d->res_mode == 1) nbs_fwd_kernel<true, 1><<<N, NBS_T, 0, st>>>(*d);
+    else if (d->res_mode == 2) nbs_fwd_kernel<true, 2><<<N, NBS_T, 0, st>>>(*d);
+    else nbs_fwd_kernel<true, 3><<<N, NBS_T, 0, st>>>(*d);
+    return check_launch("nbs_fwd");
+  }
   if (use_nb_cluster(d)) {
     static bool attr = false;
     if (!attr) {
@@ -2999,6 +3614,31 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   BVAE_REQUIRE(d->dout_pitch % 8 == 0 && d->dy_pitch % 8 == 0, BVAE_ERR_ALIGN, "nb_backward: pitches % 8 != 0");
   BVAE_REQUIRE(d->uhat != nullptr, BVAE_ERR_SHAPE, "nb_backward: uhat is NULL (the forward pass ran in inference mode)");
   const int N = d->N, HW = d->H * d->W, C = d->C;
+  if (nbs_enabled(d)) {
+    if (!d->has_cbam) {
+      nbs_bwd_plain_kernel<<<N, NBS_T, 0, st>>>(*d);
+      return check_launch("nbs_bwd_plain");
+    }
+    BVAE_REQUIRE(d->res_mode >= 1 && d->res_mode <= 3, BVAE_ERR_SHAPE, "nb_backward: CBAM needs res_mode 1..3");
+    static bool attr_s = false;
+    if (!attr_s) {
+      cudaFuncSetAttribute(nb_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (1 + 2 * MLP_NS) * 1024 * 4);
+      attr_s = true;
+    }
+    // reduction sweeps -> batched channel-MLP backward + InstanceNorm coefficients -> dy sweep -> MLP weight gradients
+    if (d->res_mode == 1) nbs_bwd1_kernel<1><<<N, NBS_T, 0, st>>>(*d);
+    else if (d->res_mode == 2) nbs_bwd1_kernel<2><<<N, NBS_T, 0, st>>>(*d);
+    else nbs_bwd1_kernel<3><<<N, NBS_T, 0, st>>>(*d);
+    if ((rc = check_launch("nbs_bwd1"))) return rc;
+    nb_mlp_bwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + 2 * MLP_NS) * C * sizeof(float), st>>>(
+        N, HW, C, d->Cr, d->w1, d->w2, d->beta, d->nc, d->bwd_nc, d->bwd_h, d->dgamma, d->dbeta);
+    if ((rc = check_launch("nb_mlp_bwd"))) return rc;
+    if (d->res_mode == 1) nbs_bwd2_kernel<1><<<N, NBS_T, 0, st>>>(*d);
+    else if (d->res_mode == 2) nbs_bwd2_kernel<2><<<N, NBS_T, 0, st>>>(*d);
+    else nbs_bwd2_kernel<3><<<N, NBS_T, 0, st>>>(*d);
+    if ((rc = check_launch("nbs_bwd2"))) return rc;
+    return launch_bwd_w(d, st);
+  }
   if (use_nb_cluster(d)) {
     static bool attr = false;
     if (!attr) {

@@ -151,7 +151,7 @@ def _torch_block(y, gamma, beta, cb, res_mode, slope, res):
 
 
 @pytest.mark.parametrize("C,H,W", [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60),
-                                   (64, 48, 30), (64, 192, 30)])
+                                   (64, 48, 30), (64, 192, 30), (256, 12, 8), (512, 24, 4), (1024, 12, 2)])
 @pytest.mark.parametrize("mode", ["plain", "self", "ext"])
 @pytest.mark.parametrize("raw", ["f32", "bf16"])
 def test_norm_block(C, H, W, mode, raw):
@@ -184,17 +184,19 @@ def test_kernel_variants_contractions(opt):
     assert lib.load().bvae_get_option(opt[0].encode(), -7) == -7
 
 
-NB_VARIANTS = [("BVAE_NB_MLP", 0), ("BVAE_NB_MLP", 2), ("BVAE_NB_MODE", 1), ("BVAE_NB_MODE", 2), ("BVAE_NB_SPLIT", 0),
-               ("BVAE_NB_FAST", 0)]
+NB_VARIANTS = [("BVAE_NB_MLP", 0), ("BVAE_NB_MLP", 1), ("BVAE_NB_MODE", 1), ("BVAE_NB_MODE", 2), ("BVAE_NB_SPLIT", 0),
+               ("BVAE_NB_FAST", 0), ("BVAE_NB_SMALL", 0)]
 
 
 @pytest.mark.parametrize("opt", NB_VARIANTS, ids=lambda o: "%s=%d" % o)
 def test_kernel_variants_norm_blocks(opt):
     """channel MLP inside / outside the per-sample kernels, cluster and per-sample kernels on every map size, unsplit
-    reduction sweeps, the generic (non-restructured) sweeps: all shapes and residual modes of test_norm_block"""
+    reduction sweeps, the generic (non-restructured) sweeps, the per-sample small-map kernels with the batched MLP
+    (BVAE_NB_SMALL=0: the round-2 default; any other non-default BVAE_NB_MLP / BVAE_NB_MODE selects them too): all shapes
+    and residual modes of test_norm_block"""
     lib = pkg("_lib")
     with lib.option(*opt):
-        for C, H, W in [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60)]:
+        for C, H, W in [(32, 48, 30), (64, 12, 8), (128, 24, 15), (512, 6, 4), (1024, 3, 2), (64, 96, 60), (256, 12, 8)]:
             for mode in ("plain", "self", "ext"):
                 _run_norm_block(C, H, W, mode, "f32")
 
