@@ -69,7 +69,7 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync(int group = 0) { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
 }
@@ -148,6 +148,24 @@ __device__ __forceinline__ void umma_f16_steps(uint32_t tmem_d, uint64_t adesc, 
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// ---- 2-CTA cluster helpers (wgrad_tc_kernel with TMA multicast of the shared operand)
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the box lands at the same shared-memory offset of every CTA in `mask`, and each of them gets the complete_tx on its own
+// barrier at the same offset
+__device__ __forceinline__ void tma_load_4d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                               int c3, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+// like umma_commit, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
@@ -383,8 +401,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // BRES: the whole weight operand (all taps x K chunks of the single N tile) is loaded ONCE per CTA and stays resident in
 // shared memory; the pipeline then streams activation tiles only (small-channel layers are L2-bandwidth bound and the
 // weights were a third of their traffic).
+// Narrow tiles (BN <= 64) have main loops of 0.2-0.6 us while one pass of the epilogue (accumulator wait, tcgen05.ld, two
+// named barriers, slab write, TMA store) takes about 1.5 us (measured: 23 040 tiles of 32->32 3x3 at 512 bars in 246 us
+// = 1.58 us per tile and SM at 3 % tensor-pipe and 30 % DRAM utilisation).  They therefore get TWO epilogue groups of four
+// warps (384 threads): group g drains accumulator buffer g, i.e. the CTA's even / odd tiles, through its own pair of output
+// slabs and its own named barrier, so two epilogues run concurrently next to the main loop of a third tile.
+template <int BN>
+struct ConvTc2Cfg {
+  static constexpr int EG = BN <= 64 ? 2 : 1;            // epilogue groups
+  static constexpr int THREADS = 128 + 128 * EG;
+};
+
 template <int KB, int BN, int STAGES, bool BRES>
-__global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(ConvTc2Cfg<BN>::THREADS, 1) conv_tc2_kernel(const __grid_constant__ ConvTcParams p) {
+  constexpr int EG = ConvTc2Cfg<BN>::EG;
   constexpr int A_BYTES = 128 * KB * 2;
   constexpr int B_BYTES = BN * KB * 2;
   constexpr int STAGE_BYTES = BRES ? A_BYTES : A_BYTES + B_BYTES;
@@ -523,13 +553,17 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
     }
   } else if (warp >= 4) {
     // ---------------- epilogue warps: TMEM -> registers -> global ----------------
-    const int wq = warp - 4;                       // TMEM lane quarter this warp may access (= warp id % 4)
+    const int wq = warp & 3;                       // TMEM lane quarter this warp may access (= warp id % 4)
+    const uint32_t eg = (uint32_t)(warp - 4) >> 2; // epilogue group: drains accumulator buffer eg (EG == 2) or both
+    uint8_t* const yslabs = ystage + eg * 32768u;  // this group's two output slabs
+    uint32_t gsl = 0;                              // slabs this group has handed to TMA so far
     const int r = wq * 32 + lane;
     const int rows_box = p.bn * p.bh * p.bw;
     const int nn = r / (p.bh * p.bw), hh = (r / p.bw) % p.bh, ww = r % p.bw;
     uint32_t ti = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++ti) {
       const uint32_t ab = ti & 1u, aph = (ti >> 1) & 1u;
+      if (EG == 2 && ab != eg) continue;  // the other group's tile
       const int n_tile = tile % p.n_tiles;
       int m_tile = tile / p.n_tiles;
       int ph = m_tile % p.nphase; m_tile /= p.nphase;
@@ -567,15 +601,13 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
         // requests per 128x64 fp32 tile), which made the epilogue the longest stage of the small-K layers.  Rows and
         // columns outside the output are clipped by the store.
         const int CS = p.out_f32 ? 32 : 64;                 // columns per slab
-        const uint32_t slabs = (uint32_t)(BN / CS);
 #pragma unroll(PRE ? 2 : 1)
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tacc + (uint32_t)c0, v);
           if (c0 + 32 >= BN) { tc_fence_before(); mbar_arrive(tempty + ab); }     // accumulator drained
           const int cs0 = c0 & ~(CS - 1);                   // first column of this slab
-          const uint32_t sl = ti * slabs + (uint32_t)(cs0 / CS);
-          uint8_t* slab = ystage + (sl & 1u) * 16384u;
+          uint8_t* slab = yslabs + (gsl & 1u) * 16384u;
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
@@ -624,7 +656,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
           if (p.out_f32) {
             // the store issued from this slab buffer two slabs ago must have finished reading it
             if (r == 0) tma_store_wait_read<1>();
-            epi_bar_sync();
+            epi_bar_sync(eg);
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(row + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
@@ -632,7 +664,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
             const int half = (c0 - cs0) >> 5;               // which 64-byte half of the 128-byte row
             if (half == 0) {
               if (r == 0) tma_store_wait_read<1>();
-              epi_bar_sync();
+              epi_bar_sync(eg);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -640,11 +672,12 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
             if (half == 0) continue;                        // the slab is complete after its second half
           }
           fence_proxy_async();
-          epi_bar_sync();
+          epi_bar_sync(eg);
           if (r == 0) {
             tma_store_4d(&p.ymap[ph], slab, col0 + cs0, tw * p.bw, th * p.bh, tn * p.bn);
             tma_store_commit();
           }
+          ++gsl;
         }
         continue;
       }
@@ -750,7 +783,7 @@ __global__ void __launch_bounds__(256, 1) conv_tc2_kernel(const __grid_constant_
       mbar_arrive(tempty + ab);                    // 128 arrivals release the accumulator buffer
     }
   }
-  if (threadIdx.x == 128 && BN <= 128 && p.tma_store) tma_store_wait_all();      // thread r == 0 of the epilogue
+  if ((threadIdx.x == 128 || (EG == 2 && threadIdx.x == 256)) && BN <= 128 && p.tma_store) tma_store_wait_all();   // r == 0 of each epilogue group
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -770,6 +803,7 @@ struct alignas(64) WgradTcParams {
   int bw, bh, bn, chunks_w, chunks_h, chunks_n, nchunks, chunks_per_split, splits;
   int a_atoms;                      // 64-channel atoms of the anchor tile actually loaded (1 or 2)
   int ra_tiles, rs_tiles;
+  int mc;                           // 2: launched as 2-CTA clusters that share the shifted tile (TMA multicast); else 1
   int Ca, Cs;
   float* dw;                        // destination of the reduction (parameter gradient or packed scratch)
   long long s_ra, s_t;              // element strides of the anchor channel / the tap; the shifted channel stride is
@@ -802,11 +836,19 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // mc == 2: CTAs 2k and 2k+1 form a cluster.  They own the anchor tiles 2j and 2j+1 of the SAME (shifted tile, tap group,
+  // pixel split), so every shifted atom is needed by both: each CTA fetches every other atom and multicasts it into both
+  // shared memories (L2 -> SM bytes per 64-pixel chunk: 16 KB + 32 KB instead of 16 KB + 64 KB for NS = 256, the traffic
+  // that bounds these layers at half of the tensor peak).  A stage may be refilled only when BOTH CTAs have consumed
+  // it, so the MMA commits arrive on the empty barrier of both (count 2).
+  const bool mc = p.mc == 2;
   int b = blockIdx.x;
+  const int rank = mc ? (b & 1) : 0;
+  if (mc) b >>= 1;
   const int split = b % p.splits; b /= p.splits;
   const int tg = b % p.tap_groups; b /= p.tap_groups;
   const int rs_tile = b % p.rs_tiles;
-  const int ra_tile = b / p.rs_tiles;
+  const int ra_tile = mc ? (b / p.rs_tiles) * 2 + rank : b / p.rs_tiles;
   const int tap0 = tg * p.tpc;
   const int ntap = min(p.tpc, p.ntaps - tap0);
   const int ck0 = split * p.chunks_per_split;
@@ -817,7 +859,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, mc ? 2 : 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.amap);
@@ -826,10 +868,11 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (mc) cluster_sync_all();        // the peer's barriers are initialised and its buffer zeroed before anything is multicast
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0 && lane == 0) {
-    const uint32_t tx = (uint32_t)(rows_box * ROW_BYTES * (p.a_atoms + ntap * S_ATOMS));
+    const uint32_t tx = (uint32_t)(rows_box * ROW_BYTES * (p.a_atoms + ntap * S_ATOMS));   // bytes landing HERE (own + peer's loads)
     int it = 0;
     for (int ck = ck0; ck < ck1; ++ck, ++it) {
       int q = ck;
@@ -846,9 +889,14 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       for (int t = 0; t < ntap; ++t) {
         const int tap = tap0 + t;
         const CUtensorMap* sm = &p.smap[p.tap_view[tap]];
-        for (int a = 0; a < S_ATOMS; ++a)
-          tma_load_4d(st + (A_ATOMS + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * CB,
-                      cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn);
+        for (int a = 0; a < S_ATOMS; ++a) {
+          if (!mc)
+            tma_load_4d(st + (A_ATOMS + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * CB,
+                        cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn);
+          else if (((t * S_ATOMS + a) & 1) == rank)
+            tma_load_4d_mc(st + (A_ATOMS + t * S_ATOMS + a) * ATOM_BYTES, sm, full_bar + s, rs_tile * NS + a * CB,
+                           cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn, (uint16_t)3);
+        }
       }
     }
   } else if (warp == 1) {
@@ -878,7 +926,8 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
               umma_f16(tmem_base + (uint32_t)(t * NS), adesc + KSTEP * j, bdesc + KSTEP * j, idesc, (it | j) ? 1u : 0u);
           }
         }
-        umma_commit(empty_bar + s);
+        if (mc) umma_commit_mc(empty_bar + s, (uint16_t)3);
+        else umma_commit(empty_bar + s);
       }
       __syncwarp();
     }
@@ -914,6 +963,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();        // no CTA leaves while its peer may still arrive on its barriers
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
@@ -1278,11 +1328,12 @@ static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t str
   constexpr int B_BYTES = BN * KB * 2;
   constexpr int STAGE = BRES ? 128 * KB * 2 : 128 * KB * 2 + B_BYTES;
   constexpr int YSTAGE = BN <= 128 ? 33 * 1024 : 0;             // two output slabs of the TMA-store epilogue (+ alignment)
+  constexpr int YSTAGE2 = (ConvTc2Cfg<BN>::EG - 1) * 32 * 1024; // the second epilogue group's slabs (BN <= 64)
   constexpr int BUDGET = (BRES ? 128 * 1024 : 200 * 1024) - YSTAGE;   // resident weights take up to 72 KB of their own
   constexpr int ST_RAW = BUDGET / STAGE;
   // small-channel layers are bound by the bytes in flight per SM (8 KB stages): give them a deep ring
   constexpr int STAGES = ST_RAW > 16 ? 16 : ST_RAW;
-  const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 32 + YSTAGE;
+  const int smem = 1024 + (BRES ? P.ntaps * P.kchunks * B_BYTES : 0) + STAGES * STAGE + (2 * STAGES + 5) * 8 + 32 + YSTAGE + YSTAGE2;
   static int attr_smem = 0;
   static int num_sms = 148;
   if (smem > attr_smem) {
@@ -1294,7 +1345,7 @@ static int launch_conv2_impl(const ConvTcParams& P, long tiles, cudaStream_t str
     attr_smem = smem;
   }
   const int grid = (int)(tiles < num_sms ? tiles : num_sms);
-  conv_tc2_kernel<KB, BN, STAGES, BRES><<<grid, 256, smem, stream>>>(P);
+  conv_tc2_kernel<KB, BN, STAGES, BRES><<<grid, ConvTc2Cfg<BN>::THREADS, smem, stream>>>(P);
   note_kernel("conv_tc2_kernel<%d,%d,%d,%d>%s", KB, BN, STAGES, (int)BRES, P.halo ? "+halo" : "");
   return check_launch("conv_tc2");
 }
@@ -1455,8 +1506,24 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
     BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
     attr_done = true;
   }
-  wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
-  note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
+  if (P.mc == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<CB, NS, STAGES>, P);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cluster launch failed: %s", cudaGetErrorString(e));
+    note_kernel("wgrad_tc_kernel<%d,%d,%d>+mc2", CB, NS, STAGES);
+  } else {
+    wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
+    note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
+  }
   return check_launch("wgrad_tc");
 }
 
@@ -1608,6 +1675,12 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.ra_tiles = ceil_div(d->Ca, 128); P.rs_tiles = d->Cs / NS;
   P.a_atoms = d->Ca >= 128 ? 128 / CB : d->Ca / CB;
   P.Ca = d->Ca; P.Cs = d->Cs;
+  // BVAE_WGRAD_MC=1 (opt-in): pairs of anchor tiles as 2-CTA clusters with the shifted tile multicast (>= 256 anchor
+  // channels).  Correct (parity-tested) but not faster -- 23 launches of <64,256,2> per step 3.98 ms at 0.47 of the tensor peak
+  // against 3.84 ms at 0.50 without: halving the L2 reads does not help because every SM still RECEIVES 80 KB per 64-pixel
+  // chunk; what bounds these layers is the per-SM operand inflow, which only a cta_group::2 MMA (each SM holds half of the
+  // shifted tile) would halve.
+  P.mc = (option("BVAE_WGRAD_MC", 0) != 0 && CB == 64 && NS >= 128 && P.ra_tiles % 2 == 0) ? 2 : 1;
 
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
   bool packed = false;

@@ -3386,6 +3386,9 @@ static bool use_nb_cluster(const bvae_nb_desc* d) {
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+// Tried and dropped (round 3): sizing the grids to fill their last wave (512 samples x 2 chunks = 1024 CTAs are 2.3 waves of
+// 444 resident CTAs; 6 chunks per sample are 6.9) -- 41.0 instead of 39.4 ms per step: the extra CTAs re-load the per-channel
+// constants and triple the per-CTA atomics, and the sweeps are not wave-quantised the way a compute-bound grid is.
 static int pick_ppc(int HW, int N, int G) {
   // pixels per CTA: a multiple of the CTA's pixel-group count, sized so the grid has ~4 waves of 148 SMs
   const int pg = 8 * (32 / G);
@@ -3731,9 +3734,9 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
   } else if (fast) {
     NBF_MODES({
       nbf_bwd2_kernel<MD><<<gp, 256, C * sizeof(float), st>>>((const bf16*)d->dout, d->dout_pitch, (const bf16*)d->out,
-                                                              d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
-                                                              d->beta, d->gs, d->cidx, d->bwd_px, d->slope, (bf16*)d->dres,
-                                                              d->dres_pitch, d->bwd_nc, ppc);
+                                                               d->out_pitch, (const bf16*)d->uhat, HW, C, d->nc, d->gamma,
+                                                               d->beta, d->gs, d->cidx, d->bwd_px, d->slope, (bf16*)d->dres,
+                                                               d->dres_pitch, d->bwd_nc, ppc);
     });
   } else {
     DISPATCH_ITERS(iters, {
