@@ -815,7 +815,7 @@ struct alignas(64) WgradTcParams {
 
 // CB = channels per swizzle atom (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NS = shifted-channel tile (multiple of
 // CB, <= 256); KP = 64 pixel rows per stage
-template <int CB, int NS, int STAGES>
+template <int CB, int NS, int STAGES, bool MC = false>
 __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
   constexpr int KP = 64;
   constexpr int ROW_BYTES = CB * 2;
@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   // shared memories (L2 -> SM bytes per 64-pixel chunk: 16 KB + 32 KB instead of 16 KB + 64 KB for NS = 256, the traffic
   // that bounds these layers at half of the tensor peak).  A stage may be refilled only when BOTH CTAs have consumed
   // it, so the MMA commits arrive on the empty barrier of both (count 2).
-  const bool mc = p.mc == 2;
+  constexpr bool mc = MC;             // a template parameter: the runtime flag cost the default kernels 5-15 % (producer issue path)
   int b = blockIdx.x;
   const int rank = mc ? (b & 1) : 0;
   if (mc) b >>= 1;
@@ -1497,6 +1497,30 @@ int wgrad_tc_eligible(const bvae_wgrad_desc* d) {
 }
 
 template <int CB, int NS, int STAGES>
+static int launch_wgrad_mc(const WgradTcParams& P, int grid, cudaStream_t stream, int smem) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<CB, NS, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<CB, NS, STAGES, true>, P);
+  BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cluster launch failed: %s", cudaGetErrorString(e));
+  note_kernel("wgrad_tc_kernel<%d,%d,%d>+mc2", CB, NS, STAGES);
+  return check_launch("wgrad_tc");
+}
+
+template <int CB, int NS, int STAGES>
 static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
   constexpr int max_tpc = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
   constexpr int smem = 1024 + STAGES * (128 / CB + max_tpc * (NS / CB)) * (64 * CB * 2) + (2 * STAGES + 1) * 8 + 16;
@@ -1507,23 +1531,10 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
     attr_done = true;
   }
   if (P.mc == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(128);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc_kernel<CB, NS, STAGES>, P);
-    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cluster launch failed: %s", cudaGetErrorString(e));
-    note_kernel("wgrad_tc_kernel<%d,%d,%d>+mc2", CB, NS, STAGES);
-  } else {
-    wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
-    note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
+    if constexpr (CB == 64 && NS >= 128) return launch_wgrad_mc<CB, NS, STAGES>(P, grid, stream, smem);
   }
+  wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
+  note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
   return check_launch("wgrad_tc");
 }
 

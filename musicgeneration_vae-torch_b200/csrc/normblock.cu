@@ -2742,22 +2742,28 @@ __global__ void __launch_bounds__(256) nb_mlp_bwd_kernel(int N, int HW, int C, i
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Small maps, round 3: "wide" kernels (nbs_*) for H*W <= 128 and C = 256 / 512 / 1024 with fp32 raw input.
-// The per-sample nb_cl_* kernels above are latency bound on these sites (ncu: 60-75 % of the warp samples wait on
-// the long scoreboard with 14-24 resident warps per SM, 3-15 % of the DRAM peak): one 128-thread CTA walks a sample
-// through five barrier-separated phases, each a chain of dependent L2 round trips, with shared-memory atomics (64-bit
-// CAS loops for the arg-max keys) in between.  Here
+// Per-sample "wide" kernels (nbs_*), round 3: sites whose sample fits one CTA's sweep (H*W <= 1440, C = 32 .. 1024, fp32
+// raw input).  The per-sample nb_cl_* kernels above are latency bound (ncu on the small maps: 60-75 % of the warp samples
+// wait on the long scoreboard with 14-24 resident warps per SM, 3-15 % of the DRAM peak): one 128-thread CTA walks a
+// sample through five barrier-separated phases, each a chain of dependent L2 round trips, with shared-memory atomics
+// (64-bit CAS loops for the arg-max keys) in between; the tiled nb_* / nbf_* kernels pay 5-6 dependent launches, a memset
+// and global atomics per site, which is most of their time on the medium maps (C128 24x15: 233 us forward against a
+// 58 us traffic floor).  Here
 //   * a thread owns FOUR channels (one 16-byte fp32 / 8-byte bf16 access per pixel) whose per-channel constants live
-//     in registers; a warp covers 128 consecutive channels of one pixel; the 8 warps of a CTA are CW = C/128 channel
-//     warps x 8/CW pixel lanes, and every pixel loop issues the loads of 2-4 pixels before the first use;
-//   * per-pixel reductions over channels are one warp shuffle tree plus CW partials in shared memory, per-channel
-//     reductions over pixels are registers plus one partial per pixel lane in shared memory -- every slot has exactly
-//     one writer and the partials are summed in a fixed order: no atomics, deterministic by construction;
-//   * the statistics kernel is not per sample at all: a CTA owns (sample, 128 channels), its warps split the pixels.
+//     in registers; LPP = min(32, C/4) lanes cover a pixel's channels (or 128 of them: CW = C/128 channel warps for
+//     C > 128), so a 256-thread CTA has PLn = (8/CW) * (32/LPP) pixel lanes, and every pixel loop issues the loads of
+//     four pixels before the first use;
+//   * per-pixel reductions over channels are one shuffle tree over LPP lanes plus CW partials in shared memory,
+//     per-channel reductions over pixels are registers plus one partial per pixel lane in shared memory -- every slot
+//     has exactly one writer and the partials are summed in a fixed order: no atomics, deterministic by construction;
+//   * the statistics kernel is not per sample: a CTA owns (sample, <= 128 channels), its 8 warps split the pixels;
+//   * everything after the (batched) channel MLP is ONE kernel per sample: sweep, 3x3 gate conv from shared memory,
+//     second sweep from L1/L2 -- forward 3 launches instead of 5, backward 4 instead of 7, no memset.
 // Scratch layouts (nc, nc_idx, sa, cidx, gs, bwd_nc, bwd_px, bwd_h) are those of the nb_cl_* kernels, so the batched
 // channel MLP (nb_mlp_fwd / nb_mlp_bwd), the MLP weight-gradient kernels and the tests' state readers are unchanged.
 // ---------------------------------------------------------------------------------------------------
 constexpr int NBS_T = 256;
+constexpr int NBS_MAX_HW = 1440;
 
 __device__ __forceinline__ void nbs_unpack4(const uint2 r, float* f) {
   f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
@@ -2768,33 +2774,62 @@ __device__ __forceinline__ void nbs_st4(bf16* p, const float* f) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack2(f[0], f[1]), pack2(f[2], f[3]));
 }
 
-// forward 1: InstanceNorm statistics and coefficients.  grid (C/128, N), block 256: warp w sweeps pixels w, w+8, ...
+// thread geometry of a 256-thread CTA over a [pixels][C] tile
+struct NbsGeo {
+  int LPP;    // lanes per pixel inside a warp: min(32, C/4)
+  int CW;     // channel warps per pixel: max(1, C/128)
+  int PLn;    // pixel lanes of the CTA
+  int cwi;    // this thread's channel warp
+  int lcl;    // lane inside the pixel's lane group
+  int pl;     // this thread's pixel lane
+  int pl0;    // first pixel lane of this WARP (warp-uniform loop base)
+  int c;      // first of this thread's 4 channels
+};
+__device__ __forceinline__ NbsGeo nbs_geo(int C) {
+  NbsGeo g;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  g.LPP = C >= 128 ? 32 : (C >> 2);
+  g.CW = C >= 128 ? (C >> 7) : 1;
+  const int PPW = 32 / g.LPP;
+  g.PLn = (8 / g.CW) * PPW;
+  g.cwi = w % g.CW;
+  g.lcl = lane % g.LPP;
+  g.pl0 = (w / g.CW) * PPW;
+  g.pl = g.pl0 + lane / g.LPP;
+  g.c = g.cwi * 128 + g.lcl * 4;
+  return g;
+}
+
+// forward 1: InstanceNorm statistics and coefficients.  grid (max(1, C/128), N), block 256: the CTA owns CC = min(C, 128)
+// channels of one sample, its 8 * (128/CC) pixel lanes sweep pixels lane, lane + lanes, ...
 // EXT = false (sites without CBAM): no extrema, the pooled value is reported as the mean like nb_coef_kernel does.
 template <bool EXT>
 __global__ void __launch_bounds__(NBS_T) nbs_stats_kernel(const float* __restrict__ y, int y_pitch, int HW, int C,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float eps, float* __restrict__ nc, int32_t* __restrict__ nc_idx) {
-  __shared__ float4 s_sum[8][32], s_sq[8][32];
-  __shared__ ulonglong2 s_kx[EXT ? 8 : 1][64], s_kn[EXT ? 8 : 1][64];
+  __shared__ __align__(16) float s_sum[1024], s_sq[1024];            // [pixel lane][CC]: lanes * CC == 1024
+  __shared__ __align__(16) u64 s_kx[EXT ? 1024 : 2], s_kn[EXT ? 1024 : 2];
+  const int CC = C < 128 ? C : 128, LPP = CC >> 2, PLs = 1024 / CC;
   const int n = blockIdx.y, cb = blockIdx.x * 128;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const float* base = y + (int64_t)n * HW * y_pitch + cb + lane * 4;
+  const int lcl = lane % LPP, plane = w * (32 / LPP) + lane / LPP;
+  const float* base = y + (int64_t)n * HW * y_pitch + cb + lcl * 4;
   const float4 sh4 = __ldg(reinterpret_cast<const float4*>(base));          // pixel 0: the shift of the shifted sums
   const float sh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
   float sum[4], sq[4], vmx[4], vmn[4];
   int imx[4], imn[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { sum[i] = 0.f; sq[i] = 0.f; vmx[i] = -INFINITY; vmn[i] = INFINITY; imx[i] = 0; imn[i] = 0; }
-  for (int p0 = w; p0 < HW; p0 += 32) {
+  for (int p0 = plane; p0 < HW; p0 += 4 * PLs) {
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + 8 * u;
+      const int p = p0 + PLs * u;
       if (p < HW) v[u] = __ldg(reinterpret_cast<const float4*>(base + (int64_t)p * y_pitch));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + 8 * u;
+      const int p = p0 + PLs * u;
       if (p < HW) {
         const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
@@ -2809,29 +2844,26 @@ __global__ void __launch_bounds__(NBS_T) nbs_stats_kernel(const float* __restric
       }
     }
   }
-  s_sum[w][lane] = make_float4(sum[0], sum[1], sum[2], sum[3]);
-  s_sq[w][lane] = make_float4(sq[0], sq[1], sq[2], sq[3]);
+  const int slot = plane * CC + lcl * 4;
+  *reinterpret_cast<float4*>(s_sum + slot) = make_float4(sum[0], sum[1], sum[2], sum[3]);
+  *reinterpret_cast<float4*>(s_sq + slot) = make_float4(sq[0], sq[1], sq[2], sq[3]);
   if (EXT) {
-    u64 kx[4], kn[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {       // warps that saw no pixel contribute the neutral key 0
-      kx[i] = vmx[i] == -INFINITY ? 0ull : make_key(vmx[i], (uint32_t)imx[i]);
-      kn[i] = vmn[i] == INFINITY ? 0ull : make_key(-vmn[i], (uint32_t)imn[i]);
+    for (int i = 0; i < 4; ++i) {       // pixel lanes that saw no pixel contribute the neutral key 0
+      s_kx[slot + i] = vmx[i] == -INFINITY ? 0ull : make_key(vmx[i], (uint32_t)imx[i]);
+      s_kn[slot + i] = vmn[i] == INFINITY ? 0ull : make_key(-vmn[i], (uint32_t)imn[i]);
     }
-    s_kx[w][lane * 2] = make_ulonglong2(kx[0], kx[1]); s_kx[w][lane * 2 + 1] = make_ulonglong2(kx[2], kx[3]);
-    s_kn[w][lane * 2] = make_ulonglong2(kn[0], kn[1]); s_kn[w][lane * 2 + 1] = make_ulonglong2(kn[2], kn[3]);
   }
   __syncthreads();
-  if (threadIdx.x < 128) {
+  if ((int)threadIdx.x < CC) {
     const int cl = threadIdx.x, c = cb + cl;
     float tsum = 0.f, tsq = 0.f;
     u64 kx = 0, kn = 0;
-#pragma unroll
-    for (int ww = 0; ww < 8; ++ww) {                                         // fixed order: deterministic
-      tsum += reinterpret_cast<const float*>(&s_sum[ww][0])[cl];
-      tsq += reinterpret_cast<const float*>(&s_sq[ww][0])[cl];
+    for (int j = 0; j < PLs; ++j) {                                          // fixed order: deterministic
+      tsum += s_sum[j * CC + cl];
+      tsq += s_sq[j * CC + cl];
       if (EXT) {
-        const u64 a = reinterpret_cast<const u64*>(&s_kx[ww][0])[cl], b = reinterpret_cast<const u64*>(&s_kn[ww][0])[cl];
+        const u64 a = s_kx[j * CC + cl], b = s_kn[j * CC + cl];
         kx = a > kx ? a : kx;
         kn = b > kn ? b : kn;
       }
@@ -2883,16 +2915,20 @@ __device__ __forceinline__ float nbs_sa_conv(const float2* s_sa, const float* s_
 //   with CBAM:    sweep 1 writes uhat and the per-pixel mean / max / arg-max over channels of u*gc; the 3x3 gate conv
 //                 runs from shared memory; sweep 2 re-reads the raw tile (L1/L2) and writes out = act(r + u*gc*gs).
 // MODE = res_mode of the CBAM sites (1 self, 2 external, 3 none); ignored without CBAM.
+// dynamic smem (CBAM): u64 s_pk[HW*CW] | float2 s_sa[HW] | float s_ps[HW*CW] | float s_gs[HW]
+static size_t nbs_fwd_smem(int HW, int C) { const int CW = C >= 128 ? C / 128 : 1; return (size_t)HW * CW * 12 + (size_t)HW * 12; }
 template <bool CBAM, int MODE>
 __global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d) {
-  __shared__ float s_ps[CBAM ? 128 : 1][8];
-  __shared__ u64 s_pk[CBAM ? 128 : 1][8];
-  __shared__ float2 s_sa[CBAM ? 128 : 1];
-  __shared__ float s_gs[CBAM ? 128 : 1];
+  extern __shared__ __align__(16) unsigned char nbs_dyn[];
   __shared__ float s_w[18];
-  const int C = d.C, H = d.H, W = d.W, HW = H * W, CW = C >> 7, PLn = 8 / CW;
-  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const int C = d.C, H = d.H, W = d.W, HW = H * W;
+  const NbsGeo g = nbs_geo(C);
+  const int CW = g.CW, PLn = g.PLn, c = g.c;
+  u64* s_pk = reinterpret_cast<u64*>(nbs_dyn);
+  float2* s_sa = reinterpret_cast<float2*>(s_pk + (CBAM ? HW * CW : 0));
+  float* s_ps = reinterpret_cast<float*>(s_sa + (CBAM ? HW : 0));
+  float* s_gs = s_ps + (CBAM ? HW * CW : 0);
+  const int n = blockIdx.x, t = threadIdx.x;
   float h_r[4], h_nm[4], h_a[4], h_b[4], h_gc[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -2908,39 +2944,33 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d)
   bf16* ub = d.uhat != nullptr ? (bf16*)d.uhat + (int64_t)n * HW * C + c : nullptr;
   bf16* ob = (bf16*)d.out + (int64_t)n * HW * out_pitch + c;
 
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int pb = g.pl0; pb < HW; pb += 4 * PLn) {        // warp-uniform bounds: the shuffles below need every lane
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * PLn;
+      const int p = pb + (g.pl - g.pl0) + u * PLn;
       if (p < HW) v[u] = __ldg(reinterpret_cast<const float4*>(yb + (int64_t)p * y_pitch));
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * PLn;                     // warp-uniform: the shuffles below are safe inside the branch
-      if (p < HW) {
+      const int p = pb + (g.pl - g.pl0) + u * PLn;
+      const bool valid = p < HW;
+      if (pb + u * PLn >= HW) break;                    // warp-uniform: no lane of this warp has a pixel left
+      float sum = 0.f, mx = -INFINITY;
+      int mxc = 0;
+      if (valid) {
         const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
         float uh[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) uh[i] = fmaf(f[i], h_r[i], h_nm[i]);
         if (ub != nullptr) nbs_st4(ub + (int64_t)p * C, uh);                 // inference: nothing is saved
         if (CBAM) {
-          float sum = 0.f, mx = -INFINITY;
-          int mxc = 0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float u1 = fmaf(h_a[i], f[i], h_b[i]) * h_gc[i];
             sum += u1;
             if (u1 > mx) { mx = u1; mxc = c + i; }
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
-            const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
-            if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
-          }
-          if (lane == 0) { s_ps[p][cwi] = sum; s_pk[p][cwi] = make_key(mx, (uint32_t)mxc); }
         } else {
           float o[4];
 #pragma unroll
@@ -2948,30 +2978,39 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d)
           nbs_st4(ob + (int64_t)p * out_pitch, o);
         }
       }
+      if (CBAM) {
+        for (int o = g.LPP >> 1; o > 0; o >>= 1) {
+          sum += __shfl_xor_sync(0xffffffffu, sum, o);
+          const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+          const int omc = __shfl_xor_sync(0xffffffffu, mxc, o);
+          if (omx > mx || (omx == mx && omc < mxc)) { mx = omx; mxc = omc; }
+        }
+        if (valid && g.lcl == 0) { s_ps[p * CW + g.cwi] = sum; s_pk[p * CW + g.cwi] = make_key(mx, (uint32_t)mxc); }
+      }
     }
   }
   if (!CBAM) return;
   __syncthreads();
-  if (t < HW) {
+  for (int p = t; p < HW; p += NBS_T) {
     float s = 0.f;
     u64 k = 0;
-    for (int j = 0; j < CW; ++j) { s += s_ps[t][j]; const u64 o = s_pk[t][j]; k = o > k ? o : k; }
+    for (int j = 0; j < CW; ++j) { s += s_ps[p * CW + j]; const u64 o = s_pk[p * CW + j]; k = o > k ? o : k; }
     const float2 v = make_float2(s / (float)C, key_val(k));
-    s_sa[t] = v;
-    const int64_t o = (int64_t)n * HW + t;
+    s_sa[p] = v;
+    const int64_t o = (int64_t)n * HW + p;
     reinterpret_cast<float2*>(d.sa)[o] = v;
     d.cidx[o] = (int32_t)key_idx(k);
   }
   __syncthreads();
-  if (t < HW) {
-    const float g = 1.f / (1.f + expf(-nbs_sa_conv(s_sa, s_w, H, W, t / W, t % W)));
-    s_gs[t] = g;
-    d.gs[(int64_t)n * HW + t] = g;
+  for (int p = t; p < HW; p += NBS_T) {
+    const float gg = 1.f / (1.f + expf(-nbs_sa_conv(s_sa, s_w, H, W, p / W, p % W)));
+    s_gs[p] = gg;
+    d.gs[(int64_t)n * HW + p] = gg;
   }
   __syncthreads();
   const int res_pitch = d.res_pitch;
   const bf16* rb = MODE == 2 ? (const bf16*)d.res + (int64_t)n * HW * res_pitch + c : nullptr;
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int p0 = g.pl; p0 < HW; p0 += 4 * PLn) {
     float4 v[4];
     uint2 rr[4];
 #pragma unroll
@@ -2987,13 +3026,13 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d)
       const int p = p0 + u * PLn;
       if (p < HW) {
         const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-        const float g = s_gs[p];
+        const float gg = s_gs[p];
         float r[4], o[4];
         if (MODE == 2) nbs_unpack4(rr[u], r);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float uu = fmaf(h_a[i], f[i], h_b[i]);
-          const float k = h_gc[i] * g;
+          const float k = h_gc[i] * gg;
           const float tt = MODE == 1 ? fmaf(uu, k, uu) : (MODE == 2 ? fmaf(uu, k, r[i]) : uu * k);
           o[i] = act_fwd(tt, slope);
         }
@@ -3007,16 +3046,23 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_fwd_kernel(const bvae_nb_desc d)
 // then dq, the 3x3 transpose conv (dmean, dmax) and the attention-conv weight gradient from shared memory; sweep 2:
 // S1 = sum du, S2 = sum du*uhat, dgc += sum dsp*u, dres.  Output: bwd_nc = {dgc, S1, S2, 0}, bwd_px = {dq, dmean/C, dmax, 0}
 // (consumed by nb_mlp_bwd_kernel and nbs_bwd2_kernel).
+// dynamic smem: float s_pp[HW*CW] | s_gs[HW] | s_dq[HW] | s_dmean[HW] | s_dmax[HW] | int s_cidx[HW]
+static size_t nbs_bwd1_smem(int HW, int C) { const int CW = C >= 128 ? C / 128 : 1; return (size_t)HW * CW * 4 + (size_t)HW * 20; }
 template <int MODE>
 __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d) {
-  __shared__ float s_pp[128][8];
+  extern __shared__ __align__(16) unsigned char nbs_dyn[];
   __shared__ float4 s_red[3][256];              // [sum][pixel lane * (C/4) + channel quad]: PLn * C/4 == 256
-  __shared__ float s_gs[128], s_dq[128], s_dmean[128], s_dmax[128];
-  __shared__ int s_cidx[128];
   __shared__ float s_w[18], s_dw[18];
-  const int C = d.C, H = d.H, W = d.W, HW = H * W, CW = C >> 7, PLn = 8 / CW;
-  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const int C = d.C, H = d.H, W = d.W, HW = H * W;
+  const NbsGeo g = nbs_geo(C);
+  const int CW = g.CW, PLn = g.PLn, c = g.c;
+  float* s_pp = reinterpret_cast<float*>(nbs_dyn);
+  float* s_gs = s_pp + HW * CW;
+  float* s_dq = s_gs + HW;
+  float* s_dmean = s_dq + HW;
+  float* s_dmax = s_dmean + HW;
+  int* s_cidx = reinterpret_cast<int*>(s_dmax + HW);
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31;
   const float slope = d.slope;
   float h_g[4], h_b[4], h_gc[4];
 #pragma unroll
@@ -3024,7 +3070,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
     h_g[i] = __ldg(d.gamma + c + i); h_b[i] = __ldg(d.beta + c + i);
     h_gc[i] = __ldg(d.nc + ((int64_t)n * C + c + i) * NC_W + NC_GC);
   }
-  if (t < HW) { s_gs[t] = d.gs[(int64_t)n * HW + t]; s_cidx[t] = d.cidx[(int64_t)n * HW + t]; }
+  for (int p = t; p < HW; p += NBS_T) { s_gs[p] = d.gs[(int64_t)n * HW + p]; s_cidx[p] = d.cidx[(int64_t)n * HW + p]; }
   if (t < 18) { s_w[t] = d.wsp[t]; s_dw[t] = 0.f; }
   __syncthreads();
   const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dres_pitch = d.dres_pitch;
@@ -3037,11 +3083,11 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
 #pragma unroll
   for (int i = 0; i < 4; ++i) { acc[i] = 0.f; a1[i] = 0.f; a2[i] = 0.f; }
   // ---- sweep 1
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int pb = g.pl0; pb < HW; pb += 4 * PLn) {        // warp-uniform bounds (shuffles)
     uint2 ru[4], ro[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * PLn;
+      const int p = pb + (g.pl - g.pl0) + u * PLn;
       if (p < HW) {
         ru[u] = nbs_ld4(ub + (int64_t)p * C);
         ro[u] = nbs_ld4(ob + (int64_t)p * out_pitch);
@@ -3050,41 +3096,43 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int p = p0 + u * PLn;                     // warp-uniform
-      if (p < HW) {
+      const int p = pb + (g.pl - g.pl0) + u * PLn;
+      const bool valid = p < HW;
+      if (pb + u * PLn >= HW) break;                    // warp-uniform
+      float dgs = 0.f;
+      if (valid) {
         float uh[4], o[4], dd[4];
         nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
-        const float g = s_gs[p];
-        float dgs = 0.f;
+        const float gg = s_gs[p];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
           const float tt = ds * fmaf(h_g[i], uh[i], h_b[i]);
           dgs += tt * h_gc[i];
-          acc[i] += tt * g;
+          acc[i] += tt * gg;
         }
-        dgs = warp_sum(dgs);
-        if (lane == 0) s_pp[p][cwi] = dgs;
       }
+      for (int o = g.LPP >> 1; o > 0; o >>= 1) dgs += __shfl_xor_sync(0xffffffffu, dgs, o);
+      if (valid && g.lcl == 0) s_pp[p * CW + g.cwi] = dgs;
     }
   }
   __syncthreads();
-  if (t < HW) {
+  for (int p = t; p < HW; p += NBS_T) {
     float dgs = 0.f;
-    for (int j = 0; j < CW; ++j) dgs += s_pp[t][j];
-    const float g = s_gs[t];
-    s_dq[t] = dgs * g * (1.f - g);
+    for (int j = 0; j < CW; ++j) dgs += s_pp[p * CW + j];
+    const float gg = s_gs[p];
+    s_dq[p] = dgs * gg * (1.f - gg);
   }
   __syncthreads();
-  // ---- 3x3 transpose conv of dq and the attention-conv weight gradient (warps 0..3 take part in the warp sums)
-  if (t < 128) {
+  // ---- 3x3 transpose conv of dq and the attention-conv weight gradient
+  {
     float part[18];
 #pragma unroll
     for (int i = 0; i < 18; ++i) part[i] = 0.f;
-    if (t < HW) {
-      const float* sa_n = d.sa + (int64_t)n * HW * 2;
-      const int py = t / W, px = t % W;
-      const float dq = s_dq[t];
+    const float* sa_n = d.sa + (int64_t)n * HW * 2;
+    for (int p = t; p < HW; p += NBS_T) {
+      const int py = p / W, px = p % W;
+      const float dq = s_dq[p];
       float dmean = 0.f, dmax = 0.f;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
@@ -3104,20 +3152,22 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
           }
         }
       dmean /= (float)C;
-      s_dmean[t] = dmean;
-      s_dmax[t] = dmax;
-      reinterpret_cast<float4*>(d.bwd_px)[(int64_t)n * HW + t] = make_float4(dq, dmean, dmax, 0.f);
+      s_dmean[p] = dmean;
+      s_dmax[p] = dmax;
+      reinterpret_cast<float4*>(d.bwd_px)[(int64_t)n * HW + p] = make_float4(dq, dmean, dmax, 0.f);
     }
+    if (t < ((HW + 31) & ~31)) {                        // whole warps: the ones that own at least one pixel
 #pragma unroll
-    for (int i = 0; i < 18; ++i) {
-      const float v = warp_sum(part[i]);
-      if (lane == 0 && v != 0.f) atomicAdd(&s_dw[i], v);
+      for (int i = 0; i < 18; ++i) {
+        const float v = warp_sum(part[i]);
+        if (lane == 0 && v != 0.f) atomicAdd(&s_dw[i], v);
+      }
     }
   }
   __syncthreads();
   if (t < 18) atomicAdd(d.dwsp + t, s_dw[t]);
   // ---- sweep 2 (the sample's tensors come back from L1 / L2)
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int p0 = g.pl; p0 < HW; p0 += 4 * PLn) {
     uint2 ru[4], ro[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -3134,14 +3184,14 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
       if (p < HW) {
         float uh[4], o[4], dd[4], dsv[4];
         nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
-        const float g = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
+        const float gg = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
         const int ci = s_cidx[p];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
           dsv[i] = ds;
           const float dsp = dm + ((c + i) == ci ? dx : 0.f);           // grad wrt u*gc from the spatial branch
-          const float v = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * g + dsp * h_gc[i];
+          const float v = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * gg + dsp * h_gc[i];
           a1[i] += v;
           a2[i] += v * uh[i];
           acc[i] += dsp * fmaf(h_g[i], uh[i], h_b[i]);
@@ -3150,7 +3200,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
       }
     }
   }
-  const int slot = pl * (C >> 2) + (c >> 2);
+  const int slot = g.pl * (C >> 2) + (c >> 2);
   s_red[0][slot] = make_float4(acc[0], acc[1], acc[2], acc[3]);
   s_red[1][slot] = make_float4(a1[0], a1[1], a1[2], a1[3]);
   s_red[2][slot] = make_float4(a2[0], a2[1], a2[2], a2[3]);
@@ -3167,13 +3217,18 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd1_kernel(const bvae_nb_desc d
 }
 
 // backward 2 (CBAM sites, after nb_mlp_bwd_kernel): dy = a*du + [p == argmax] a*d_mx - a*m1 - uhat*(a*m2)
+// dynamic smem: float s_gs[HW] | s_dmean[HW] | s_dmax[HW] | int s_cidx[HW]
 template <int MODE>
 __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d) {
-  __shared__ float s_gs[128], s_dmean[128], s_dmax[128];
-  __shared__ int s_cidx[128];
-  const int C = d.C, HW = d.H * d.W, CW = C >> 7, PLn = 8 / CW;
-  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  extern __shared__ __align__(16) unsigned char nbs_dyn[];
+  const int C = d.C, HW = d.H * d.W;
+  const NbsGeo g = nbs_geo(C);
+  const int PLn = g.PLn, c = g.c;
+  float* s_gs = reinterpret_cast<float*>(nbs_dyn);
+  float* s_dmean = s_gs + HW;
+  float* s_dmax = s_dmean + HW;
+  int* s_cidx = reinterpret_cast<int*>(s_dmax + HW);
+  const int n = blockIdx.x, t = threadIdx.x;
   const float slope = d.slope;
   float h_gc[4], h_a[4], h_m1[4], h_m2[4], h_dmx[4];
   int h_idx[4];
@@ -3186,11 +3241,11 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d
     h_m1[i] = bw.y; h_m2[i] = bw.z; h_dmx[i] = bw.w;
     h_idx[i] = d.nc_idx[o];
   }
-  if (t < HW) {
-    const int64_t o = (int64_t)n * HW + t;
-    s_gs[t] = d.gs[o]; s_cidx[t] = d.cidx[o];
+  for (int p = t; p < HW; p += NBS_T) {
+    const int64_t o = (int64_t)n * HW + p;
+    s_gs[p] = d.gs[o]; s_cidx[p] = d.cidx[o];
     const float4 v = reinterpret_cast<const float4*>(d.bwd_px)[o];               // {dq, dmean / C, dmax, -}
-    s_dmean[t] = v.y; s_dmax[t] = v.z;
+    s_dmean[p] = v.y; s_dmax[p] = v.z;
   }
   __syncthreads();
   const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dy_pitch = d.dy_pitch;
@@ -3198,7 +3253,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d
   const bf16* ob = (const bf16*)d.out + (int64_t)n * HW * out_pitch + c;
   const bf16* db = (const bf16*)d.dout + (int64_t)n * HW * dout_pitch + c;
   bf16* yb = (bf16*)d.dy + (int64_t)n * HW * dy_pitch + c;
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int p0 = g.pl; p0 < HW; p0 += 4 * PLn) {
     uint2 ru[4], ro[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -3215,13 +3270,13 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d
       if (p < HW) {
         float uh[4], o[4], dd[4], r[4];
         nbs_unpack4(ru[u], uh); nbs_unpack4(ro[u], o); nbs_unpack4(rd[u], dd);
-        const float g = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
+        const float gg = s_gs[p], dm = s_dmean[p], dx = s_dmax[p];
         const int ci = s_cidx[p];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float ds = dd[i] * (o[i] > 0.f ? 1.f : slope);
           const float dsp = dm + ((c + i) == ci ? dx : 0.f);
-          const float du = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * g + dsp * h_gc[i];
+          const float du = (MODE == 1 ? ds : 0.f) + ds * h_gc[i] * gg + dsp * h_gc[i];
           const float extra = (p == h_idx[i]) ? h_dmx[i] : 0.f;
           r[i] = h_a[i] * du + extra - h_m1[i] - uh[i] * h_m2[i];
         }
@@ -3236,9 +3291,10 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd2_kernel(const bvae_nb_desc d
 __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_desc d) {
   __shared__ float4 s_red[2][256];
   __shared__ float s_m1[1024], s_m2[1024];
-  const int C = d.C, HW = d.H * d.W, CW = C >> 7, PLn = 8 / CW;
-  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int cwi = w % CW, pl = w / CW, c = cwi * 128 + lane * 4;
+  const int C = d.C, HW = d.H * d.W;
+  const NbsGeo g = nbs_geo(C);
+  const int PLn = g.PLn, c = g.c;
+  const int n = blockIdx.x, t = threadIdx.x;
   const float slope = d.slope;
   const int dout_pitch = d.dout_pitch, out_pitch = d.out_pitch, dy_pitch = d.dy_pitch;
   const bf16* ub = (const bf16*)d.uhat + (int64_t)n * HW * C + c;
@@ -3248,7 +3304,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_d
   float a1[4], a2[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int p0 = g.pl; p0 < HW; p0 += 4 * PLn) {
     uint2 ru[4], ro[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -3274,7 +3330,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_d
       }
     }
   }
-  const int slot = pl * (C >> 2) + (c >> 2);
+  const int slot = g.pl * (C >> 2) + (c >> 2);
   s_red[0][slot] = make_float4(a1[0], a1[1], a1[2], a1[3]);
   s_red[1][slot] = make_float4(a2[0], a2[1], a2[2], a2[3]);
   __syncthreads();
@@ -3298,7 +3354,7 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_d
     h_a[i] = d.nc[((int64_t)n * C + c + i) * NC_W + NC_A];
     h_m1[i] = s_m1[c + i]; h_m2[i] = s_m2[c + i];
   }
-  for (int p0 = pl; p0 < HW; p0 += 4 * PLn) {
+  for (int p0 = g.pl; p0 < HW; p0 += 4 * PLn) {
     uint2 ru[4], ro[4], rd[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -3326,11 +3382,18 @@ __global__ void __launch_bounds__(NBS_T, 4) nbs_bwd_plain_kernel(const bvae_nb_d
   }
 }
 
-// BVAE_NB_SMALL (default 1): the nbs_* kernels on the small maps they cover.  Any non-default BVAE_NB_MODE / BVAE_NB_MLP
-// selects the per-sample nb_cl_* / nb_small_* kernels there, which stay as their reference implementation.
+// BVAE_NB_SMALL (default 1): the nbs_* kernels on the sites they cover; BVAE_NB_SMALL_HW / BVAE_NB_SMALL_N are the largest
+// map (pixels) and the smallest sample count that take them above 128 pixels (one CTA per sample needs enough samples to
+// fill the machine; maps of <= 128 pixels always qualify: their alternative is one CTA per sample as well).  Any non-default
+// BVAE_NB_MODE / BVAE_NB_MLP selects the nb_cl_* / nb_small_* / tiled kernels, which stay as the reference implementations.
 static bool nbs_enabled(const bvae_nb_desc* d) {
   if (option("BVAE_NB_SMALL", 1) == 0 || option("BVAE_NB_MODE", 0) != 0 || option("BVAE_NB_MLP", 2) != 2) return false;
-  return d->H * d->W <= 128 && (d->C == 256 || d->C == 512 || d->C == 1024);
+  const int HW = d->H * d->W, C = d->C;
+  if (C < 32 || C > 1024 || (C & (C - 1)) != 0) return false;
+  if (HW <= 128) return C >= 256;
+  int max_hw = option("BVAE_NB_SMALL_HW", 512);
+  if (max_hw > NBS_MAX_HW) max_hw = NBS_MAX_HW;
+  return HW <= max_hw && d->N >= option("BVAE_NB_SMALL_N", 256);
 }
 
 // BVAE_NB_MLP: 0 keeps the channel MLP inside the per-sample kernels; 1 batches it in the backward pass of the >= 512-channel
@@ -3457,7 +3520,7 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
                "nb_forward: fused statistics are only consumed by the tiled path (H*W > 128)");
   if (nbs_enabled(d) && d->y_f32 && !d->stats_fused) {
     // small maps: statistics + coefficients -> batched channel MLP -> one per-sample kernel for everything else
-    dim3 gs(C / 128, N);
+    dim3 gs(C >= 128 ? C / 128 : 1, N);
     if (d->has_cbam)
       nbs_stats_kernel<true><<<gs, NBS_T, 0, st>>>((const float*)d->y, d->y_pitch, HW, C, d->gamma, d->beta, d->eps, d->nc,
                                                    d->nc_idx);
@@ -3473,9 +3536,10 @@ extern "C" int bvae_nb_forward(const bvae_nb_desc* d, void* stream_) {
     nb_mlp_fwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + MLP_NS) * C * sizeof(float), st>>>(N, C, d->Cr, d->w1, d->w2,
                                                                                                  d->beta, d->nc);
     if ((rc = check_launch("nb_mlp_fwd"))) return rc;
-    if (d->res_mode == 1) nbs_fwd_kernel<true, 1><<<N, NBS_T, 0, st>>>(*d);
-    else if (d->res_mode == 2) nbs_fwd_kernel<true, 2><<<N, NBS_T, 0, st>>>(*d);
-    else nbs_fwd_kernel<true, 3><<<N, NBS_T, 0, st>>>(*d);
+    const size_t smf = nbs_fwd_smem(HW, C);
+    if (d->res_mode == 1) nbs_fwd_kernel<true, 1><<<N, NBS_T, smf, st>>>(*d);
+    else if (d->res_mode == 2) nbs_fwd_kernel<true, 2><<<N, NBS_T, smf, st>>>(*d);
+    else nbs_fwd_kernel<true, 3><<<N, NBS_T, smf, st>>>(*d);
     return check_launch("nbs_fwd");
   }
   if (use_nb_cluster(d)) {
@@ -3629,16 +3693,17 @@ extern "C" int bvae_nb_backward(const bvae_nb_desc* d, void* stream_) {
       attr_s = true;
     }
     // reduction sweeps -> batched channel-MLP backward + InstanceNorm coefficients -> dy sweep -> MLP weight gradients
-    if (d->res_mode == 1) nbs_bwd1_kernel<1><<<N, NBS_T, 0, st>>>(*d);
-    else if (d->res_mode == 2) nbs_bwd1_kernel<2><<<N, NBS_T, 0, st>>>(*d);
-    else nbs_bwd1_kernel<3><<<N, NBS_T, 0, st>>>(*d);
+    const size_t sm1 = nbs_bwd1_smem(HW, C), sm2 = (size_t)HW * 16;
+    if (d->res_mode == 1) nbs_bwd1_kernel<1><<<N, NBS_T, sm1, st>>>(*d);
+    else if (d->res_mode == 2) nbs_bwd1_kernel<2><<<N, NBS_T, sm1, st>>>(*d);
+    else nbs_bwd1_kernel<3><<<N, NBS_T, sm1, st>>>(*d);
     if ((rc = check_launch("nbs_bwd1"))) return rc;
     nb_mlp_bwd_kernel<<<ceil_div(N, MLP_NS), 256, (size_t)(1 + 2 * MLP_NS) * C * sizeof(float), st>>>(
         N, HW, C, d->Cr, d->w1, d->w2, d->beta, d->nc, d->bwd_nc, d->bwd_h, d->dgamma, d->dbeta);
     if ((rc = check_launch("nb_mlp_bwd"))) return rc;
-    if (d->res_mode == 1) nbs_bwd2_kernel<1><<<N, NBS_T, 0, st>>>(*d);
-    else if (d->res_mode == 2) nbs_bwd2_kernel<2><<<N, NBS_T, 0, st>>>(*d);
-    else nbs_bwd2_kernel<3><<<N, NBS_T, 0, st>>>(*d);
+    if (d->res_mode == 1) nbs_bwd2_kernel<1><<<N, NBS_T, sm2, st>>>(*d);
+    else if (d->res_mode == 2) nbs_bwd2_kernel<2><<<N, NBS_T, sm2, st>>>(*d);
+    else nbs_bwd2_kernel<3><<<N, NBS_T, sm2, st>>>(*d);
     if ((rc = check_launch("nbs_bwd2"))) return rc;
     return launch_bwd_w(d, st);
   }

@@ -204,6 +204,17 @@ def test_kernel_variants_norm_blocks(opt):
                 _run_norm_block(C, H, W, mode, "f32")
 
 
+@pytest.mark.parametrize("C,H,W", [(32, 48, 30), (64, 48, 30), (128, 24, 15), (256, 24, 15), (128, 96, 15), (64, 20, 13),
+                                   (32, 16, 9), (128, 12, 11)])
+@pytest.mark.parametrize("mode", ["plain", "self", "ext"])
+def test_norm_block_per_sample_kernels(C, H, W, mode):
+    """the per-sample nbs_* kernels on every channel count / lane geometry they take at training batch sizes (32 and 64
+    channels: several pixels per warp; maps up to 1440 pixels), forced here at 3 samples; same bounds as test_norm_block"""
+    lib = pkg("_lib")
+    with lib.option("BVAE_NB_SMALL_N", 1), lib.option("BVAE_NB_SMALL_HW", 1440):
+        _run_norm_block(C, H, W, mode, "f32")
+
+
 def _run_norm_block(C, H, W, mode, raw):
     eng = pkg("engine")
     torch.manual_seed(C + H)

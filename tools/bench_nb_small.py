@@ -1,6 +1,7 @@
 """Small-map norm sites (H*W <= 128, 256..1024 channels): forward / backward time of one site with the wide nbs_*
-kernels (BVAE_NB_SMALL=1, default) against the per-sample nb_cl_* kernels (BVAE_NB_SMALL=0), CUDA events, one JSON line
-per (site, mode).  usage: bench_nb_small.py [B]   (B = bars per step; the phrase-encoder sites run 2 x B samples)"""
+kernels (BVAE_NB_SMALL=1 with BVAE_NB_SMALL_HW=1440: every site here takes them) against the round-2 kernels
+(BVAE_NB_SMALL=0: nb_cl_* up to 128 pixels, the tiled nb_* / nbf_* sweeps above), CUDA events, one JSON line per (site, mode).
+usage: bench_nb_small.py [B [CxHxW ...]]   (B = bars per step)"""
 import importlib
 import json
 import math
@@ -16,8 +17,11 @@ eng = importlib.import_module(PKG + ".engine")
 lib = importlib.import_module(PKG + "._lib")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 dev = "cuda"
-# (C, H, W, samples): bar encoder 12x8 / 6x4 / 3x2, phrase encoder 24x4 / 12x2 (twice the samples)
-SITES = [(256, 12, 8, B), (512, 6, 4, B), (1024, 3, 2, B), (512, 24, 4, 2 * B), (1024, 12, 2, 2 * B)]
+# (C, H, W, samples): the norm sites of the model with <= 1440 pixels (tools/prof_sites.py lists them)
+SITES = [(256, 12, 8, B), (512, 6, 4, B), (1024, 3, 2, B), (512, 24, 4, B), (1024, 12, 2, B), (512, 12, 7, B), (1024, 6, 3, B),
+         (128, 24, 15, B), (256, 24, 15, B), (256, 48, 8, B), (32, 48, 30, B), (64, 48, 30, B), (128, 48, 30, B), (128, 96, 15, B)]
+if len(sys.argv) > 2:
+    SITES = [tuple(int(v) for v in a.split("x")) + (B,) for a in sys.argv[2:]]
 
 
 def run(C, H, W, N, mode, reps=20):
@@ -53,10 +57,11 @@ def run(C, H, W, N, mode, reps=20):
 
 
 for C, H, W, N in SITES:
-    for mode in ("plain", "self", "ext"):
+    for mode in ("plain", "ext"):
         with lib.option("BVAE_NB_SMALL", 0):
             f0, b0, o0, d0 = run(C, H, W, N, mode)
-        f1, b1, o1, d1 = run(C, H, W, N, mode)
+        with lib.option("BVAE_NB_SMALL_HW", 1440):
+            f1, b1, o1, d1 = run(C, H, W, N, mode)
         elems = N * H * W * C
         print(json.dumps({"site": "C%d %dx%d N%d %s" % (C, H, W, N, mode),
                           "fwd_us": {"nb_cl": round(f0, 1), "nbs": round(f1, 1)},
