@@ -1543,18 +1543,35 @@ static int wgrad_halo_mode() {
   return option("BVAE_WGRAD_HALO", 1);
 }
 
-static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_tiles, bool* packed_) {
-  // pixel splits: aim at ~2 waves of 148 CTAs and pick the candidate that fills its last wave best
+// acc_cols = accumulator columns a CTA drains in its epilogue (0: the halo kernel, which keeps the fill heuristic)
+static void wgrad_finish(const bvae_wgrad_desc* d, WgradTcParams* P, int out_tiles, bool* packed_, int acc_cols = 0) {
   const int max_splits = ceil_div(P->nchunks, 8);
   int splits = 1;
-  const int centre = ceil_div(148 * 2, out_tiles);
-  double best_fill = -1.0;
-  for (int sp = (centre > 3 ? centre - 2 : 1); sp <= centre + 2; ++sp) {
-    if (sp > max_splits) break;
-    const long ctas = (long)out_tiles * sp;
-    const long waves = (ctas + 147) / 148;
-    const double fill = (double)ctas / (double)(waves * 148);
-    if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
+  if (acc_cols > 0 && option("BVAE_WGRAD_SPLITS", 1) != 0) {
+    // Pixel splits from a cost model (round 3).  ncu on 512->512 3x3 at 6x4 x 512 bars (40 output tiles x 7 splits = 280 CTAs,
+    // 28 chunks each, 85 us): a CTA spends only ~55 % of its 42 us in the K loop (0.8 us per 64-pixel chunk); zeroing the
+    // ring, TMEM allocation, the pipeline fill and above all the epilogue -- 128 x 512 fp32 as vector atomics, not overlapped
+    // with anything because the tile owns all of TMEM -- are a fixed ~24 chunk-equivalents, paid once per WAVE.  The old rule
+    // (fill ~2 waves) bought its fill with a second round of fixed costs and 2-3x the atomic traffic.
+    const double fixed = 8.0 + 16.0 * (double)acc_cols / 512.0;
+    double best = 1e30;
+    for (int sp = 1; sp <= max_splits && sp <= 128; ++sp) {
+      const int cps = ceil_div(P->nchunks, sp), rsp = ceil_div(P->nchunks, cps);
+      const long ctas = (long)out_tiles * rsp, waves = (ctas + 147) / 148;
+      const double cost = (double)waves * (fixed + (double)cps);
+      if (cost < best - 1e-9) { best = cost; splits = rsp; }
+    }
+  } else {
+    // aim at ~2 waves of 148 CTAs and pick the candidate that fills its last wave best
+    const int centre = ceil_div(148 * 2, out_tiles);
+    double best_fill = -1.0;
+    for (int sp = (centre > 3 ? centre - 2 : 1); sp <= centre + 2; ++sp) {
+      if (sp > max_splits) break;
+      const long ctas = (long)out_tiles * sp;
+      const long waves = (ctas + 147) / 148;
+      const double fill = (double)ctas / (double)(waves * 148);
+      if (fill > best_fill + 1e-9) { best_fill = fill; splits = sp; }
+    }
   }
   if (deterministic()) splits = 1;        // one CTA accumulates a whole output tile: one ordered addition per element
   P->chunks_per_split = ceil_div(P->nchunks, splits);
@@ -1695,7 +1712,8 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
 
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
   bool packed = false;
-  wgrad_finish(d, &P, out_tiles, &packed);
+  // (the 32-channel stem layers are HBM bound and want the bytes in flight of ~2 waves: 0.84 -> 0.93 ms with the cost model)
+  wgrad_finish(d, &P, out_tiles, &packed, CB == 64 ? P.tpc * NS : 0);
   const long grid = (long)out_tiles * P.splits;
   BVAE_REQUIRE(grid > 0 && grid < (1l << 31), BVAE_ERR_SHAPE, "wgrad_tc: grid too large");
   if (CB == 32) rc = NS == 64 ? launch_wgrad<32, 64, 2>(P, (int)grid, stream) : launch_wgrad<32, 32, 2>(P, (int)grid, stream);
