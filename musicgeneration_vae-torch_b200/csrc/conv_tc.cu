@@ -60,6 +60,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 // shared -> global tiled store (bulk async group); out-of-bounds elements of the box are clipped
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -804,6 +810,7 @@ struct alignas(64) WgradTcParams {
   int a_atoms;                      // 64-channel atoms of the anchor tile actually loaded (1 or 2)
   int ra_tiles, rs_tiles;
   int mc;                           // 2: launched as 2-CTA clusters that share the shifted tile (TMA multicast); else 1
+  int wt;                           // 1: "wide TMA" -- amap / smap are 5-D {64 ch, W, H, N, channel block} maps, one request per operand
   int Ca, Cs;
   float* dw;                        // destination of the reduction (parameter gradient or packed scratch)
   long long s_ra, s_t;              // element strides of the anchor channel / the tap; the shifted channel stride is
@@ -815,7 +822,14 @@ struct alignas(64) WgradTcParams {
 
 // CB = channels per swizzle atom (64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B); NS = shifted-channel tile (multiple of
 // CB, <= 256); KP = 64 pixel rows per stage
-template <int CB, int NS, int STAGES, bool MC = false>
+// WT ("wide TMA", 64-channel atoms, boxes of a multiple of 16 pixel rows): ncu on 512->512 3x3 at 6x4 x 512 bars showed the
+// MMA warp waiting for data 45 % of the K loop at 33 % L2 and 5 % DRAM utilisation -- ten TMA requests of 6-8 KB per 64-pixel
+// stage (2 anchor atoms + 2 taps x 4 shifted atoms) against two requests per stage in conv_tc2, i.e. the request rate, not the
+// bytes, is what the two-stage ring cannot hide.  With the channel axis split as a FIFTH tensor-map dimension {64 ch, W, H, N,
+// C/64} a box {64, bw, bh, bn, atoms} lands as `atoms` consecutive [rows][64 ch] swizzled tiles: ONE request per operand and
+// tap (3 per stage instead of 10).  The tiles are packed (rows_box * 128 B apart, the descriptors' leading-dimension offset),
+// every row of every tile is rewritten by each request (out-of-bounds pixels arrive as zeros), so the ring needs no zeroing.
+template <int CB, int NS, int STAGES, bool MC = false, bool WT = false>
 __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
   constexpr int KP = 64;
   constexpr int ROW_BYTES = CB * 2;
@@ -856,8 +870,11 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   const int rows_box = p.bn * p.bh * p.bw;             // <= 64, the rest of each atom stays zero
 
   // zero the whole pipeline buffer once: rows a box never writes must contribute exactly 0 to the contraction
-  for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
+  if (!WT) {
+    for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
+  const uint32_t atom_stride = WT ? (uint32_t)(rows_box * ROW_BYTES) : (uint32_t)ATOM_BYTES;   // distance between channel atoms
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, mc ? 2 : 1); }
     mbar_init(tmem_full, 1);
@@ -884,9 +901,17 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       mbar_wait(empty_bar + s, ph ^ 1u);
       mbar_expect_tx(full_bar + s, tx);
       uint8_t* st = smem + s * STAGE_BYTES;
-      for (int a = 0; a < p.a_atoms; ++a)
+      if (WT) {
+        tma_load_5d(st, &p.amap, full_bar + s, 0, cw, ch, cn, ra_tile * A_ATOMS);
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t;
+          tma_load_5d(st + (A_ATOMS + t * S_ATOMS) * atom_stride, &p.smap[p.tap_view[tap]], full_bar + s, 0,
+                      cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn, rs_tile * S_ATOMS);
+        }
+      }
+      for (int a = 0; !WT && a < p.a_atoms; ++a)
         tma_load_4d(st + a * ATOM_BYTES, &p.amap, full_bar + s, (ra_tile * A_ATOMS + a) * CB, cw, ch, cn);
-      for (int t = 0; t < ntap; ++t) {
+      for (int t = 0; !WT && t < ntap; ++t) {
         const int tap = tap0 + t;
         const CUtensorMap* sm = &p.smap[p.tap_view[tap]];
         for (int a = 0; a < S_ATOMS; ++a) {
@@ -911,14 +936,14 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
       const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
       if (elect_one()) {
         // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
-        const uint64_t adesc = make_sdesc(st, ATOM_BYTES, SBO, LAYOUT);
+        const uint64_t adesc = make_sdesc(st, atom_stride, SBO, LAYOUT);
         // the atoms of consecutive taps are contiguous in smem and their accumulators are contiguous TMEM columns, so
         // up to 256/NS taps go into ONE instruction with N = taps*NS (A is read once for all of them)
         constexpr int TG = 256 / NS;
         for (int t = 0; t < ntap; t += TG) {
           const int tg = min(TG, ntap - t);
           const uint32_t idesc = make_idesc(128, tg * NS, 1, 1);
-          const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * ATOM_BYTES, ATOM_BYTES, SBO, LAYOUT);
+          const uint64_t bdesc = make_sdesc(st + (A_ATOMS + t * S_ATOMS) * atom_stride, atom_stride, SBO, LAYOUT);
           if (ksteps == 4) {
             umma_f16_steps<4, (int)KSTEP>(tmem_base + (uint32_t)(t * NS), adesc, bdesc, idesc, it ? 1u : 0u);
           } else {
@@ -1179,6 +1204,24 @@ static int make_view_map(CUtensorMap* m, const void* base, int C, int Wv, int Hv
   return BVAE_OK;
 }
 
+// 5-D map over the same view with the channel axis split into 64-channel blocks: dims {64, Wv, Hv, N, C/64}; a box
+// {64, bw, bh, bn, blocks} lands as `blocks` consecutive [bn*bh*bw rows][64 ch] tiles (wgrad_tc_kernel, WT)
+static int make_view_map5(CUtensorMap* m, const void* base, int C, int Wv, int Hv, int N, int64_t sw_elems, int64_t sh_elems,
+                          int64_t sn_elems, int bw, int bh, int bn, int blocks) {
+  EncodeTiledFn enc = get_encode();
+  BVAE_REQUIRE(enc, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[5] = {64, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)N, (cuuint64_t)(C / 64)};
+  cuuint64_t strides[4] = {(cuuint64_t)sw_elems * 2, (cuuint64_t)sh_elems * 2, (cuuint64_t)sn_elems * 2, 128};
+  cuuint32_t box[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn, (cuuint32_t)blocks};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BVAE_REQUIRE(r == CUDA_SUCCESS, BVAE_ERR_CUDA, "cuTensorMapEncodeTiled(5d) failed: %d (C %d dims %d,%d,%d box %d,%d,%d,%d)",
+               (int)r, C, Wv, Hv, N, bw, bh, bn, blocks);
+  return BVAE_OK;
+}
+
 // output view {C, Wv, Hv, N} (strides in elements), box {128 B of channels (32 floats / 64 bf16), bw, bh, bn}, 128B swizzle
 static int make_out_map(CUtensorMap* m, const void* base, bool f32, int C, int Wv, int Hv, int N, int64_t sw_elems,
                         int64_t sh_elems, int64_t sn_elems, int bw, int bh, int bn) {
@@ -1240,8 +1283,25 @@ static void pick_box(int N, int QH, int QW, int cap, int* bw_, int* bh_, int* bn
       if (bn > N) bn = N;
       if (bn > 256) bn = 256;
       if (bn < 1) continue;
+      if (cap == 64) {
+        // weight-gradient K chunks cost one MMA per 16 pixel rows; boxes of a multiple of 16 rows qualify for the one-request-
+        // per-operand loads of wgrad_tc_kernel<.., WT> and win ties (also try fewer samples per box to get there)
+        for (int pass = 0; pass < 2; ++pass) {
+          int b2 = bn;
+          if (pass == 1) {
+            while (b2 > 1 && (bw * bh * b2) % 16 != 0) --b2;
+            if (b2 == bn || (bw * bh * b2) % 16 != 0) break;
+          }
+          const int rows = bw * bh * b2;
+          const long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, b2) * ceil_div(rows, 16);
+          const bool m16 = rows % 16 == 0, bm16 = (bbw * bbh * bbn) % 16 == 0;
+          if (best < 0 || tiles < best || (tiles == best && ((m16 && !bm16) || (m16 == bm16 && (bw > bbw || (bw == bbw && b2 < bbn)))))) {
+            best = tiles; bbw = bw; bbh = bh; bbn = b2;
+          }
+        }
+        continue;
+      }
       long tiles = (long)ceil_div(QW, bw) * ceil_div(QH, bh) * ceil_div(N, bn);
-      if (cap == 64) tiles *= ceil_div(bw * bh * bn, 16);      // weight-gradient K chunks cost one MMA per 16 pixel rows
       // ties: wider rows first, then boxes that stay inside one sample (needed by the fused statistics)
       if (best < 0 || tiles < best || (tiles == best && (bw > bbw || (bw == bbw && bn < bbn)))) { best = tiles; bbw = bw; bbh = bh; bbn = bn; }
     }
@@ -1520,6 +1580,19 @@ static int launch_wgrad_mc(const WgradTcParams& P, int grid, cudaStream_t stream
   return check_launch("wgrad_tc");
 }
 
+template <int NS, int STAGES>
+static int launch_wgrad_wt(const WgradTcParams& P, int grid, cudaStream_t stream, int smem) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<64, NS, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    attr_done = true;
+  }
+  wgrad_tc_kernel<64, NS, STAGES, false, true><<<grid, 128, smem, stream>>>(P);
+  note_kernel("wgrad_tc_kernel<64,%d,%d>+wt", NS, STAGES);
+  return check_launch("wgrad_tc");
+}
+
 template <int CB, int NS, int STAGES>
 static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
   constexpr int max_tpc = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
@@ -1532,6 +1605,9 @@ static int launch_wgrad(const WgradTcParams& P, int grid, cudaStream_t stream) {
   }
   if (P.mc == 2) {
     if constexpr (CB == 64 && NS >= 128) return launch_wgrad_mc<CB, NS, STAGES>(P, grid, stream, smem);
+  }
+  if (P.wt == 1) {
+    if constexpr (CB == 64) return launch_wgrad_wt<NS, STAGES>(P, grid, stream, smem);
   }
   wgrad_tc_kernel<CB, NS, STAGES><<<grid, 128, smem, stream>>>(P);
   note_kernel("wgrad_tc_kernel<%d,%d,%d>", CB, NS, STAGES);
@@ -1680,15 +1756,24 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
     if (rc || done) return rc;
   }
   pick_box(d->N, d->AH, d->AW, 64, &P.bw, &P.bh, &P.bn);
-  int rc = make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
-                         (int64_t)d->AH * d->AW * d->a_pitch, CB, P.bw, P.bh, P.bn, sw128);
+  const int mc_req = (option("BVAE_WGRAD_MC", 0) != 0 && CB == 64 && NS >= 128 && ceil_div(d->Ca, 128) % 2 == 0) ? 2 : 1;
+  // BVAE_WGRAD_WIDE_TMA (default 1): one 5-D TMA request per operand and tap (see wgrad_tc_kernel, WT)
+  const bool wt = CB == 64 && (P.bw * P.bh * P.bn) % 16 == 0 && mc_req == 1 && option("BVAE_WGRAD_WIDE_TMA", 1) != 0;
+  P.wt = wt ? 1 : 0;
+  const int a_atoms = d->Ca >= 128 ? 128 / CB : d->Ca / CB;
+  int rc = wt ? make_view_map5(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
+                               (int64_t)d->AH * d->AW * d->a_pitch, P.bw, P.bh, P.bn, a_atoms)
+              : make_view_map(&P.amap, d->a, d->Ca, d->AW, d->AH, d->N, d->a_pitch, (int64_t)d->AW * d->a_pitch,
+                              (int64_t)d->AH * d->AW * d->a_pitch, CB, P.bw, P.bh, P.bn, sw128);
   if (rc) return rc;
   for (int v = 0; v < vp.nviews; ++v) {
     const int Hv = ceil_div(d->SH - vp.fy[v], d->sy), Wv = ceil_div(d->SW - vp.fx[v], d->sx);
     BVAE_REQUIRE(Hv > 0 && Wv > 0, BVAE_ERR_SHAPE, "wgrad_tc: empty view");
     const bf16* base = (const bf16*)d->s + ((int64_t)vp.fy[v] * d->SW + vp.fx[v]) * d->s_pitch;
-    rc = make_view_map(&P.smap[v], base, d->Cs, Wv, Hv, d->N, (int64_t)d->sx * d->s_pitch,
-                       (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, CB, P.bw, P.bh, P.bn, sw128);
+    rc = wt ? make_view_map5(&P.smap[v], base, d->Cs, Wv, Hv, d->N, (int64_t)d->sx * d->s_pitch,
+                             (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, P.bw, P.bh, P.bn, NS / 64)
+            : make_view_map(&P.smap[v], base, d->Cs, Wv, Hv, d->N, (int64_t)d->sx * d->s_pitch,
+                            (int64_t)d->sy * d->SW * d->s_pitch, (int64_t)d->SH * d->SW * d->s_pitch, CB, P.bw, P.bh, P.bn, sw128);
     if (rc) return rc;
   }
   for (int t = 0; t < d->ntaps; ++t) {
@@ -1705,10 +1790,9 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   P.Ca = d->Ca; P.Cs = d->Cs;
   // BVAE_WGRAD_MC=1 (opt-in): pairs of anchor tiles as 2-CTA clusters with the shifted tile multicast (>= 256 anchor
   // channels).  Correct (parity-tested) but not faster -- 23 launches of <64,256,2> per step 3.98 ms at 0.47 of the tensor peak
-  // against 3.84 ms at 0.50 without: halving the L2 reads does not help because every SM still RECEIVES 80 KB per 64-pixel
-  // chunk; what bounds these layers is the per-SM operand inflow, which only a cta_group::2 MMA (each SM holds half of the
-  // shifted tile) would halve.
-  P.mc = (option("BVAE_WGRAD_MC", 0) != 0 && CB == 64 && NS >= 128 && P.ra_tiles % 2 == 0) ? 2 : 1;
+  // against 3.84 ms at 0.50 without: L2 is at a third of its throughput on these layers (ncu), so halving the L2 reads buys
+  // nothing, and the pair's lock-step (a stage is refilled only when both CTAs have consumed it) costs a little.
+  P.mc = mc_req;
 
   const int out_tiles = P.ra_tiles * P.rs_tiles * P.tap_groups;
   bool packed = false;
