@@ -248,7 +248,7 @@ def torch_eager_gpu(dev, bars, steps=3):
 def ncu_traffic_table():
     """per-launch DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) from `ncu --set full` captures, kept under
     profiles/ (this round's file first); keyed by kernel instance"""
-    for name in ("traffic_r2.json", "traffic_r1.json"):
+    for name in ("traffic_r3.json", "traffic_r2.json", "traffic_r1.json"):
         p = os.path.join(ROOT, "profiles", name)
         if os.path.exists(p):
             try:

@@ -3390,6 +3390,8 @@ static bool nbs_enabled(const bvae_nb_desc* d) {
   if (option("BVAE_NB_SMALL", 1) == 0 || option("BVAE_NB_MODE", 0) != 0 || option("BVAE_NB_MLP", 2) != 2) return false;
   const int HW = d->H * d->W, C = d->C;
   if (C < 32 || C > 1024 || (C & (C - 1)) != 0) return false;
+  // static + dynamic shared memory of the largest kernel (nbs_bwd1: 12.2 KB static) must stay inside the default 48 KB
+  if (nbs_fwd_smem(HW, C) > 44 * 1024 || nbs_bwd1_smem(HW, C) > 35 * 1024) return false;
   if (HW <= 128) return C >= 256;
   int max_hw = option("BVAE_NB_SMALL_HW", 512);
   if (max_hw > NBS_MAX_HW) max_hw = NBS_MAX_HW;

