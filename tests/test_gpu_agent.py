@@ -28,7 +28,10 @@ def test_bargen_trains_checkpoints_and_samples(tmp_path):
     # Eight epochs over the same 8 bars (2 optimiser steps each).  The reference's training loss is BCE + 0.005 x (number of
     # notes the thresholded output misses) and the second term is not differentiable -- it RISES while the BCE falls (a model
     # that learns "mostly silence" misses every note: measured 5.27 -> 5.96 in total) -- so the criterion is the
-    # reconstruction BCE of the training bars in eval mode, before vs after: it must come down by more than a quarter.
+    # reconstruction BCE of the training bars in eval mode, before vs after.  From the reference's N(-1,1) initialisation
+    # (not reproducible through torch.manual_seed: the eval BCE before training already ranges 1.45 .. 1.93) the drop after 8
+    # epochs was measured at 21 % .. 53 % over 12 runs on the B200 (profiles/r3/agent_test_seed_scan.jsonl; the slow runs
+    # plateau at 0.77 and stay there for 16 epochs): the test asks for more than 10 %, a quarter failed one run in four.
     Loss = pkg("graph.loss.bar_loss").Loss
     dev = agent.device
     full = tuple(t.to(dev) for t in agent.make_batch([ds[i] for i in range(4)]))
@@ -48,7 +51,7 @@ def test_bargen_trains_checkpoints_and_samples(tmp_path):
         losses.append(agent.train_epoch())
     b1 = bce()
     report(test="bargen", epoch_losses=losses, bce_before=b0, bce_after=b1)
-    assert all(l == l for l in losses) and b1 < 0.75 * b0, (b0, b1, losses)
+    assert all(l == l for l in losses) and b1 < 0.9 * b0, (b0, b1, losses)
     agent.save_checkpoint(Cfg.checkpoint_file, 1)
     ck = torch.load(os.path.join(str(tmp_path), Cfg.checkpoint_dir, "checkpoint.pth.tar"), weights_only=False)
     keys = list(ck["generator_state_dict"].keys())
