@@ -1,4 +1,4 @@
-"""Small-map norm sites (H*W <= 128, 256..1024 channels): forward / backward time of one site with the wide nbs_*
+"""Norm sites with <= 1440 pixels: forward / backward time of one site with the per-sample nbs_*
 kernels (BVAE_NB_SMALL=1 with BVAE_NB_SMALL_HW=1440: every site here takes them) against the round-2 kernels
 (BVAE_NB_SMALL=0: nb_cl_* up to 128 pixels, the tiled nb_* / nbf_* sweeps above), CUDA events, one JSON line per (site, mode).
 usage: bench_nb_small.py [B [CxHxW ...]]   (B = bars per step)"""
