@@ -811,6 +811,7 @@ struct alignas(64) WgradTcParams {
   int ra_tiles, rs_tiles;
   int mc;                           // 2: launched as 2-CTA clusters that share the shifted tile (TMA multicast); else 1
   int wt;                           // 1: "wide TMA" -- amap / smap are 5-D {64 ch, W, H, N, channel block} maps, one request per operand
+  int wt_stages, wt_stage_bytes;    // WT: ring depth (2..4) and bytes per stage = atoms * rows_box * 128 (packed atoms)
   int Ca, Cs;
   float* dw;                        // destination of the reduction (parameter gradient or packed scratch)
   long long s_ra, s_t;              // element strides of the anchor channel / the tap; the shifted channel stride is
@@ -842,11 +843,18 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   constexpr uint32_t SBO = 8 * ROW_BYTES;              // 8 pixel rows
   constexpr uint32_t KSTEP = (16 * ROW_BYTES) >> 4;    // 16 pixel rows per MMA, in encoded (>>4) address units
 
+  // WT: the packed atoms make a stage atoms * rows_box * 128 bytes, so boxes of 48 / 32 pixel rows (the 6x4, 3x2, 12x2 maps of
+  // the 512 / 1024-channel layers) fit a THIRD / FOURTH ring stage into the same shared memory: the ring depth is a launch
+  // parameter there and the barriers sit in front of the ring.
+  constexpr int MAXST = WT ? 4 : STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  const int nst = WT ? p.wt_stages : STAGES;
+  const uint32_t stage_bytes = WT ? (uint32_t)p.wt_stage_bytes : (uint32_t)STAGE_BYTES;
+  uint8_t* ring = WT ? smem + 1024 : smem;
+  uint64_t* full_bar = WT ? (uint64_t*)smem : (uint64_t*)(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + MAXST;
+  uint64_t* tmem_full = empty_bar + MAXST;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -876,7 +884,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
   }
   const uint32_t atom_stride = WT ? (uint32_t)(rows_box * ROW_BYTES) : (uint32_t)ATOM_BYTES;   // distance between channel atoms
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, mc ? 2 : 1); }
+    for (int s = 0; s < MAXST; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, mc ? 2 : 1); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
     tma_prefetch_desc(&p.amap);
@@ -890,17 +898,16 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
 
   if (warp == 0 && lane == 0) {
     const uint32_t tx = (uint32_t)(rows_box * ROW_BYTES * (p.a_atoms + ntap * S_ATOMS));   // bytes landing HERE (own + peer's loads)
-    int it = 0;
-    for (int ck = ck0; ck < ck1; ++ck, ++it) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ck = ck0; ck < ck1; ++ck) {
       int q = ck;
       const int cw = (q % p.chunks_w) * p.bw; q /= p.chunks_w;
       const int ch = (q % p.chunks_h) * p.bh;
       const int cn = (q / p.chunks_h) * p.bn;
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(empty_bar + s, ph ^ 1u);
       mbar_expect_tx(full_bar + s, tx);
-      uint8_t* st = smem + s * STAGE_BYTES;
+      uint8_t* st = ring + (uint32_t)s * stage_bytes;
       if (WT) {
         tma_load_5d(st, &p.amap, full_bar + s, 0, cw, ch, cn, ra_tile * A_ATOMS);
         for (int t = 0; t < ntap; ++t) {
@@ -923,17 +930,17 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
                            cw + p.tap_ex[tap], ch + p.tap_ey[tap], cn, (uint16_t)3);
         }
       }
+      if (++s == nst) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // the whole warp walks the loop, one elected lane issues (see elect_one)
     const int ksteps = (rows_box + 15) / 16;
-    int it = 0;
+    int it = 0, s = 0;
+    uint32_t ph = 0;
     for (int ck = ck0; ck < ck1; ++ck, ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full_bar + s, ph);
       tc_fence_after();
-      const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
+      const uint32_t st = smem_u32(ring + (uint32_t)s * stage_bytes);
       if (elect_one()) {
         // MN-major: LBO = distance between CB-channel atoms, SBO = 8 pixel rows
         const uint64_t adesc = make_sdesc(st, atom_stride, SBO, LAYOUT);
@@ -955,6 +962,7 @@ __global__ void __launch_bounds__(128) wgrad_tc_kernel(const __grid_constant__ W
         else umma_commit(empty_bar + s);
       }
       __syncwarp();
+      if (++s == nst) { s = 0; ph ^= 1u; }
     }
     if (elect_one()) umma_commit(tmem_full);
     __syncwarp();
@@ -1580,16 +1588,19 @@ static int launch_wgrad_mc(const WgradTcParams& P, int grid, cudaStream_t stream
   return check_launch("wgrad_tc");
 }
 
+constexpr int WT_RING_BUDGET = 200 * 1024;     // shared memory the WT ring may take (+ 2 KB of alignment / barriers)
 template <int NS, int STAGES>
-static int launch_wgrad_wt(const WgradTcParams& P, int grid, cudaStream_t stream, int smem) {
+static int launch_wgrad_wt(const WgradTcParams& P, int grid, cudaStream_t stream, int /*smem of the fixed two-stage ring*/) {
+  const int smem = 1024 + 1024 + P.wt_stages * P.wt_stage_bytes;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<64, NS, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute(%d) failed: %s", smem, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<64, NS, STAGES, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WT_RING_BUDGET + 2048);
+    BVAE_REQUIRE(e == cudaSuccess, BVAE_ERR_CUDA, "wgrad_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_done = true;
   }
   wgrad_tc_kernel<64, NS, STAGES, false, true><<<grid, 128, smem, stream>>>(P);
-  note_kernel("wgrad_tc_kernel<64,%d,%d>+wt", NS, STAGES);
+  note_kernel("wgrad_tc_kernel<64,%d,%d>+wt", NS, P.wt_stages);
   return check_launch("wgrad_tc");
 }
 
@@ -1781,6 +1792,14 @@ int wgrad_tc_launch(const bvae_wgrad_desc* d, cudaStream_t stream) {
   }
   P.ntaps = d->ntaps; P.T = d->T;
   const int max_tpc = (512 / NS) > BVAE_MAX_TAPS ? BVAE_MAX_TAPS : (512 / NS);
+  if (wt) {
+    // BVAE_WGRAD_STAGES (default 4): cap on the ring depth; 2 = the fixed ring of the other variants
+    P.wt_stage_bytes = (128 / 64 + max_tpc * (NS / 64)) * (P.bw * P.bh * P.bn) * 128;
+    int nst = WT_RING_BUDGET / P.wt_stage_bytes, cap = option("BVAE_WGRAD_STAGES", 4);
+    if (cap < 2) cap = 2;
+    if (cap > 4) cap = 4;
+    P.wt_stages = nst > cap ? cap : (nst < 2 ? 2 : nst);
+  }
   P.tap_groups = ceil_div(d->ntaps, max_tpc);
   P.tpc = ceil_div(d->ntaps, P.tap_groups);
   P.chunks_w = ceil_div(d->AW, P.bw); P.chunks_h = ceil_div(d->AH, P.bh); P.chunks_n = ceil_div(d->N, P.bn);

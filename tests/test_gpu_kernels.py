@@ -165,7 +165,7 @@ def test_norm_block(C, H, W, mode, raw):
 
 # ---- every kernel-variant switch that ships (include/barvae.h: bvae_set_option) gets the same parity treatment ----------
 CONV_VARIANTS = [("BVAE_CONV_V1", 1), ("BVAE_CONV_TMA_STORE", 0), ("BVAE_CONV_TMA_STORE", 2), ("BVAE_CONV_HALO", 0),
-                 ("BVAE_WGRAD_HALO", 0), ("BVAE_WGRAD_MC", 1), ("BVAE_WGRAD_SPLITS", 0), ("BVAE_WGRAD_WIDE_TMA", 0)]
+                 ("BVAE_WGRAD_HALO", 0), ("BVAE_WGRAD_MC", 1), ("BVAE_WGRAD_SPLITS", 0), ("BVAE_WGRAD_WIDE_TMA", 0), ("BVAE_WGRAD_STAGES", 2)]
 
 
 @pytest.mark.parametrize("opt", CONV_VARIANTS, ids=lambda o: "%s=%d" % o)
@@ -181,7 +181,7 @@ def test_kernel_variants_contractions(opt):
             _run_gemm_layer(spec, "tc", 3)
         for spec in BIG_LAYERS[-6:]:                         # the 64 / 32-channel layers incl. all halo-mode shapes
             _run_gemm_layer(spec[:9], "tc", spec[9])
-        if opt[0] in ("BVAE_WGRAD_MC", "BVAE_WGRAD_SPLITS", "BVAE_WGRAD_WIDE_TMA"):                        # >= 256 anchor channels: where the 2-CTA multicast pairs run
+        if opt[0] in ("BVAE_WGRAD_MC", "BVAE_WGRAD_SPLITS", "BVAE_WGRAD_WIDE_TMA", "BVAE_WGRAD_STAGES"):                        # >= 256 anchor channels: where the 2-CTA multicast pairs run
             for spec in BIG_LAYERS[:-6]:
                 _run_gemm_layer(spec[:9], "tc", spec[9])
     assert lib.load().bvae_get_option(opt[0].encode(), -7) == -7
